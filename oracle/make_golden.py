@@ -1,0 +1,402 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (the only place /root/reference exists):
+
+    TZ=UTC python oracle/make_golden.py            # all cases
+    TZ=UTC python oracle/make_golden.py c0_bangbang_50
+
+For each case: `random.seed(seed)`, construct + `reset()` the reference env, snapshot the
+population, then step it with a recorded action stream while recording every random draw
+it consumes (outdoor-temperature gauss, perlin value, interpolation sample ids,
+message-drop uniforms, random_sample neighbour sets) and its outputs.  The fixtures are
+what `tests/test_oracle.py` pins the numpy oracle against and what the `-m gpu` parity
+tests replay through the CUDA path.
+
+The interpolation table `mergedGridSearchResultFinal.npy` is a missing large blob in the
+reference (`.MISSING_LARGE_BLOBS`), so interpolation cases use the synthetic table
+`default_rng(0).uniform(0, 6000, 4199040)`, regenerated on the fly.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import random
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_stubs  # noqa: E402
+import mdr_oracle as orc  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(HERE), "tests", "golden")
+TABLE_SIZE = 4199040
+
+
+def synthetic_table():
+    return np.random.default_rng(0).uniform(0, 6000, TABLE_SIZE)
+
+
+def relevant_config(cfg):
+    keys = ("default_house_prop", "noise_house_prop", "noise_house_prop_test", "default_hvac_prop",
+            "noise_hvac_prop", "noise_hvac_prop_test", "default_env_prop")
+    return {k: copy.deepcopy(cfg[k]) for k in keys}
+
+
+def config_to_json(cfg) -> str:
+    return json.dumps(relevant_config(cfg), sort_keys=False)
+
+
+def snapshot(env):
+    """Population + per-env scalars of a freshly reset reference env -> dict of arrays."""
+    houses = [env.cluster.houses[i] for i in env.agent_ids]
+    g = env.power_grid
+    f = lambda fn: np.array([fn(h) for h in houses], dtype=np.float64)
+    i = lambda fn: np.array([fn(h) for h in houses], dtype=np.int64)
+    snap = {
+        "ua": f(lambda h: h.Ua), "cm": f(lambda h: h.Cm), "ca": f(lambda h: h.Ca), "hm": f(lambda h: h.Hm),
+        "cap": f(lambda h: h.hvac.cooling_capacity), "cop": f(lambda h: h.hvac.COP),
+        "latent": f(lambda h: h.hvac.latent_cooling_fraction),
+        "target": f(lambda h: h.target_temp), "deadband": f(lambda h: h.deadband),
+        "t_air": f(lambda h: h.current_temp), "t_mass": f(lambda h: h.current_mass_temp),
+        "lockout_dur": i(lambda h: h.hvac.lockout_duration), "sso": i(lambda h: h.hvac.seconds_since_off),
+        "on": i(lambda h: bool(h.hvac.turned_on)), "lockout": i(lambda h: bool(h.hvac.lockout)),
+        "t_epoch": np.int64(orc.from_datetime(env.datetime)),
+        "phase": np.float64(env.cluster.phase),
+        "od_temp": np.float64(env.cluster.current_OD_temp),
+        "artificial_ratio": np.float64(g.artificial_ratio),
+        "max_power": np.float64(env.cluster.max_power),
+        "base_power": np.float64(g.base_power),
+        "time_since_interp": np.int64(getattr(g, "time_since_last_interp", 0)),
+        "signal": np.float64(g.current_signal),
+        "cluster_power": np.float64(env.cluster.cluster_hvac_power),
+        "solar_gain": np.float64(0.0),
+    }
+    return snap
+
+
+class Recorder:
+    """Wraps the draw sources the reference consumes while stepping."""
+
+    def __init__(self, env, np_seed):
+        self.gauss, self.choices, self.samples, self.rands, self.perlin = [], [], [], [], []
+        self._g, self._c, self._s = random.gauss, random.choices, random.sample
+        self._r = np.random.rand
+        self.rng = np.random.default_rng(np_seed)
+        rec = self
+
+        def gauss(mu, sigma):
+            v = rec._g(mu, sigma)
+            rec.gauss.append(v)
+            return v
+
+        def choices(pop, *a, **k):
+            v = rec._c(pop, *a, **k)
+            rec.choices.append(list(v))
+            return v
+
+        def sample(pop, k):
+            v = rec._s(pop, k=k)
+            rec.samples.append(list(v))
+            return v
+
+        def rand(*a):
+            v = rec.rng.random()
+            rec.rands.append(v)
+            return v
+
+        random.gauss, random.choices, random.sample = gauss, choices, sample
+        np.random.rand = rand
+        if hasattr(env.power_grid, "perlin"):
+            p = env.power_grid.perlin
+            orig = p.calculate_noise
+
+            def calc(x):
+                v = orig(x)
+                rec.perlin.append(v)
+                return v
+
+            p.calculate_noise = calc
+
+    def drain(self):
+        out = (self.gauss, self.choices, self.samples, self.rands, self.perlin)
+        self.gauss, self.choices, self.samples, self.rands, self.perlin = [], [], [], [], []
+        return out
+
+    def close(self):
+        random.gauss, random.choices, random.sample = self._g, self._c, self._s
+        np.random.rand = self._r
+
+
+def set_path(cfg, path, value):
+    d = cfg
+    for k in path[:-1]:
+        d = d[k]
+    d[path[-1]] = value
+
+
+CASES = {}
+
+
+def case(name):
+    def deco(fn):
+        CASES[name] = fn
+        return fn
+    return deco
+
+
+def base_config(cfg, n, **kw):
+    c = copy.deepcopy(cfg)
+    ep = c["default_env_prop"]
+    ep["cluster_prop"]["nb_agents"] = n
+    ep["power_grid_prop"]["base_power_mode"] = kw.get("base_power_mode", "constant")
+    c["default_house_prop"]["solar_gain_bool"] = kw.get("solar", False)
+    return c
+
+
+@case("c0_bangbang_50")
+def _c0(cfg):
+    """BASELINE config 0: main-deploy defaults (50 houses, solar gain off, perlin signal),
+    bang-bang actions; constant base power because the table blob is missing."""
+    c = base_config(cfg, 50)
+    return dict(config=c, seed=1, steps=120, policy="bangbang", check="all", obs_steps=[0, 1, 2, 60, 119])
+
+
+@case("hetero_37_solar_lockout")
+def _hetero(cfg):
+    c = base_config(cfg, 37, solar=True)
+    c["noise_house_prop"]["noise_mode"] = "big_noise"
+    c["noise_hvac_prop"]["noise_mode"] = "big_noise"
+    c["default_hvac_prop"]["lockout_noise"] = 8
+    c["default_house_prop"]["deadband"] = 1.0
+    ep = c["default_env_prop"]
+    ep["start_datetime"] = "2021-06-15 07:20:00"
+    ep["start_datetime_mode"] = "fixed"
+    ep["power_grid_prop"]["signal_mode"] = "sinusoidals"
+    return dict(config=c, seed=7, steps=300, policy="random", check="all", obs_steps=[0, 149, 150, 151, 299])
+
+
+@case("interp_150_sinus_solar")
+def _interp150(cfg):
+    c = base_config(cfg, 150, solar=True, base_power_mode="interpolation")
+    c["noise_house_prop"]["noise_mode"] = "small_noise"
+    c["noise_hvac_prop"]["noise_mode"] = "small_noise"
+    ep = c["default_env_prop"]
+    ep["start_datetime"] = "2021-03-20 10:00:00"
+    ep["start_datetime_mode"] = "fixed"
+    ep["power_grid_prop"]["signal_mode"] = "sinusoidals"
+    return dict(config=c, seed=11, steps=160, policy="random", check=[0, 1, 74, 75, 76, 149, 150, 159], obs_steps=[0, 75, 159])
+
+
+@case("interp_40_perlin")
+def _interp40(cfg):
+    c = base_config(cfg, 40, base_power_mode="interpolation")
+    c["noise_house_prop"]["noise_mode"] = "big_noise"
+    ep = c["default_env_prop"]
+    ep["power_grid_prop"]["artificial_signal_ratio_range"] = 3
+    return dict(config=c, seed=3, steps=160, policy="bangbang", check=[0, 1, 74, 75, 149, 150, 159], obs_steps=[0, 75, 159])
+
+
+def _modes(cfg, n, comm_mode, penalty, signal_mode, seed, defect=0.0, all_flags=False, nb_comm=3):
+    c = base_config(cfg, n, solar=all_flags)
+    ep = c["default_env_prop"]
+    ep["cluster_prop"]["agents_comm_mode"] = comm_mode
+    ep["cluster_prop"]["nb_agents_comm"] = nb_comm
+    ep["cluster_prop"]["comm_defect_prob"] = defect
+    ep["reward_prop"]["temp_penalty_mode"] = penalty
+    ep["power_grid_prop"]["signal_mode"] = signal_mode
+    c["noise_house_prop"]["noise_mode"] = "small_noise"
+    if all_flags:
+        for k in ep["state_properties"]:
+            ep["state_properties"][k] = True
+        for k in ep["message_properties"]:
+            ep["message_properties"][k] = True
+        c["noise_hvac_prop"]["noise_mode"] = "small_noise"
+        ep["start_datetime"] = "2021-12-31 23:58:00"   # rolls over the year boundary
+        ep["start_datetime_mode"] = "fixed"
+    return dict(config=c, seed=seed, steps=40, policy="random", check="all", obs_steps="all")
+
+
+@case("modes_12_closed_common_l2_steps")
+def _m1(cfg):
+    return _modes(cfg, 12, "closed_groups", "common_L2", "regular_steps", 21)
+
+
+@case("modes_10_closed_mixture_flat")
+def _m2(cfg):
+    d = _modes(cfg, 10, "closed_groups", "mixture", "flat", 22)
+    d["config"]["default_env_prop"]["reward_prop"]["temp_penalty_parameters"]["mixture"]["alpha_common_max"] = 0.5
+    return d
+
+
+@case("modes_12_allflags_defect_max")
+def _m3(cfg):
+    return _modes(cfg, 12, "neighbours", "common_max", "perlin", 23, defect=0.3, all_flags=True, nb_comm=10)
+
+
+@case("n2d_25")
+def _m4(cfg):
+    return _modes(cfg, 25, "neighbours_2D", "individual_L2", "sinusoidals", 24)
+
+
+@case("random_fixed_20")
+def _m5(cfg):
+    return _modes(cfg, 20, "random_fixed", "individual_L2", "perlin", 25, nb_comm=4)
+
+
+@case("random_sample_15")
+def _m6(cfg):
+    return _modes(cfg, 15, "random_sample", "individual_L2", "flat", 26, nb_comm=4)
+
+
+@case("no_message_5_small")
+def _m7(cfg):
+    d = _modes(cfg, 5, "no_message", "individual_L2", "perlin", 27)
+    return d
+
+
+@case("tiny_3_comm_clipped")
+def _m8(cfg):
+    return _modes(cfg, 3, "neighbours", "individual_L2", "perlin", 28, nb_comm=10)
+
+
+@case("c1_1000_fp64")
+def _c1(cfg):
+    """BASELINE config 1: single env, 1000 houses, regulation signal (perlin on interpolated
+    base power), nb_agents_comm = 10."""
+    c = base_config(cfg, 1000, base_power_mode="interpolation")
+    return dict(config=c, seed=5, steps=80, policy="bangbang",
+                check=[0, 1, 2, 9, 19, 39, 59, 74, 75, 79], obs_steps=[0, 75])
+
+
+def run_case(name, Env, norm, cfg):
+    spec = CASES[name](cfg)
+    c = spec["config"]
+    gp = c["default_env_prop"]["power_grid_prop"]
+    tmp = None
+    if gp["base_power_mode"] == "interpolation":
+        tmp = tempfile.mkdtemp()
+        path = os.path.join(tmp, "table.npy")
+        np.save(path, synthetic_table())
+        ip = gp["base_power_parameters"]["interpolation"]
+        ip["path_datafile"] = path
+        ip["path_parameter_dict"] = os.path.join(ref_stubs.REFERENCE_ROOT, "monteCarlo", "interp_parameters_dict.json")
+        ip["path_dict_keys"] = os.path.join(ref_stubs.REFERENCE_ROOT, "monteCarlo", "interp_dict_keys.csv")
+    n = c["default_env_prop"]["cluster_prop"]["nb_agents"]
+    defect = c["default_env_prop"]["cluster_prop"]["comm_defect_prob"]
+    steps = spec["steps"]
+
+    random.seed(spec["seed"])
+    env = Env(c)
+    obs = env.reset()
+    rec = Recorder(env, np_seed=spec["seed"] + 1000)
+    try:
+        # reset() drew its message drops from the unseeded np.random: regenerate the initial
+        # observation under the recorder so that the drops are known
+        snap = snapshot(env)
+        comm_mode = c["default_env_prop"]["cluster_prop"]["agents_comm_mode"]
+        if comm_mode == "random_sample":
+            comm0 = None
+        else:
+            comm0 = np.array([env.cluster.agent_communicators[i] for i in env.agent_ids], dtype=np.int32).reshape(n, -1)
+        C = int(min(c["default_env_prop"]["cluster_prop"]["nb_agents_comm"], n - 1)) if comm_mode != "no_message" else 0
+        if comm0 is not None:
+            C = comm0.shape[1]
+        obs0_raw = env.cluster.make_cluster_obs_dict(env.datetime)
+        obs0_raw = env.merge_cluster_powergrid_obs(obs0_raw, env.power_grid.current_signal, env.cluster.cluster_hvac_power)
+        _, _, samples, rands, _ = rec.drain()
+        init_keep = (np.array(rands) > defect).astype(np.uint8).reshape(n, C) if rands else np.ones((n, C), np.uint8)
+        init_comm = np.array(samples, dtype=np.int32).reshape(n, C) if samples else None
+        obs0 = np.stack([norm(obs0_raw[i], c) for i in env.agent_ids])
+        obs = obs0_raw
+
+        prng = np.random.default_rng(spec["seed"] + 2000)
+        check = list(range(steps)) if spec["check"] == "all" else list(spec["check"])
+        obs_steps = list(range(steps)) if spec["obs_steps"] == "all" else list(spec["obs_steps"])
+        A = np.zeros((steps, n), np.uint8)
+        od_noise = np.zeros(steps)
+        sig_noise = np.zeros(steps)
+        interp_ids = -np.ones((steps, 100), np.int32)
+        msg_keep = np.ones((steps, n, C), np.uint8)
+        comm_t = np.zeros((steps, n, C), np.int32) if comm_mode == "random_sample" else None
+        out = {k: [] for k in ("t_air", "t_mass", "on", "lockout", "sso", "reward")}
+        power, signal, od_temp, solar = np.zeros(steps), np.zeros(steps), np.zeros(steps), np.zeros(steps)
+        obs_rec = []
+        for t in range(steps):
+            if spec["policy"] == "bangbang":
+                act = {i: bool(obs[i]["house_temp"] > obs[i]["house_target_temp"]) for i in env.agent_ids}
+            else:
+                act = {i: bool(prng.random() < 0.5) for i in env.agent_ids}
+            A[t] = [act[i] for i in env.agent_ids]
+            obs, rew, done, info = env.step(act)
+            gauss, choices, samples, rands, perlin = rec.drain()
+            assert len(gauss) == 1, len(gauss)
+            od_noise[t] = gauss[0]
+            if perlin:
+                assert len(perlin) == 1
+                sig_noise[t] = perlin[0]
+            if choices:
+                assert len(choices) == 1 and len(choices[0]) == 100
+                interp_ids[t] = choices[0]
+            if rands:
+                msg_keep[t] = (np.array(rands) > defect).astype(np.uint8).reshape(n, C)
+            if samples:
+                comm_t[t] = np.array(samples, dtype=np.int32).reshape(n, C)
+            power[t] = info["cluster_hvac_power"]
+            signal[t] = env.power_grid.current_signal
+            od_temp[t] = env.cluster.current_OD_temp
+            solar[t] = env.cluster.houses[0].current_solar_gain
+            if t in check:
+                hs = [env.cluster.houses[i] for i in env.agent_ids]
+                out["t_air"].append([h.current_temp for h in hs])
+                out["t_mass"].append([h.current_mass_temp for h in hs])
+                out["on"].append([bool(h.hvac.turned_on) for h in hs])
+                out["lockout"].append([bool(h.hvac.lockout) for h in hs])
+                out["sso"].append([h.hvac.seconds_since_off for h in hs])
+                out["reward"].append([rew[i] for i in env.agent_ids])
+            if t in obs_steps:
+                obs_rec.append(np.stack([norm(obs[i], c) for i in env.agent_ids]))
+    finally:
+        rec.close()
+
+    # do not bake container-specific paths into the fixture
+    if gp["base_power_mode"] == "interpolation":
+        ip = gp["base_power_parameters"]["interpolation"]
+        ip["path_datafile"] = "synthetic:default_rng(0).uniform(0,6000,4199040)"
+        ip["path_parameter_dict"] = "./monteCarlo/interp_parameters_dict.json"
+        ip["path_dict_keys"] = "./monteCarlo/interp_dict_keys.csv"
+    data = dict(
+        config_json=np.array(config_to_json(c)), seed=np.int64(spec["seed"]), steps=np.int64(steps),
+        actions=A, od_noise=od_noise, sig_noise=sig_noise, interp_ids=interp_ids, msg_keep=msg_keep,
+        check_steps=np.array(check, np.int64), obs_steps=np.array(obs_steps, np.int64),
+        power=power, signal=signal, od_temp=od_temp, solar=solar, obs0=obs0, init_keep=init_keep,
+        obs=np.stack(obs_rec) if obs_rec else np.zeros((0, n, obs0.shape[1])),
+        t_air=np.array(out["t_air"]), t_mass=np.array(out["t_mass"]),
+        on=np.array(out["on"], np.uint8), lockout=np.array(out["lockout"], np.uint8),
+        sso=np.array(out["sso"], np.int32), reward=np.array(out["reward"]),
+    )
+    if comm0 is not None:
+        data["comm"] = comm0
+    if comm_t is not None:
+        data["comm_t"] = comm_t
+        data["init_comm"] = init_comm
+    for k, v in snap.items():
+        data["snap_" + k] = v
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **data)
+    print("%-36s N=%-5d T=%-4d F=%-4d %7.1f KB" % (name, n, steps, obs0.shape[1], os.path.getsize(path) / 1024))
+
+
+def main(argv):
+    Env, norm, cfg, _ = ref_stubs.import_reference()
+    names = argv[1:] or list(CASES)
+    for name in names:
+        run_case(name, Env, norm, cfg)
+
+
+if __name__ == "__main__":
+    main(sys.argv)
