@@ -1,0 +1,226 @@
+/*
+ * mdr_b200.h -- C ABI of the B200-native MADemandResponseEnv step path.
+ *
+ * The reference (zhimaerfan/marl-demandresponse-original) is pure Python and has no
+ * FFI/plugin interface for this path: its boundary is the duck-typed class
+ * `MADemandResponseEnv` (env/MA_DemandResponse.py:37) with `reset()` (:135-172) and
+ * `step(action_dict)` (:174-210).  This header is what a ctypes binding of that class binds
+ * instead of the Python object graph HVAC -> SingleHouse -> ClusterHouses -> PowerGrid; each
+ * entry point cites the reference code it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer is allocated by the caller (torch,
+ *     cudaMalloc, ...) on `MdrConfig.device`; the library never allocates, frees or keeps
+ *     global state, and it never synchronises the stream except in the *_host entry points;
+ *   - every function returns an MdrStatus (0 = OK, negative = error) and never throws/prints;
+ *   - "real" is float when MdrConfig.precision == MDR_F32 and double when == MDR_F64;
+ *   - per-house arrays are [n_envs * n_houses], env-major (house h of env e at e*n_houses+h),
+ *     16-byte aligned; per-env arrays are [n_envs];
+ *   - callable from any host thread; re-entrant; one stream per shard.
+ */
+#ifndef MDR_B200_H
+#define MDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDR_ABI_VERSION 3
+#define MDR_MAX_SINUSOIDS 8
+#define MDR_INTERP_DIMS 10
+#define MDR_INTERP_MAX_AXIS 12
+#define MDR_MAX_HOUSES_PER_ENV 1024 /* one env lives in one CTA (thread per house) */
+
+typedef enum MdrStatus {
+  MDR_OK = 0,
+  MDR_ERR_NULL = -1,        /* a required pointer is NULL */
+  MDR_ERR_SHAPE = -2,       /* n_envs / n_houses / n_comm / n_features inconsistent */
+  MDR_ERR_MODE = -3,        /* unknown enum value (reference raises ValueError) */
+  MDR_ERR_ALIGN = -4,       /* a buffer is not 16-byte aligned */
+  MDR_ERR_CUDA = -5,        /* a CUDA runtime call failed (see mdr_last_cuda_error) */
+  MDR_ERR_UNSUPPORTED = -6, /* valid in the reference but outside this build (e.g. N > 1024) */
+  MDR_ERR_VERSION = -7      /* MdrConfig.abi_version != MDR_ABI_VERSION */
+} MdrStatus;
+
+enum { MDR_F32 = 4, MDR_F64 = 8 };
+
+/* agents_comm_mode, env/MA_DemandResponse.py:806-902 */
+enum {
+  MDR_COMM_NEIGHBOURS = 0, /* implicit circular table, :816-828 */
+  MDR_COMM_TABLE = 1,      /* explicit int32 [n_houses, n_comm] shared by all envs
+                              (closed_groups :830-844, random_fixed :849-854, neighbours_2D :856-890) */
+  MDR_COMM_TABLE_PER_ENV = 2, /* explicit int32 [n_envs, n_houses, n_comm] (random_sample :976-983, replayed) */
+  MDR_COMM_NONE = 3        /* no_message :893-895 */
+};
+
+/* state_properties / message_properties, utils.py:740-880 */
+enum {
+  MDR_STATE_HOUR = 1, MDR_STATE_DAY = 2, MDR_STATE_SOLAR = 4, MDR_STATE_THERMAL = 8, MDR_STATE_HVAC = 16,
+  MDR_MSG_THERMAL = 1, MDR_MSG_HVAC = 2
+};
+
+/* temp_penalty_mode, env/MA_DemandResponse.py:253-328 */
+enum { MDR_PEN_INDIVIDUAL_L2 = 0, MDR_PEN_COMMON_L2 = 1, MDR_PEN_COMMON_MAX = 2, MDR_PEN_MIXTURE = 3 };
+/* base_power_mode, env/MA_DemandResponse.py:1248-1255 */
+enum { MDR_BASE_CONSTANT = 0, MDR_BASE_INTERPOLATION = 1 };
+/* signal_mode, env/MA_DemandResponse.py:1257-1310 */
+enum { MDR_SIG_FLAT = 0, MDR_SIG_SINUSOIDALS = 1, MDR_SIG_REGULAR_STEPS = 2, MDR_SIG_PERLIN = 3 };
+/* where the HVAC commands come from */
+enum {
+  MDR_ACT_ARRAY = 0,    /* MdrStepInputs.actions (the reference's action_dict) */
+  MDR_ACT_BANGBANG = 1, /* on-device restatement of agents/bangbang_controllers.py:41-61 (benchmark source) */
+  MDR_ACT_RANDOM = 2    /* Philox Bernoulli(1/2) per house (benchmark source) */
+};
+
+/* Flattened form of the reference's nested config dict (config.py), built once per env. */
+typedef struct MdrConfig {
+  int32_t abi_version; /* MDR_ABI_VERSION */
+  int32_t device;      /* CUDA device ordinal that owns every buffer */
+  int32_t precision;   /* MDR_F32 | MDR_F64 */
+  int32_t n_envs;      /* E: independent clusters in this shard */
+  int32_t n_houses;    /* N: default_env_prop.cluster_prop.nb_agents */
+  int32_t n_comm;      /* C: messages per agent (min(nb_agents_comm, N-1), :808-810) */
+  int32_t n_features;  /* F: must equal mdr_obs_width(cfg) */
+  int32_t time_step;   /* seconds, default_env_prop.time_step */
+  int32_t comm_mode;   /* MDR_COMM_* */
+  int32_t state_flags; /* MDR_STATE_* bitmask */
+  int32_t msg_flags;   /* MDR_MSG_* bitmask */
+  int32_t temp_penalty_mode; /* MDR_PEN_* */
+  int32_t solar_gain;  /* default_house_prop.solar_gain_bool */
+  int32_t base_power_mode;   /* MDR_BASE_* */
+  int32_t signal_mode; /* MDR_SIG_* */
+  int32_t n_sinusoids;
+  int32_t interp_update_period; /* seconds */
+  int32_t interp_nb_agents;     /* houses sampled per refresh */
+  int32_t perlin_nb_octaves, perlin_octaves_step;
+  int32_t action_source; /* MDR_ACT_* */
+  int32_t obs_norm_agents; /* nb_agents used by normStateDict (utils.py:833-839); normally == n_houses */
+  /* reward, env/MA_DemandResponse.py:330-373 */
+  double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty;
+  double mix_alpha_ind, mix_alpha_common, mix_alpha_max;
+  /* normStateDict divisors, utils.py:740-880 */
+  double norm_reg_sig, def_ua, def_cm, def_ca, def_hm, def_cop, def_latent, def_cap;
+  /* HVAC constants shared by all houses (the reference never noises COP / latent fraction) */
+  double hvac_cop, hvac_latent;
+  /* outdoor temperature model, :1057-1081 */
+  double day_temp, night_temp, temp_std;
+  /* solar gain, utils.py:1277-1350 */
+  double window_area, shading_coeff;
+  /* power grid */
+  double avg_power_per_hvac;
+  double sin_periods[MDR_MAX_SINUSOIDS], sin_ratios[MDR_MAX_SINUSOIDS];
+  double steps_amplitude_per_hvac, steps_period;
+  double perlin_amplitude, perlin_period;
+  double comm_defect_prob; /* only used when MdrStepInputs.msg_keep is NULL */
+  /* interpolation grid, monteCarlo/interp_parameters_dict.json in interp_dict_keys.csv order */
+  int32_t interp_dims[MDR_INTERP_DIMS];
+  double interp_axes[MDR_INTERP_DIMS][MDR_INTERP_MAX_AXIS];
+  uint64_t seed; /* Philox key for draws that are not replayed */
+} MdrConfig;
+
+/* Per-house struct-of-arrays.  Packed vectors keep every access a coalesced 8/16-byte load. */
+typedef struct MdrHouses {
+  /* raw properties (double regardless of precision); read by mdr_precompute, by the optional
+     observation blocks and by the interpolation refresh */
+  const double *ua, *cm, *ca, *hm;    /* SingleHouse.Ua/Cm/Ca/Hm, :581-584 */
+  const double *cap;                  /* HVAC.cooling_capacity, :428 */
+  const double *target, *deadband;    /* SingleHouse.target_temp/deadband, :577-578 */
+  const int32_t *lockout_dur;         /* HVAC.lockout_duration (noise already applied), :430 */
+  /* derived coefficients written by mdr_precompute, real4/real4/real2 per house */
+  void *coef_a; /* (d11, m12, m21, d22): expm(A*dt) - I of the ETP ODE, :704-735 */
+  void *coef_b; /* (1/Ua, Q_on = -cap/(1+latent), P_on = cap/COP, target) */
+  void *coef_c; /* (deadband, lockout_duration as real) */
+  int32_t *interp_key; /* flat table offset of the nearest (Ua,Cm,Ca,Hm ratio, HVAC power) cell */
+  /* state, read and written by every step */
+  void *temps;   /* real2 (T_air, T_mass) in Celsius, :536-537 */
+  int32_t *hvac; /* (seconds_since_off << 2) | (lockout << 1) | turned_on, :405-406,433 */
+} MdrHouses;
+
+/* Per-env (cluster + power grid) scalars; always double / integer. */
+typedef struct MdrEnvs {
+  int64_t *t_epoch;          /* naive seconds since 1970-01-01 of MADemandResponseEnv.datetime */
+  const double *phase;       /* ClusterHouses.phase, :789-792 */
+  double *od_temp;           /* ClusterHouses.current_OD_temp, :793,1037 */
+  double *solar_gain;        /* SingleHouse.current_solar_gain used by the last update, :694 */
+  double *solar_next;        /* gain the next step will use (= house_solar_gain(t + dt)) */
+  const double *artificial_ratio; /* PowerGrid.artificial_ratio, :1116 */
+  const double *max_power;   /* ClusterHouses.max_power, :796-802 */
+  double *base_power;        /* PowerGrid.base_power */
+  double *signal;            /* PowerGrid.current_signal */
+  double *cluster_power;     /* ClusterHouses.cluster_hvac_power */
+  int32_t *time_since_interp;/* PowerGrid.time_since_last_interp */
+  const double *perlin_seed; /* seed of the device perlin (production mode only) */
+  double *metrics;           /* optional [n_envs, MDR_N_METRICS] running sums, or NULL */
+} MdrEnvs;
+
+#define MDR_N_METRICS 6 /* steps, sum reward/N, sum |T-target|/N, sum (S-P)^2, max |T-target|, sum |S-P|/N^2 */
+
+/* Inputs of one step.  NULL replay pointers select on-device generation. */
+typedef struct MdrStepInputs {
+  const uint8_t *actions;     /* [E*N] nonzero = ON (ignored unless action_source == MDR_ACT_ARRAY) */
+  const double *od_noise;     /* [E] replayed random.gauss(0, temp_std) draw (:1079) */
+  const double *signal_noise; /* [E] replayed Perlin.calculate_noise value (:1299) */
+  const int32_t *interp_ids;  /* [E*interp_nb_agents] replayed random.choices ids (:1214) */
+  const uint8_t *msg_keep;    /* [E*N*C] 1 = delivered (replays np.random.rand() > p, :992) */
+  const int32_t *comm_table;  /* MDR_COMM_TABLE(_PER_ENV) neighbour ids */
+  const void *interp_table;   /* real[prod(interp_dims)], C order (mergedGridSearchResultFinal.npy) */
+  uint64_t step_index;        /* counter for the Philox streams */
+} MdrStepInputs;
+
+typedef struct MdrOutputs {
+  void *obs;    /* real [E, N, F]: the normStateDict vector of every agent, or NULL to skip */
+  void *reward; /* real [E, N], or NULL to skip */
+} MdrOutputs;
+
+int mdr_version(void);
+const char *mdr_strerror(int status);
+/* text of the last CUDA error seen by the calling thread ("" if none) */
+const char *mdr_last_cuda_error(void);
+
+/* F of utils.normStateDict (utils.py:740-880) for these flags; negative MdrStatus on error. */
+int mdr_obs_width(const MdrConfig *cfg);
+
+/* Validates cfg (modes, shapes) the way the reference constructors raise ValueError
+   (env/MA_DemandResponse.py:249,324,898,1169,1306). */
+int mdr_validate(const MdrConfig *cfg);
+
+/* Launch geometry the step kernel will use (for tests and the roofline report). */
+int mdr_launch_geometry(const MdrConfig *cfg, int has_obs, int32_t *envs_per_cta, int32_t *threads,
+                        int32_t *ctas, size_t *smem_bytes);
+
+/* Replaces the per-step recomputation of a,b,c,r1,r2,A3,A4,exp(r*dt) in
+   SingleHouse.update_temperature (:704-735) and HVAC.get_Q/power_consumption (:494-523):
+   fills coef_a/b/c and interp_key from the raw properties. */
+int mdr_precompute(const MdrConfig *cfg, const MdrHouses *houses, void *stream);
+
+/* MADemandResponseEnv.build_environment tail + reset (:133, :163-172): PowerGrid.step at the
+   start datetime (initial signal, incl. the first interpolation), cluster power = 0, solar
+   gain schedule, and the initial observation. */
+int mdr_reset(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
+              const MdrStepInputs *in, const MdrOutputs *out, void *stream);
+
+/* Observation of the current state without advancing anything (what reset() returns at
+   :163-172 once the signal is known; also used after loading a checkpoint). */
+int mdr_observe(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
+                const MdrStepInputs *in, const MdrOutputs *out, void *stream);
+
+/* MADemandResponseEnv.step (:174-210) for every env of the shard, `n_steps` times (n_steps > 1
+   requires on-device action/noise sources).  One kernel launch per step. */
+int mdr_step(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
+             const MdrStepInputs *in, const MdrOutputs *out, int32_t n_steps, void *stream);
+
+/* Same step with HOST buffers: copies `host_actions` to `in->actions` (device staging), runs
+   the step, copies obs / reward / per-env (power, signal) back into the host pointers and
+   synchronises the stream.  This is the call the dict API and the e2e benchmark use. */
+int mdr_step_host(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
+                  const MdrStepInputs *in, const MdrOutputs *out, const uint8_t *host_actions,
+                  void *host_obs, void *host_reward, double *host_power, double *host_signal,
+                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDR_B200_H */

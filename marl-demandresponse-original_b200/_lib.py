@@ -1,0 +1,119 @@
+"""ctypes binding of include/mdr_b200.h.  There is no CPU fallback: if the CUDA library is
+missing the import of the environment classes fails loudly."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+MDR_ABI_VERSION = 3
+MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
+F32, F64 = 4, 8
+COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
+STATE_HOUR, STATE_DAY, STATE_SOLAR, STATE_THERMAL, STATE_HVAC = 1, 2, 4, 8, 16
+MSG_THERMAL, MSG_HVAC = 1, 2
+PEN = {"individual_L2": 0, "common_L2": 1, "common_max": 2, "mixture": 3}
+BASE = {"constant": 0, "interpolation": 1}
+SIG_FLAT, SIG_SINUSOIDALS, SIG_REGULAR_STEPS, SIG_PERLIN = 0, 1, 2, 3
+ACT = {"array": 0, "bangbang": 1, "random": 2}
+
+_i32, _f64, _vp = C.c_int32, C.c_double, C.c_void_p
+
+
+class MdrConfig(C.Structure):
+    _fields_ = (
+        [(n, _i32) for n in (
+            "abi_version", "device", "precision", "n_envs", "n_houses", "n_comm", "n_features", "time_step",
+            "comm_mode", "state_flags", "msg_flags", "temp_penalty_mode", "solar_gain", "base_power_mode",
+            "signal_mode", "n_sinusoids", "interp_update_period", "interp_nb_agents", "perlin_nb_octaves",
+            "perlin_octaves_step", "action_source", "obs_norm_agents")]
+        + [(n, _f64) for n in (
+            "alpha_temp", "alpha_sig", "norm_temp_penalty", "norm_sig_penalty", "mix_alpha_ind", "mix_alpha_common",
+            "mix_alpha_max", "norm_reg_sig", "def_ua", "def_cm", "def_ca", "def_hm", "def_cop", "def_latent",
+            "def_cap", "hvac_cop", "hvac_latent", "day_temp", "night_temp", "temp_std", "window_area",
+            "shading_coeff", "avg_power_per_hvac")]
+        + [("sin_periods", _f64 * MAX_SINUSOIDS), ("sin_ratios", _f64 * MAX_SINUSOIDS)]
+        + [(n, _f64) for n in ("steps_amplitude_per_hvac", "steps_period", "perlin_amplitude", "perlin_period",
+                               "comm_defect_prob")]
+        + [("interp_dims", _i32 * INTERP_DIMS), ("interp_axes", (_f64 * INTERP_MAX_AXIS) * INTERP_DIMS),
+           ("seed", C.c_uint64)]
+    )
+
+
+class MdrHouses(C.Structure):
+    _fields_ = [(n, _vp) for n in ("ua", "cm", "ca", "hm", "cap", "target", "deadband", "lockout_dur", "coef_a",
+                                   "coef_b", "coef_c", "interp_key", "temps", "hvac")]
+
+
+class MdrEnvs(C.Structure):
+    _fields_ = [(n, _vp) for n in ("t_epoch", "phase", "od_temp", "solar_gain", "solar_next", "artificial_ratio",
+                                   "max_power", "base_power", "signal", "cluster_power", "time_since_interp",
+                                   "perlin_seed", "metrics")]
+
+
+class MdrStepInputs(C.Structure):
+    _fields_ = [(n, _vp) for n in ("actions", "od_noise", "signal_noise", "interp_ids", "msg_keep", "comm_table",
+                                   "interp_table")] + [("step_index", C.c_uint64)]
+
+
+class MdrOutputs(C.Structure):
+    _fields_ = [("obs", _vp), ("reward", _vp)]
+
+
+EXPORTS = ("mdr_version", "mdr_strerror", "mdr_last_cuda_error", "mdr_obs_width", "mdr_validate",
+           "mdr_launch_geometry", "mdr_precompute", "mdr_reset", "mdr_observe", "mdr_step", "mdr_step_host")
+
+_lib = None
+
+
+class MdrError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Loads (building first if the sources are newer) the CUDA library; raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this box: use the shipped .so if there is one
+            if not os.path.isfile(path):
+                raise MdrError("libmdr_b200.so is missing and could not be built: %s" % exc)
+    if not os.path.isfile(path):
+        raise MdrError("CUDA extension %s not found; run `python __graft_entry__.py` (build) first. "
+                       "There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise MdrError("libmdr_b200.so does not export %s" % name)
+    lib.mdr_version.restype = C.c_int
+    lib.mdr_strerror.restype = C.c_char_p
+    lib.mdr_strerror.argtypes = [C.c_int]
+    lib.mdr_last_cuda_error.restype = C.c_char_p
+    P = C.POINTER
+    lib.mdr_obs_width.argtypes = [P(MdrConfig)]
+    lib.mdr_validate.argtypes = [P(MdrConfig)]
+    lib.mdr_launch_geometry.argtypes = [P(MdrConfig), C.c_int, P(_i32), P(_i32), P(_i32), P(C.c_size_t)]
+    lib.mdr_precompute.argtypes = [P(MdrConfig), P(MdrHouses), _vp]
+    step_args = [P(MdrConfig), P(MdrHouses), P(MdrEnvs), P(MdrStepInputs), P(MdrOutputs)]
+    lib.mdr_reset.argtypes = step_args + [_vp]
+    lib.mdr_observe.argtypes = step_args + [_vp]
+    lib.mdr_step.argtypes = step_args + [_i32, _vp]
+    lib.mdr_step_host.argtypes = step_args + [_vp, _vp, _vp, _vp, _vp, _vp]
+    if lib.mdr_version() != MDR_ABI_VERSION:
+        raise MdrError("libmdr_b200.so ABI %d != binding ABI %d (rebuild)" % (lib.mdr_version(), MDR_ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "mdr call"):
+    if status != 0:
+        lib = load()
+        msg = lib.mdr_strerror(status).decode()
+        if status == -5:
+            msg += ": " + lib.mdr_last_cuda_error().decode()
+        if status == -3:
+            raise ValueError("%s: %s" % (what, msg))
+        raise MdrError("%s failed (%d): %s" % (what, status, msg))

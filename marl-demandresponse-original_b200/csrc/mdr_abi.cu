@@ -1,0 +1,304 @@
+// C ABI of the step path (include/mdr_b200.h): argument validation, launch geometry, launches,
+// error mapping.  No allocation, no global mutable state besides a per-device "attribute set"
+// latch inside the launcher, no stream synchronisation except in mdr_step_host.
+#include <stdio.h>
+#include <string.h>
+
+#include "mdr_kernels.h"
+
+using mdr::Geometry;
+using mdr::KernelParams;
+
+static thread_local char g_cuda_error[256] = "";
+
+static int cuda_fail(cudaError_t err) {
+  snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s", cudaGetErrorName(err), cudaGetErrorString(err));
+  return MDR_ERR_CUDA;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int mdr_version(void) { return MDR_ABI_VERSION; }
+
+extern "C" const char* mdr_last_cuda_error(void) { return g_cuda_error; }
+
+extern "C" const char* mdr_strerror(int status) {
+  switch (status) {
+    case MDR_OK: return "ok";
+    case MDR_ERR_NULL: return "a required pointer is NULL";
+    case MDR_ERR_SHAPE: return "inconsistent shape (n_envs / n_houses / n_comm / n_features)";
+    case MDR_ERR_MODE: return "unknown mode value";
+    case MDR_ERR_ALIGN: return "buffer is not 16-byte aligned";
+    case MDR_ERR_CUDA: return "CUDA runtime error (see mdr_last_cuda_error)";
+    case MDR_ERR_UNSUPPORTED: return "configuration not supported by this build";
+    case MDR_ERR_VERSION: return "MdrConfig.abi_version does not match the library";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int mdr_obs_width(const MdrConfig* c) {
+  if (!c) return MDR_ERR_NULL;
+  // utils.normStateDict, utils.py:740-880
+  int own = 11;  // T_air, T_mass, target, deadband, cap, on, lockout, sso, lockout_dur, signal, power
+  if (c->state_flags & MDR_STATE_THERMAL) own += 1 + 4;
+  if (c->state_flags & MDR_STATE_DAY) own += 2;
+  if (c->state_flags & MDR_STATE_HOUR) own += 2;
+  if (c->state_flags & MDR_STATE_SOLAR) own += 1;
+  if (c->state_flags & MDR_STATE_HVAC) own += 2;
+  int msg = 4;
+  if (c->msg_flags & MDR_MSG_THERMAL) msg += 4;
+  if (c->msg_flags & MDR_MSG_HVAC) msg += 3;
+  return own + msg * c->n_comm;
+}
+
+extern "C" int mdr_validate(const MdrConfig* c) {
+  if (!c) return MDR_ERR_NULL;
+  if (c->abi_version != MDR_ABI_VERSION) return MDR_ERR_VERSION;
+  if (c->precision != MDR_F32 && c->precision != MDR_F64) return MDR_ERR_MODE;
+  if (c->n_envs < 1 || c->n_houses < 1 || c->n_comm < 0 || c->time_step < 1) return MDR_ERR_SHAPE;
+  if (c->n_comm > 0 && c->comm_mode == MDR_COMM_NEIGHBOURS && c->n_comm > c->n_houses - 1) return MDR_ERR_SHAPE;
+  if (c->comm_mode < MDR_COMM_NEIGHBOURS || c->comm_mode > MDR_COMM_NONE) return MDR_ERR_MODE;
+  if (c->comm_mode == MDR_COMM_NONE && c->n_comm != 0) return MDR_ERR_SHAPE;
+  if (c->temp_penalty_mode < MDR_PEN_INDIVIDUAL_L2 || c->temp_penalty_mode > MDR_PEN_MIXTURE) return MDR_ERR_MODE;
+  if (c->base_power_mode != MDR_BASE_CONSTANT && c->base_power_mode != MDR_BASE_INTERPOLATION) return MDR_ERR_MODE;
+  if (c->signal_mode < MDR_SIG_FLAT || c->signal_mode > MDR_SIG_PERLIN) return MDR_ERR_MODE;
+  if (c->action_source < MDR_ACT_ARRAY || c->action_source > MDR_ACT_RANDOM) return MDR_ERR_MODE;
+  if (c->n_sinusoids < 0 || c->n_sinusoids > MDR_MAX_SINUSOIDS) return MDR_ERR_SHAPE;
+  if (c->n_features != mdr_obs_width(c)) return MDR_ERR_SHAPE;
+  if (c->n_houses > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
+  if (c->base_power_mode == MDR_BASE_INTERPOLATION) {
+    if (c->interp_nb_agents < 1 || c->interp_nb_agents > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_SHAPE;
+    for (int d = 0; d < MDR_INTERP_DIMS; ++d)
+      if (c->interp_dims[d] < 2 || c->interp_dims[d] > MDR_INTERP_MAX_AXIS) return MDR_ERR_SHAPE;
+    if (c->interp_dims[7] > 16) return MDR_ERR_SHAPE;
+  }
+  return MDR_OK;
+}
+
+static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
+  const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
+  if (N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
+  int gmax = 256 / N;
+  if (gmax < 1) gmax = 1;
+  if (gmax > E) gmax = E;
+  int G = gmax;
+  if (has_obs) {  // a CTA's first observation row should be 16-byte aligned for the bulk store
+    for (int k = gmax; k >= 1; --k)
+      if (((size_t)k * N * F * rb) % 16 == 0) { G = k; break; }
+  }
+  const int threads = ((G * N + 31) / 32) * 32;
+  const int nwarps = threads / 32;
+  const bool need_val = c->base_power_mode == MDR_BASE_INTERPOLATION;
+  const bool need_pen = c->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2;
+  int blocks_per_sm = 896 / threads;
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  const size_t budget = (size_t)MDR_MAX_SMEM_BYTES / blocks_per_sm - 1024;
+  int rpp = 0;
+  size_t smem = 0;
+  for (int r = 32; r >= 1; r >>= 1) {
+    smem = mdr::step_smem_bytes(rb, threads, G, nwarps, r, F, need_val, need_pen, has_obs);
+    if (smem <= budget) { rpp = r; break; }
+  }
+  if (rpp == 0) {
+    for (int r = 32; r >= 1; r >>= 1) {
+      smem = mdr::step_smem_bytes(rb, threads, G, nwarps, r, F, need_val, need_pen, has_obs);
+      if (smem <= (size_t)MDR_MAX_SMEM_BYTES) { rpp = r; break; }
+    }
+  }
+  if (rpp == 0) return MDR_ERR_UNSUPPORTED;
+  g->envs_per_cta = G;
+  g->threads = threads;
+  g->hmax = threads;
+  g->ctas = (E + G - 1) / G;
+  g->rows_per_pass = rpp;
+  g->smem_bytes = smem;
+  return MDR_OK;
+}
+
+extern "C" int mdr_launch_geometry(const MdrConfig* cfg, int has_obs, int32_t* envs_per_cta, int32_t* threads,
+                                   int32_t* ctas, size_t* smem_bytes) {
+  int st = mdr_validate(cfg);
+  if (st != MDR_OK) return st;
+  Geometry g;
+  st = choose_geometry(cfg, has_obs != 0, &g);
+  if (st != MDR_OK) return st;
+  if (envs_per_cta) *envs_per_cta = g.envs_per_cta;
+  if (threads) *threads = g.threads;
+  if (ctas) *ctas = g.ctas;
+  if (smem_bytes) *smem_bytes = g.smem_bytes;
+  return MDR_OK;
+}
+
+static void fill_config(KernelParams& k, const MdrConfig* c) {
+  memset(&k, 0, sizeof(k));
+  k.E = c->n_envs; k.N = c->n_houses; k.C = c->n_comm; k.F = c->n_features; k.dt = c->time_step;
+  k.comm_mode = c->comm_mode; k.state_flags = c->state_flags; k.msg_flags = c->msg_flags;
+  k.temp_penalty_mode = c->temp_penalty_mode; k.solar = c->solar_gain != 0;
+  k.base_power_mode = c->base_power_mode; k.signal_mode = c->signal_mode; k.n_sinusoids = c->n_sinusoids;
+  k.interp_update_period = c->interp_update_period; k.interp_nb_agents = c->interp_nb_agents;
+  k.perlin_nb_octaves = c->perlin_nb_octaves; k.perlin_octaves_step = c->perlin_octaves_step;
+  k.action_source = c->action_source; k.seed = c->seed;
+  k.alpha_temp = c->alpha_temp; k.alpha_sig = c->alpha_sig;
+  k.norm_temp_penalty = c->norm_temp_penalty; k.norm_sig_penalty = c->norm_sig_penalty;
+  k.mix_alpha_ind = c->mix_alpha_ind; k.mix_alpha_common = c->mix_alpha_common; k.mix_alpha_max = c->mix_alpha_max;
+  k.inv_norm_reg_sig = 1.0 / c->norm_reg_sig;
+  const int agents = c->obs_norm_agents > 0 ? c->obs_norm_agents : c->n_houses;
+  k.inv_norm_sig_agents = 1.0 / (c->norm_reg_sig * agents);
+  k.cop_over_def_cap = c->hvac_cop / c->def_cap;
+  k.def_ua = c->def_ua; k.def_cm = c->def_cm; k.def_ca = c->def_ca; k.def_hm = c->def_hm;
+  k.def_cop = c->def_cop; k.def_latent = c->def_latent; k.def_cap = c->def_cap;
+  k.hvac_cop = c->hvac_cop; k.hvac_latent = c->hvac_latent;
+  k.day_temp = c->day_temp; k.night_temp = c->night_temp; k.temp_std = c->temp_std;
+  k.window_area = c->window_area; k.shading_coeff = c->shading_coeff;
+  k.avg_power_per_hvac = c->avg_power_per_hvac;
+  memcpy(k.sin_periods, c->sin_periods, sizeof(k.sin_periods));
+  memcpy(k.sin_ratios, c->sin_ratios, sizeof(k.sin_ratios));
+  k.steps_amplitude_per_hvac = c->steps_amplitude_per_hvac; k.steps_period = c->steps_period;
+  k.perlin_amplitude = c->perlin_amplitude; k.perlin_period = c->perlin_period;
+  k.comm_defect_prob = c->comm_defect_prob;
+  memcpy(k.interp_dims, c->interp_dims, sizeof(k.interp_dims));
+  memcpy(k.interp_axes, c->interp_axes, sizeof(k.interp_axes));
+}
+
+static int fill_houses(KernelParams& k, const MdrConfig* c, const MdrHouses* h, bool for_step) {
+  if (!h) return MDR_ERR_NULL;
+  if (!h->coef_a || !h->coef_b || !h->coef_c) return MDR_ERR_NULL;
+  if (!aligned16(h->coef_a) || !aligned16(h->coef_b) || !aligned16(h->coef_c)) return MDR_ERR_ALIGN;
+  const bool interp = c->base_power_mode == MDR_BASE_INTERPOLATION;
+  if (interp && !h->interp_key) return MDR_ERR_NULL;
+  if (for_step) {
+    if (!h->temps || !h->hvac) return MDR_ERR_NULL;
+    if (!aligned16(h->temps) || !aligned16(h->hvac)) return MDR_ERR_ALIGN;
+    const bool need_raw = (c->state_flags & MDR_STATE_THERMAL) || (c->msg_flags & MDR_MSG_THERMAL);
+    if (need_raw && (!h->ua || !h->cm || !h->ca || !h->hm)) return MDR_ERR_NULL;
+    if ((c->msg_flags & MDR_MSG_HVAC) && !h->cap) return MDR_ERR_NULL;
+  } else {
+    if (!h->ua || !h->cm || !h->ca || !h->hm || !h->cap || !h->target || !h->deadband || !h->lockout_dur)
+      return MDR_ERR_NULL;
+  }
+  k.ua = h->ua; k.cm = h->cm; k.ca = h->ca; k.hm = h->hm; k.cap = h->cap;
+  k.target = h->target; k.deadband = h->deadband; k.lockout_dur = h->lockout_dur;
+  k.coef_a = h->coef_a; k.coef_b = h->coef_b; k.coef_c = h->coef_c; k.interp_key = h->interp_key;
+  k.temps = h->temps; k.hvac = h->hvac;
+  return MDR_OK;
+}
+
+static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, const MdrStepInputs* in,
+                     const MdrOutputs* out, int is_reset) {
+  if (!e || !in || !out) return MDR_ERR_NULL;
+  if (!e->t_epoch || !e->phase || !e->od_temp || !e->artificial_ratio || !e->max_power || !e->base_power ||
+      !e->signal || !e->cluster_power)
+    return MDR_ERR_NULL;
+  if (c->solar_gain && (!e->solar_gain || !e->solar_next)) return MDR_ERR_NULL;
+  const bool interp = c->base_power_mode == MDR_BASE_INTERPOLATION;
+  if (interp && (!e->time_since_interp || !in->interp_table)) return MDR_ERR_NULL;
+  if (c->signal_mode == MDR_SIG_PERLIN && !in->signal_noise && !e->perlin_seed) return MDR_ERR_NULL;
+  if (!is_reset && c->action_source == MDR_ACT_ARRAY && !in->actions) return MDR_ERR_NULL;
+  if ((c->comm_mode == MDR_COMM_TABLE || c->comm_mode == MDR_COMM_TABLE_PER_ENV) && c->n_comm > 0 && !in->comm_table &&
+      out->obs)
+    return MDR_ERR_NULL;
+  if (out->obs && !aligned16(out->obs)) return MDR_ERR_ALIGN;
+  if (e->metrics) return MDR_ERR_UNSUPPORTED;  // reserved
+  k.t_epoch = e->t_epoch; k.phase = e->phase; k.od_temp = e->od_temp; k.solar_gain = e->solar_gain;
+  k.solar_next = e->solar_next; k.artificial_ratio = e->artificial_ratio; k.max_power = e->max_power;
+  k.base_power = e->base_power; k.signal = e->signal; k.cluster_power = e->cluster_power;
+  k.time_since_interp = e->time_since_interp; k.perlin_seed = e->perlin_seed;
+  k.actions = in->actions; k.od_noise = in->od_noise; k.signal_noise = in->signal_noise;
+  k.interp_ids = in->interp_ids; k.msg_keep = in->msg_keep; k.comm_table = in->comm_table;
+  k.interp_table = in->interp_table; k.step_index = in->step_index;
+  k.obs = out->obs; k.reward = out->reward;
+  k.is_reset = is_reset;
+  return MDR_OK;
+}
+
+extern "C" int mdr_precompute(const MdrConfig* cfg, const MdrHouses* houses, void* stream) {
+  int st = mdr_validate(cfg);
+  if (st != MDR_OK) return st;
+  KernelParams k;
+  fill_config(k, cfg);
+  st = fill_houses(k, cfg, houses, false);
+  if (st != MDR_OK) return st;
+  cudaError_t err = cudaSetDevice(cfg->device);
+  if (err != cudaSuccess) return cuda_fail(err);
+  err = mdr::launch_precompute_any(k, cfg->precision, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? MDR_OK : cuda_fail(err);
+}
+
+static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs, const MdrStepInputs* in,
+                     const MdrOutputs* out, int n_steps, int is_reset, cudaStream_t stream) {
+  int st = mdr_validate(cfg);
+  if (st != MDR_OK) return st;
+  if (n_steps < 1) return MDR_ERR_SHAPE;
+  KernelParams k;
+  fill_config(k, cfg);
+  st = fill_houses(k, cfg, houses, true);
+  if (st != MDR_OK) return st;
+  st = fill_step(k, cfg, envs, in, out, is_reset);
+  if (st != MDR_OK) return st;
+  Geometry g;
+  st = choose_geometry(cfg, out->obs != nullptr, &g);
+  if (st != MDR_OK) return st;
+  k.G = g.envs_per_cta;
+  k.hmax = g.hmax;
+  k.rows_per_pass = g.rows_per_pass;
+  cudaError_t err = cudaSetDevice(cfg->device);
+  if (err != cudaSuccess) return cuda_fail(err);
+  for (int i = 0; i < n_steps; ++i) {
+    err = mdr::launch_step_any(k, g, cfg->precision, stream);
+    if (err != cudaSuccess) return cuda_fail(err);
+    k.step_index += 1;
+  }
+  return MDR_OK;
+}
+
+extern "C" int mdr_reset(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs, const MdrStepInputs* in,
+                         const MdrOutputs* out, void* stream) {
+  return run_steps(cfg, houses, envs, in, out, 1, 1, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mdr_observe(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs, const MdrStepInputs* in,
+                           const MdrOutputs* out, void* stream) {
+  return run_steps(cfg, houses, envs, in, out, 1, 2, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mdr_step(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs, const MdrStepInputs* in,
+                        const MdrOutputs* out, int32_t n_steps, void* stream) {
+  return run_steps(cfg, houses, envs, in, out, n_steps, 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mdr_step_host(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs,
+                             const MdrStepInputs* in, const MdrOutputs* out, const uint8_t* host_actions,
+                             void* host_obs, void* host_reward, double* host_power, double* host_signal,
+                             void* stream_v) {
+  if (!cfg || !in || !out || !envs) return MDR_ERR_NULL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  cudaError_t err = cudaSetDevice(cfg->device);
+  if (err != cudaSuccess) return cuda_fail(err);
+  const size_t houses_total = (size_t)cfg->n_envs * cfg->n_houses;
+  if (host_actions) {
+    if (!in->actions) return MDR_ERR_NULL;
+    err = cudaMemcpyAsync(const_cast<uint8_t*>(in->actions), host_actions, houses_total, cudaMemcpyHostToDevice, stream);
+    if (err != cudaSuccess) return cuda_fail(err);
+  }
+  int st = run_steps(cfg, houses, envs, in, out, 1, 0, stream);
+  if (st != MDR_OK) return st;
+  const size_t rb = (size_t)cfg->precision;
+  if (host_obs && out->obs) {
+    err = cudaMemcpyAsync(host_obs, out->obs, houses_total * cfg->n_features * rb, cudaMemcpyDeviceToHost, stream);
+    if (err != cudaSuccess) return cuda_fail(err);
+  }
+  if (host_reward && out->reward) {
+    err = cudaMemcpyAsync(host_reward, out->reward, houses_total * rb, cudaMemcpyDeviceToHost, stream);
+    if (err != cudaSuccess) return cuda_fail(err);
+  }
+  if (host_power) {
+    err = cudaMemcpyAsync(host_power, envs->cluster_power, sizeof(double) * cfg->n_envs, cudaMemcpyDeviceToHost, stream);
+    if (err != cudaSuccess) return cuda_fail(err);
+  }
+  if (host_signal) {
+    err = cudaMemcpyAsync(host_signal, envs->signal, sizeof(double) * cfg->n_envs, cudaMemcpyDeviceToHost, stream);
+    if (err != cudaSuccess) return cuda_fail(err);
+  }
+  err = cudaStreamSynchronize(stream);
+  return err == cudaSuccess ? MDR_OK : cuda_fail(err);
+}

@@ -1,0 +1,175 @@
+// Device-side helpers of the fused MADemandResponseEnv step kernel (sm_100a only).
+// Reference citations are relative to zhimaerfan/marl-demandresponse-original.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mdr_b200.h"
+
+namespace mdr {
+
+template <typename R> struct Vec;
+template <> struct Vec<float> { using T2 = float2; using T4 = float4; };
+template <> struct Vec<double> { using T2 = double2; using T4 = double4; };
+
+__device__ __forceinline__ float2 make2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ double2 make2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float4 make4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+__device__ __forceinline__ double4 make4(double a, double b, double c, double d) { return make_double4(a, b, c, d); }
+
+// Non-contracted arithmetic: the interpolation and the grid signal are evaluated in the
+// reference's operation order (scipy/_rgi.py:520-549, env/MA_DemandResponse.py:1295-1314) so
+// that fp64 results agree to the last bit with numpy given identical inputs.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator: every (entity, step, stream) owns its own draw, so
+// results do not depend on the launch geometry.
+// ---------------------------------------------------------------------------------------
+enum : uint32_t { STREAM_OD = 1, STREAM_ACT = 2, STREAM_IDS = 3, STREAM_MSG = 4, STREAM_PERLIN = 5 };
+
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t key) {
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {  // (0, 1), 53 bits
+  const uint64_t v = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);
+  return ((double)(v & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ double philox_normal(uint32_t entity, uint64_t step, uint32_t stream, uint64_t key) {
+  const uint4 r = philox4x32(entity, (uint32_t)step, (uint32_t)(step >> 32), stream, key);
+  const double u1 = u01(r.x, r.y), u2 = u01(r.z, r.w);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// ---------------------------------------------------------------------------------------
+// Calendar (proleptic Gregorian, naive datetime like the reference's `datetime` objects)
+// ---------------------------------------------------------------------------------------
+struct Calendar {
+  int year, month, day, yday;  // yday = tm_yday (1-based)
+  int hour, minute, second, sod;
+};
+
+__device__ __forceinline__ int64_t days_from_civil(int64_t y, int m, int d) {
+  y -= m <= 2;
+  const int64_t era = (y >= 0 ? y : y - 399) / 400;
+  const int64_t yoe = y - era * 400;
+  const int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + doe - 719468;
+}
+
+__device__ __forceinline__ Calendar calendar_from_epoch(int64_t t) {
+  Calendar c;
+  int64_t days = t / 86400;
+  int64_t rem = t - days * 86400;
+  if (rem < 0) { rem += 86400; days -= 1; }
+  c.sod = (int)rem;
+  c.hour = c.sod / 3600;
+  c.minute = (c.sod - c.hour * 3600) / 60;
+  c.second = c.sod - c.hour * 3600 - c.minute * 60;
+  const int64_t z = days + 719468;
+  const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  const int64_t doe = z - era * 146097;
+  const int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  const int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const int64_t mp = (5 * doy + 2) / 153;
+  c.day = (int)(doy - (153 * mp + 2) / 5 + 1);
+  c.month = (int)(mp < 10 ? mp + 3 : mp - 9);
+  const int64_t y = yoe + era * 400 + (c.month <= 2);
+  c.year = (int)y;
+  c.yday = (int)(days - days_from_civil(y, 1, 1)) + 1;
+  return c;
+}
+
+// utils.py:1277-1350 -- CIBSE solar cooling load polynomial, same term order.
+__device__ __forceinline__ double solar_gain(const Calendar& c, double window_area, double shading_coeff) {
+  const double x = c.hour + c.minute / 60.0 - 7.5;
+  double scl = 0.0;
+  if (!(x < 0 || x > 10)) {
+    const double y = c.month + c.day / 30.0 - 1;
+    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2, y2 = y * y, y3 = y2 * y, y4 = y2 * y2;
+    scl = 4.36579418e01 + x * 1.58055357e02 + y * 8.76635241e01 + x2 * -4.55944821e01 +
+          x2 * y * 3.24275366e00 + x2 * y2 * -4.56096472e-01 + y2 * -1.47795612e01 +
+          x * y2 * 4.68950855e00 + x * y * -3.73313090e01 + x3 * 5.78827663e00 + y3 * 1.04354810e00 +
+          x3 * y * 2.12969604e-02 + x3 * y2 * 2.58881400e-03 + x3 * y3 * -5.11397219e-04 +
+          x2 * y3 * 1.56398008e-02 + x * y3 * -1.18302764e-01 + x4 * -2.71446436e-01 + y4 * -3.97855577e-02;
+  }
+  return window_area * shading_coeff * scl;
+}
+
+// ---------------------------------------------------------------------------------------
+// 1-D perlin (production mode only; parity mode replays the host value).  Same construction
+// as utils.Perlin (utils.py:1231-1253) over perlin_noise.PerlinNoise: per octave o,
+//   n_o(x) = sum_{i in {floor(xo), floor(xo)+1}} fade(1-|xo-i|) * g_o(i) * (xo-i),  xo = x*octaves
+// with lattice gradients g_o(i) ~ U(-1,1) drawn from Philox instead of python's `random`.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double perlin_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
+
+__device__ __forceinline__ double perlin_octave(double x, int octaves, uint32_t oct_id, uint64_t key) {
+  const double xo = x * octaves;
+  const double f = floor(xo);
+  const int64_t i0 = (int64_t)f;
+  double v = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int64_t i = i0 + k;
+    const uint4 r = philox4x32((uint32_t)i, (uint32_t)((uint64_t)i >> 32), oct_id, STREAM_PERLIN, key);
+    const double g = 2.0 * u01(r.x, r.y) - 1.0;
+    const double d = xo - (double)i;
+    v += perlin_fade(1.0 - fabs(d)) * g * d;
+  }
+  return v;
+}
+
+__device__ __forceinline__ double perlin_noise(double x, int nb_octaves, int octaves_step, uint64_t key) {
+  double noise = 0.0;
+  for (int j = 0; j < nb_octaves - 1; ++j)
+    noise += perlin_octave(x, (1 << j) * octaves_step, (uint32_t)j, key) / (double)(1 << j);
+  noise += perlin_octave(x, (1 << (nb_octaves - 1)) * octaves_step, (uint32_t)(nb_octaves - 1), key) /
+           (double)((1 << nb_octaves) - 1);
+  return noise;
+}
+
+// ---------------------------------------------------------------------------------------
+// warp reductions (fixed shuffle tree => run-to-run deterministic)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// bulk (TMA) shared -> global store of a contiguous, 16-byte aligned tile (SASS: UBLKCP)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+}  // namespace mdr

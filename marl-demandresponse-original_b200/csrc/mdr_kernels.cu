@@ -1,0 +1,603 @@
+// Fused MADemandResponseEnv step for B200 (sm_100a): one CTA owns G whole envs (clusters),
+// one thread owns one house.  Replaces the Python object loops of
+//   ClusterHouses.step        env/MA_DemandResponse.py:1005-1055
+//   HVAC.step                 env/MA_DemandResponse.py:463-492
+//   SingleHouse.update_temperature  :664-738
+//   compute_rewards           :330-373
+//   PowerGrid.step            :1236-1316 (+ interpolatePower :1195-1234)
+//   make_cluster_obs_dict + normStateDict  :904-1003, utils.py:740-880
+// Phases inside the single launch (block barriers between them):
+//   A  per house : load packed state/coefficients (8/16-byte coalesced), lockout state machine,
+//                  2x2 affine ETP update, store state, stage message + power in shared memory
+//   B  per env   : one warp reduces the env's power (shuffle tree), lane 0 advances the clock,
+//                  draws/replays the outdoor temperature, evaluates the grid signal
+//   C/D (refresh steps only) per house multilinear table interpolation -> per env base power
+//   E  per house : reward, observation row assembled in a per-warp shared-memory tile from the
+//                  neighbours' staged messages, tile written with one bulk (TMA) store
+#include "mdr_kernels.h"
+
+#include <math.h>
+
+#include "mdr_device.cuh"
+
+namespace mdr {
+
+// ----------------------------------------------------------------------------------------
+struct EnvScratch {
+  double P, od_new, rew_sig, pen_mean, pen_max, hour_s, date;
+  double f_sig, f_pow, f_od, f_sin_day, f_cos_day, f_sin_hr, f_cos_hr, f_solar;
+  int due, pad;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// shared-memory carve-up (must match between host sizing and the kernel)
+struct SmemLayout {
+  size_t off_msg, off_pw, off_val, off_pen, off_env, off_stage, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarps, int rows_per_pass,
+                                                  int n_features, bool need_val, bool need_pen, bool has_obs) {
+  SmemLayout L;
+  size_t o = 0;
+  L.off_msg = o; o += align16((size_t)hmax * 4 * real_bytes);
+  L.off_pw = o;  o += align16((size_t)hmax * real_bytes);
+  L.off_val = o; o += need_val ? align16((size_t)hmax * sizeof(double)) : 0;
+  L.off_pen = o; o += need_pen ? align16((size_t)hmax * sizeof(double)) : 0;
+  L.off_env = o; o += align16((size_t)genvs_max * sizeof(EnvScratch));
+  L.off_stage = o;
+  o += has_obs ? align16((size_t)nwarps * rows_per_pass * n_features * real_bytes) : 0;
+  L.total = o;
+  return L;
+}
+
+// ----------------------------------------------------------------------------------------
+// multilinear interpolation, monteCarlo/interpolation.py:113-142 + scipy linear interpn.
+// `key` = (flat index over the 4 nearest thermal-ratio cells) * 16 + nearest HVAC-power index.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ double clip_axis(const KernelParams& p, int d, double v) {
+  const double lo = p.interp_axes[d][0], hi = p.interp_axes[d][p.interp_dims[d] - 1];
+  if (v > hi) v = hi;
+  else if (v < lo) v = lo;
+  return v;
+}
+
+template <typename R>
+__device__ __noinline__ double interp_eval(const KernelParams& p, int key, double air, double mass, double od,
+                                           double hour, double date) {
+  const int dims[5] = {4, 5, 6, 8, 9};
+  const double x[5] = {clip_axis(p, 4, air), clip_axis(p, 5, mass), clip_axis(p, 6, od), clip_axis(p, 8, hour),
+                       clip_axis(p, 9, date)};
+  int idx[5];
+  double w[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int d = dims[k];
+    const int n = p.interp_dims[d];
+    int i = 0;
+    for (int j = 1; j < n; ++j) i += (p.interp_axes[d][j] <= x[k]) ? 1 : 0;  // searchsorted(right) - 1
+    i = min(i, n - 2);
+    idx[k] = i;
+    w[k] = (x[k] - p.interp_axes[d][i]) / (p.interp_axes[d][i + 1] - p.interp_axes[d][i]);
+  }
+  const int therm = key >> 4, ih = key & 15;
+  const R* __restrict__ table = reinterpret_cast<const R*>(p.interp_table);
+  const int n4 = p.interp_dims[4], n5 = p.interp_dims[5], n6 = p.interp_dims[6], n7 = p.interp_dims[7],
+            n8 = p.interp_dims[8], n9 = p.interp_dims[9];
+  double value = 0.0;
+#pragma unroll 1
+  for (int c = 0; c < 32; ++c) {  // itertools.product order: first dimension slowest
+    const int b0 = (c >> 4) & 1, b1 = (c >> 3) & 1, b2 = (c >> 2) & 1, b3 = (c >> 1) & 1, b4 = c & 1;
+    double weight = 1.0;
+    weight = mul_rn(weight, b0 ? w[0] : 1.0 - w[0]);
+    weight = mul_rn(weight, b1 ? w[1] : 1.0 - w[1]);
+    weight = mul_rn(weight, b2 ? w[2] : 1.0 - w[2]);
+    weight = mul_rn(weight, b3 ? w[3] : 1.0 - w[3]);
+    weight = mul_rn(weight, b4 ? w[4] : 1.0 - w[4]);
+    size_t off = (size_t)therm;
+    off = off * n4 + (idx[0] + b0);
+    off = off * n5 + (idx[1] + b1);
+    off = off * n6 + (idx[2] + b2);
+    off = off * n7 + ih;
+    off = off * n8 + (idx[3] + b3);
+    off = off * n9 + (idx[4] + b4);
+    value = add_rn(value, mul_rn((double)__ldg(table + off), weight));
+  }
+  return value;
+}
+
+// PowerGrid.step signal shapes, env/MA_DemandResponse.py:1257-1314
+__device__ __forceinline__ double grid_signal(const KernelParams& p, double base, const Calendar& cal, double noise,
+                                              double ratio, double max_power) {
+  double sig;
+  const double two_pi = 2.0 * 3.141592653589793;
+  if (p.signal_mode == MDR_SIG_FLAT) {
+    sig = base;
+  } else if (p.signal_mode == MDR_SIG_SINUSOIDALS) {
+    const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
+    sig = base;
+    for (int i = 0; i < p.n_sinusoids; ++i) {
+      const double amp = mul_rn(base, p.sin_ratios[i]);
+      sig = add_rn(sig, mul_rn(amp, sin(mul_rn(two_pi, (double)time_sec) / p.sin_periods[i])));
+    }
+  } else if (p.signal_mode == MDR_SIG_REGULAR_STEPS) {
+    const double amplitude = p.steps_amplitude_per_hvac * p.N;
+    const double r = base / amplitude;
+    const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
+    const double arg = fmod((double)time_sec, p.steps_period) - mul_rn(1.0 - r, p.steps_period);
+    sig = amplitude * (arg >= 0.0 ? 1.0 : 0.0);  // np.heaviside(arg, 1)
+  } else {                                         // perlin family
+    sig = fmax(0.0, add_rn(base, mul_rn(mul_rn(base, p.perlin_amplitude), noise)));
+  }
+  sig = mul_rn(sig, ratio);
+  return fmin(sig, max_power);
+}
+
+// ----------------------------------------------------------------------------------------
+// precompute: per-house derived coefficients (reset-time, fp64 math)
+// ----------------------------------------------------------------------------------------
+template <typename R>
+__global__ void precompute_kernel(const __grid_constant__ KernelParams p) {
+  using T2 = typename Vec<R>::T2;
+  using T4 = typename Vec<R>::T4;
+  const size_t h = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= (size_t)p.E * p.N) return;
+  const double ua = p.ua[h], cm = p.cm[h], ca = p.ca[h], hm = p.hm[h], cap = p.cap[h];
+  const double dt = (double)p.dt;
+  // env/MA_DemandResponse.py:704-711
+  const double a = cm * ca / hm;
+  const double b = cm * (ua + hm) / hm + ca;
+  const double c = ua;
+  const double disc = sqrt(b * b - 4.0 * a * c);
+  const double r1 = (-b + disc) / (2.0 * a);
+  const double r2 = (-b - disc) / (2.0 * a);
+  // :722-723
+  const double A3 = r1 * ca / hm + (ua + hm) / hm;
+  const double A4 = r2 * ca / hm + (ua + hm) / hm;
+  // x = T_air - T_ss, y = T_mass - T_ss with T_ss = T_od + Q_a/Ua (= d/c, :707) turns :713-735 into
+  //   x' = x*e2 + A1*(e1-e2),  y' = x*A4*e2 + A1*(A3*e1 - A4*e2),  A1 = (s*x - (Hm/Ca)*y)/(r2-r1)
+  const double em1 = expm1(r1 * dt), em2 = expm1(r2 * dt);
+  const double e1 = em1 + 1.0, e2 = em2 + 1.0;
+  const double s = r2 + (ua + hm) / ca;
+  const double k = (em1 - em2) / (r2 - r1);
+  const double kk = (A3 * e1 - A4 * e2) / (r2 - r1);
+  const double d11 = em2 + k * s;
+  const double m12 = -k * hm / ca;
+  const double m21 = A4 * e2 + kk * s;
+  const double d22 = -kk * hm / ca - 1.0;
+  reinterpret_cast<T4*>(p.coef_a)[h] = make4((R)d11, (R)m12, (R)m21, (R)d22);
+  // HVAC.get_Q :505, HVAC.max_consumption :436
+  const double q_on = -1.0 * cap / (1.0 + p.hvac_latent);
+  const double p_on = cap / p.hvac_cop;
+  reinterpret_cast<T4*>(p.coef_b)[h] = make4((R)(1.0 / ua), (R)q_on, (R)p_on, (R)p.target[h]);
+  reinterpret_cast<T2*>(p.coef_c)[h] = make2((R)p.deadband[h], (R)p.lockout_dur[h]);
+  // nearest cell of the interpolation table on the 4 thermal ratios and the HVAC power,
+  // monteCarlo/interpolation.py:120-133 after utils.clipInterpolationPoint
+  if (p.interp_key != nullptr) {
+    const double v[4] = {ua / p.def_ua, cm / p.def_cm, ca / p.def_ca, hm / p.def_hm};
+    int key = 0;
+    for (int d = 0; d < 4; ++d) {
+      const double x = clip_axis(p, d, v[d]);
+      int best = 0;
+      double bd = fabs(p.interp_axes[d][0] - x);
+      for (int j = 1; j < p.interp_dims[d]; ++j) {
+        const double dist = fabs(p.interp_axes[d][j] - x);
+        if (dist < bd) { bd = dist; best = j; }
+      }
+      key = key * p.interp_dims[d] + best;
+    }
+    const double x = clip_axis(p, 7, cap);
+    int best = 0;
+    double bd = fabs(p.interp_axes[7][0] - x);
+    for (int j = 1; j < p.interp_dims[7]; ++j) {
+      const double dist = fabs(p.interp_axes[7][j] - x);
+      if (dist < bd) { bd = dist; best = j; }
+    }
+    p.interp_key[h] = key * 16 + best;
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// the fused step kernel
+// ----------------------------------------------------------------------------------------
+template <typename R, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(const __grid_constant__ KernelParams p) {
+  using T2 = typename Vec<R>::T2;
+  using T4 = typename Vec<R>::T4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int N = p.N;
+  const int env0 = blockIdx.x * p.G;
+  const int genvs = min(p.G, p.E - env0);
+  const int H = genvs * N;
+  const bool active = tid < H;
+  const int le = active ? tid / N : 0;
+  const int li = tid - le * N;
+  const int e = env0 + le;
+  const size_t h = (size_t)env0 * N + tid;
+  const bool reset = p.is_reset != 0;          // 1 = reset (grid step + obs), 2 = observe only
+  const bool observe_only = p.is_reset == 2;
+  const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
+  const bool need_pen = p.temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2;
+
+  const SmemLayout L = smem_layout((int)sizeof(R), p.hmax, p.G, nwarps, p.rows_per_pass, p.F, interp_mode, need_pen,
+                                   p.obs != nullptr);
+  T4* s_msg = reinterpret_cast<T4*>(smem_raw + L.off_msg);
+  R* s_pw = reinterpret_cast<R*>(smem_raw + L.off_pw);
+  double* s_val = reinterpret_cast<double*>(smem_raw + L.off_val);
+  double* s_pen = reinterpret_cast<double*>(smem_raw + L.off_pen);
+  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + L.off_env);
+  R* s_stage = reinterpret_cast<R*>(smem_raw + L.off_stage);
+
+  // ---------------- phase A: per house -------------------------------------------------
+  R ta = 0, tm = 0, target = 0, deadband = 0, lockdur_r = 1, p_on = 0, pen = 0;
+  int on = 0, lock = 0, sso = 0;
+  int any_due = 0;
+  if (active) {
+    T2 tt = reinterpret_cast<const T2*>(p.temps)[h];
+    const int hv = p.hvac[h];
+    const T4 cb = reinterpret_cast<const T4*>(p.coef_b)[h];
+    const T2 cc = reinterpret_cast<const T2*>(p.coef_c)[h];
+    target = cb.w;
+    p_on = cb.z;
+    deadband = cc.x;
+    lockdur_r = cc.y;
+    on = hv & 1;
+    lock = (hv >> 1) & 1;
+    sso = hv >> 2;
+    if (!reset) {
+      const T4 ca4 = reinterpret_cast<const T4*>(p.coef_a)[h];
+      int cmd;
+      if (p.action_source == MDR_ACT_ARRAY) {
+        cmd = p.actions[h] != 0;
+      } else if (p.action_source == MDR_ACT_BANGBANG) {
+        cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61 on the previous observation
+      } else {
+        cmd = philox4x32((uint32_t)h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
+      }
+      // HVAC.step, :475-492
+      const int dt = p.dt;
+      const int lockdur = (int)lockdur_r;
+      if (!on) sso += dt;
+      lock = !(on || sso >= lockdur);
+      const int new_on = lock ? 0 : cmd;
+      if (!lock && new_on) sso = 0;
+      if (!lock && !new_on && sso + dt < lockdur) lock = 1;
+      on = new_on;
+      // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature
+      const R od_old = (R)p.od_temp[e];
+      const R gain = p.solar ? (R)p.solar_next[e] : (R)0;
+      const R qa = (on ? cb.y : (R)0) + gain;
+      const R tss = od_old + qa * cb.x;
+      const R x = tt.x - tss, y = tt.y - tss;
+      tt.x = tt.x + (ca4.x * x + ca4.y * y);
+      tt.y = tt.y + (ca4.z * x + ca4.w * y);
+      reinterpret_cast<T2*>(p.temps)[h] = tt;
+      p.hvac[h] = (sso << 2) | (lock << 1) | on;
+    }
+    ta = tt.x;
+    tm = tt.y;
+    const R pw = on ? p_on : (R)0;
+    s_pw[tid] = pw;
+    const R inv_norm = (R)p.inv_norm_reg_sig;
+    s_msg[tid] = make4((ta - target) * (R)0.2, (R)sso, pw * inv_norm, p_on * inv_norm);
+    // utils.deadbandL2, utils.py:1266-1274
+    const R hi = target + deadband / 2, lo = target - deadband / 2;
+    if (hi < ta) pen = (ta - hi) * (ta - hi);
+    else if (lo > ta) pen = (lo - ta) * (lo - ta);
+    else pen = 0;
+    if (need_pen) s_pen[tid] = (double)pen;
+    if (interp_mode && !observe_only) any_due = (p.time_since_interp[e] + p.dt >= p.interp_update_period);
+  }
+  if (interp_mode) any_due = __syncthreads_or(any_due);
+  else __syncthreads();
+
+  // ---------------- phase B: per env (one warp each) ------------------------------------
+  for (int le2 = warp; le2 < genvs; le2 += nwarps) {
+    const int e2 = env0 + le2;
+    double acc = 0.0;
+    for (int i = lane; i < N; i += 32) acc += (double)s_pw[le2 * N + i];
+    acc = warp_sum(acc);
+    double pmean = 0.0, pmax = 0.0;
+    if (need_pen) {
+      for (int i = lane; i < N; i += 32) {
+        const double v = s_pen[le2 * N + i];
+        pmean += v / N;
+        pmax = fmax(pmax, v);
+      }
+      pmean = warp_sum(pmean);
+      pmax = warp_max(pmax);
+    }
+    if (lane == 0) {
+      EnvScratch& es = s_env[le2];
+      int64_t t = p.t_epoch[e2];
+      if (!reset) t += p.dt;
+      const Calendar cal = calendar_from_epoch(t);
+      const double s_old = p.signal[e2];
+      double od_new = p.od_temp[e2];
+      if (!reset) {
+        // ClusterHouses.compute_OD_temp, :1070-1081
+        const double noise = p.od_noise ? p.od_noise[e2]
+                                        : p.temp_std * philox_normal((uint32_t)e2, p.step_index, STREAM_OD, p.seed);
+        const double amplitude = (p.day_temp - p.night_temp) / 2, bias = (p.day_temp + p.night_temp) / 2;
+        const double delay = -6 + p.phase[e2];
+        const double time_day = cal.hour + cal.minute / 60.0;
+        od_new = amplitude * sin(2 * 3.141592653589793 * (time_day + delay) / 24) + bias;
+        od_new += noise;
+        p.od_temp[e2] = od_new;
+        p.t_epoch[e2] = t;
+      }
+      es.P = acc;
+      es.od_new = od_new;
+      es.pen_mean = pmean;
+      es.pen_max = pmax;
+      es.f_pow = acc * p.inv_norm_sig_agents;
+      es.f_od = (od_new - 20) / 5;
+      if (p.state_flags & MDR_STATE_DAY) {
+        es.f_sin_day = sin(cal.yday * 2 * 3.141592653589793 / 365);
+        es.f_cos_day = cos(cal.yday * 2 * 3.141592653589793 / 365);
+      }
+      if (p.state_flags & MDR_STATE_HOUR) {
+        es.f_sin_hr = sin(cal.hour * 2 * 3.141592653589793 / 24);
+        es.f_cos_hr = cos(cal.hour * 2 * 3.141592653589793 / 24);
+      }
+      es.due = 0;
+      if (observe_only) {
+        es.f_solar = p.solar ? p.solar_gain[e2] / 1000 : 0.0;
+        es.f_sig = s_old * p.inv_norm_sig_agents;
+        continue;
+      }
+      // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
+      const double sp = ((acc - s_old) / N) * ((acc - s_old) / N);
+      es.rew_sig = p.alpha_sig * sp / p.norm_sig_penalty;
+      p.cluster_power[e2] = acc;
+      // solar gain of this step (for the obs) and of the next one (for the next update)
+      double gain_now = 0.0;
+      if (p.solar) {
+        gain_now = reset ? 0.0 : p.solar_next[e2];
+        Calendar nxt = calendar_from_epoch(t + p.dt);
+        p.solar_next[e2] = solar_gain(nxt, p.window_area, p.shading_coeff);
+        p.solar_gain[e2] = gain_now;
+      }
+      es.f_solar = gain_now / 1000;
+      if (p.solar) {  // interpolatePower point, :1198-1207
+        es.hour_s = (double)cal.sod;
+        es.date = (double)cal.yday;
+      } else {
+        es.hour_s = 0.0;
+        es.date = 0.0;
+      }
+      int due = 0;
+      double base = p.avg_power_per_hvac * N;  // PowerGrid.step :1248-1249
+      if (interp_mode) {
+        const int tsi = p.time_since_interp[e2] + p.dt;
+        due = tsi >= p.interp_update_period;
+        base = p.base_power[e2];
+        if (!due) p.time_since_interp[e2] = tsi;
+      }
+      es.due = due;
+      if (!due) {
+        double noise = 0.0;
+        if (p.signal_mode == MDR_SIG_PERLIN)
+          noise = p.signal_noise ? p.signal_noise[e2]
+                                 : perlin_noise((double)cal.sod / p.perlin_period, p.perlin_nb_octaves,
+                                                p.perlin_octaves_step, p.seed ^ __double_as_longlong(p.perlin_seed[e2]));
+        const double sig = grid_signal(p, base, cal, noise, p.artificial_ratio[e2], p.max_power[e2]);
+        p.base_power[e2] = base;
+        p.signal[e2] = sig;
+        es.f_sig = sig * p.inv_norm_sig_agents;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phases C/D: interpolation refresh (every interp_update_period) -------
+  if (any_due) {
+    const int nb = p.interp_nb_agents;
+    const int nsamp = N <= nb ? N : nb;
+    if (active && s_env[le].due && li < nsamp) {
+      int src = li;
+      if (N > nb) {
+        if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
+        else {
+          const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                                     STREAM_IDS + 16 * (uint32_t)li, p.seed);
+          src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
+        }
+      }
+      const size_t hs = (size_t)e * N + src;
+      const T2 t2 = reinterpret_cast<const T2*>(p.temps)[hs];
+      const double tg = (double)reinterpret_cast<const T4*>(p.coef_b)[hs].w;
+      const EnvScratch& es = s_env[le];
+      s_val[tid] = interp_eval<R>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, es.od_new - tg, es.hour_s,
+                                  es.date);
+    }
+    __syncthreads();
+    for (int le2 = warp; le2 < genvs; le2 += nwarps) {
+      EnvScratch& es = s_env[le2];
+      if (lane == 0 && es.due) {
+        const int e2 = env0 + le2;
+        double base = 0.0;
+        for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le2 * N + i]);  // id order, :1218-1232
+        if (N > nb) base = mul_rn(base, (double)N / (double)nb);
+        const Calendar cal = calendar_from_epoch(p.t_epoch[e2]);
+        double noise = 0.0;
+        if (p.signal_mode == MDR_SIG_PERLIN)
+          noise = p.signal_noise ? p.signal_noise[e2]
+                                 : perlin_noise((double)cal.sod / p.perlin_period, p.perlin_nb_octaves,
+                                                p.perlin_octaves_step, p.seed ^ __double_as_longlong(p.perlin_seed[e2]));
+        const double sig = grid_signal(p, base, cal, noise, p.artificial_ratio[e2], p.max_power[e2]);
+        p.base_power[e2] = base;
+        p.time_since_interp[e2] = 0;
+        p.signal[e2] = sig;
+        es.f_sig = sig * p.inv_norm_sig_agents;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---------------- phase E: reward + observation ----------------------------------------
+  if (active && !reset && p.reward != nullptr) {
+    const EnvScratch& es = s_env[le];
+    double tp = (double)pen;
+    if (p.temp_penalty_mode == MDR_PEN_COMMON_L2) tp = es.pen_mean;
+    else if (p.temp_penalty_mode == MDR_PEN_COMMON_MAX) tp = es.pen_max;
+    else if (p.temp_penalty_mode == MDR_PEN_MIXTURE)
+      tp = (p.mix_alpha_ind * tp + p.mix_alpha_common * es.pen_mean + p.mix_alpha_max * es.pen_max) /
+           (p.mix_alpha_ind + p.mix_alpha_common + p.mix_alpha_max);
+    reinterpret_cast<R*>(p.reward)[h] = (R)(-1.0 * (p.alpha_temp * tp / p.norm_temp_penalty + es.rew_sig));
+  }
+
+  if (p.obs == nullptr) return;
+  const int F = p.F, C = p.C;
+  const int rpp = p.rows_per_pass;
+  R* stage = s_stage + (size_t)warp * rpp * F;
+  const int wrow0 = warp * 32;
+  const int nrows_w = max(0, min(32, H - wrow0));
+  R* gobs = reinterpret_cast<R*>(p.obs) + ((size_t)env0 * N + wrow0) * F;
+  bool issued = false;
+  for (int pass0 = 0; pass0 < nrows_w; pass0 += rpp) {
+    const int nr = min(rpp, nrows_w - pass0);
+    if (lane >= pass0 && lane < pass0 + nr) {
+      const EnvScratch& es = s_env[le];
+      R* row = stage + (size_t)(lane - pass0) * F;
+      const R inv_lock = (R)1 / lockdur_r;
+      int c = 0;
+      // own features, utils.normStateDict order (utils.py:774-840)
+      row[c++] = (ta - 20) * (R)0.2;
+      row[c++] = (tm - 20) * (R)0.2;
+      row[c++] = (target - 20) * (R)0.2;
+      if (p.state_flags & MDR_STATE_THERMAL) row[c++] = (R)es.f_od;
+      row[c++] = deadband;
+      if (p.state_flags & MDR_STATE_DAY) { row[c++] = (R)es.f_sin_day; row[c++] = (R)es.f_cos_day; }
+      if (p.state_flags & MDR_STATE_HOUR) { row[c++] = (R)es.f_sin_hr; row[c++] = (R)es.f_cos_hr; }
+      if (p.state_flags & MDR_STATE_SOLAR) row[c++] = (R)es.f_solar;
+      row[c++] = p_on * (R)p.cop_over_def_cap;
+      if (p.state_flags & MDR_STATE_THERMAL) {
+        row[c++] = (R)(p.ua[h] / p.def_ua);
+        row[c++] = (R)(p.cm[h] / p.def_cm);
+        row[c++] = (R)(p.ca[h] / p.def_ca);
+        row[c++] = (R)(p.hm[h] / p.def_hm);
+      }
+      if (p.state_flags & MDR_STATE_HVAC) {
+        row[c++] = (R)(p.hvac_cop / p.def_cop);
+        row[c++] = (R)(p.hvac_latent / p.def_latent);
+      }
+      row[c++] = (R)on;
+      row[c++] = (R)lock;
+      row[c++] = (R)sso * inv_lock;
+      row[c++] = (R)1;
+      row[c++] = (R)es.f_sig;
+      row[c++] = (R)es.f_pow;
+      // messages, SingleHouse.message :624-662 normalised as utils.py:842-868
+      const int half = C >> 1;
+      for (int k = 0; k < C; ++k) {
+        int j;
+        if (p.comm_mode == MDR_COMM_NEIGHBOURS) {  // :816-828
+          j = k < half ? li - half + k : li + 1 + (k - half);
+          if (j < 0) j += N;
+          if (j >= N) j -= N;
+        } else {
+          const size_t base = p.comm_mode == MDR_COMM_TABLE_PER_ENV ? (size_t)e * N * C : 0;
+          j = p.comm_table[base + (size_t)li * C + k];
+        }
+        T4 m = s_msg[le * N + j];
+        bool keep = true;
+        if (p.msg_keep) keep = p.msg_keep[h * C + k] != 0;
+        else if (p.comm_defect_prob > 0.0) {
+          const uint4 r = philox4x32((uint32_t)h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                                     STREAM_MSG + 16 * (uint32_t)k, p.seed);
+          keep = u01(r.x, r.y) > p.comm_defect_prob;
+        }
+        const R kf = keep ? (R)1 : (R)0;
+        row[c++] = m.x * kf;
+        row[c++] = m.y * inv_lock * kf;
+        row[c++] = m.z * kf;
+        row[c++] = m.w * kf;
+        if (p.msg_flags) {
+          const size_t hj = (size_t)e * N + j;
+          if (p.msg_flags & MDR_MSG_THERMAL) {
+            row[c++] = (R)(p.ua[hj] / p.def_ua) * kf;
+            row[c++] = (R)(p.cm[hj] / p.def_cm) * kf;
+            row[c++] = (R)(p.ca[hj] / p.def_ca) * kf;
+            row[c++] = (R)(p.hm[hj] / p.def_hm) * kf;
+          }
+          if (p.msg_flags & MDR_MSG_HVAC) {
+            row[c++] = (R)(p.hvac_cop / p.def_cop) * kf;
+            row[c++] = (R)(p.hvac_latent / p.def_latent) * kf;
+            row[c++] = (R)(p.cap[hj] / p.def_cap) * kf;
+          }
+        }
+      }
+    }
+    R* dst = gobs + (size_t)pass0 * F;
+    const uint32_t bytes = (uint32_t)(nr * F * sizeof(R));
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
+    if (bulk_ok) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_store_s2g(dst, stage, bytes);
+      issued = true;
+      if (pass0 + rpp < nrows_w) {
+        if (lane == 0) bulk_wait_read_all();
+        __syncwarp();
+      }
+    } else {
+      __syncwarp();
+      for (int i = lane; i < nr * F; i += 32) dst[i] = stage[i];
+      __syncwarp();
+    }
+  }
+  if (issued && lane == 0) bulk_wait_read_all();
+}
+
+// ----------------------------------------------------------------------------------------
+// host-side launch helpers
+// ----------------------------------------------------------------------------------------
+template <typename R>
+static cudaError_t launch_precompute(const KernelParams& kp, cudaStream_t stream) {
+  const size_t total = (size_t)kp.E * kp.N;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  precompute_kernel<R><<<blocks, threads, 0, stream>>>(kp);
+  return cudaGetLastError();
+}
+
+template <typename R, int kMaxThreads>
+static cudaError_t launch_step_t(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaError_t err = cudaFuncSetAttribute(step_kernel<R, kMaxThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           MDR_MAX_SMEM_BYTES);
+    if (err != cudaSuccess) return err;
+    attr_set[dev] = true;
+  }
+  step_kernel<R, kMaxThreads><<<g.ctas, g.threads, g.smem_bytes, stream>>>(kp);
+  return cudaGetLastError();
+}
+
+template <typename R>
+static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  if (g.threads <= 256) return launch_step_t<R, 256>(kp, g, stream);
+  if (g.threads <= 512) return launch_step_t<R, 512>(kp, g, stream);
+  return launch_step_t<R, 1024>(kp, g, stream);
+}
+
+cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream) {
+  return precision == MDR_F32 ? launch_precompute<float>(kp, stream) : launch_precompute<double>(kp, stream);
+}
+
+cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream) {
+  return precision == MDR_F32 ? launch_step_r<float>(kp, g, stream) : launch_step_r<double>(kp, g, stream);
+}
+
+size_t step_smem_bytes(int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass, int n_features, bool need_val,
+                       bool need_pen, bool has_obs) {
+  return smem_layout(real_bytes, hmax, genvs, nwarps, rows_per_pass, n_features, need_val, need_pen, has_obs).total;
+}
+
+}  // namespace mdr

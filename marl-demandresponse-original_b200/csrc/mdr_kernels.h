@@ -1,0 +1,64 @@
+// Internal interface between the C ABI (mdr_abi.cu) and the kernels (mdr_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mdr_b200.h"
+
+#define MDR_MAX_SMEM_BYTES (227 * 1024)
+
+namespace mdr {
+
+// Everything the kernels need, passed by value as the kernel parameter (constant bank).
+struct KernelParams {
+  // shape / geometry
+  int E, N, C, F, G, hmax, rows_per_pass, dt;
+  int is_reset, comm_mode, state_flags, msg_flags, temp_penalty_mode, solar, base_power_mode, signal_mode;
+  int n_sinusoids, interp_update_period, interp_nb_agents, perlin_nb_octaves, perlin_octaves_step, action_source;
+  // per-house arrays
+  const double *ua, *cm, *ca, *hm, *cap, *target, *deadband;
+  const int32_t* lockout_dur;
+  void *coef_a, *coef_b, *coef_c;
+  int32_t* interp_key;
+  void* temps;
+  int32_t* hvac;
+  // per-env arrays
+  int64_t* t_epoch;
+  const double* phase;
+  double *od_temp, *solar_gain, *solar_next;
+  const double *artificial_ratio, *max_power;
+  double *base_power, *signal, *cluster_power;
+  int32_t* time_since_interp;
+  const double* perlin_seed;
+  // step inputs / outputs
+  const uint8_t* actions;
+  const double *od_noise, *signal_noise;
+  const int32_t* interp_ids;
+  const uint8_t* msg_keep;
+  const int32_t* comm_table;
+  const void* interp_table;
+  void *obs, *reward;
+  uint64_t step_index, seed;
+  // scalars
+  double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
+  double inv_norm_reg_sig, inv_norm_sig_agents, cop_over_def_cap;
+  double def_ua, def_cm, def_ca, def_hm, def_cop, def_latent, def_cap, hvac_cop, hvac_latent;
+  double day_temp, night_temp, temp_std, window_area, shading_coeff, avg_power_per_hvac;
+  double sin_periods[MDR_MAX_SINUSOIDS], sin_ratios[MDR_MAX_SINUSOIDS];
+  double steps_amplitude_per_hvac, steps_period, perlin_amplitude, perlin_period, comm_defect_prob;
+  int interp_dims[MDR_INTERP_DIMS];
+  double interp_axes[MDR_INTERP_DIMS][MDR_INTERP_MAX_AXIS];
+};
+
+struct Geometry {
+  int envs_per_cta, threads, ctas, rows_per_pass, hmax;
+  size_t smem_bytes;
+};
+
+size_t step_smem_bytes(int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass, int n_features, bool need_val,
+                       bool need_pen, bool has_obs);
+cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);
+cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream);
+
+}  // namespace mdr

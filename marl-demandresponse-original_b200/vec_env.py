@@ -1,0 +1,348 @@
+"""Tensor fast path: E independent clusters x N houses resident in HBM, stepped by one fused
+CUDA kernel per time step through the C ABI (include/mdr_b200.h).
+
+``reset_tensor() -> obs[E, N, F]`` and
+``step_tensor(actions[E, N]) -> (obs[E, N, F], reward[E, N], power[E], signal[E])``
+are the batched generalisation of ``MADemandResponseEnv.reset/step``
+(env/MA_DemandResponse.py:135-210) with the observation already normalised like
+``utils.normStateDict`` (utils.py:740-880).  All returned tensors are CUDA tensors owned by
+the environment and overwritten by the next call; nothing synchronises the host.
+
+PyTorch is used for device memory and streams only; every per-step computation happens in
+``csrc/mdr_kernels.cu``.  There is no CPU fallback.
+"""
+import copy
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config_flatten import FlatConfig
+from .default_config import INTERP_KEYS
+
+_PRECISIONS = {"fp32": (_lib.F32, torch.float32), "fp64": (_lib.F64, torch.float64),
+               "f32": (_lib.F32, torch.float32), "f64": (_lib.F64, torch.float64)}
+TABLE_SIZE = 4199040
+
+
+def load_interp_table(flat: FlatConfig):
+    """np.load of power_grid_prop.base_power_parameters.interpolation.path_datafile
+    (monteCarlo/interpolation.py:40); the blob is not shipped with the reference."""
+    path = flat.interp_paths["path_datafile"]
+    if not os.path.isfile(path):
+        raise FileNotFoundError(
+            "interpolation table %r not found (the reference lists it in .MISSING_LARGE_BLOBS); pass "
+            "interp_table=... or use base_power_mode='constant'" % path)
+    return np.load(path)
+
+
+class VecDemandResponseEnv:
+    def __init__(self, config, population, *, precision="fp32", device=None, interp_table=None, seed=0,
+                 action_source="array", comm_table=None, test=False, with_obs=True):
+        if not torch.cuda.is_available():
+            raise _lib.MdrError("a CUDA device is required: this environment has no CPU fallback")
+        self.lib = _lib.load()
+        self.flat = config if isinstance(config, FlatConfig) else FlatConfig(config, test=test)
+        self.precision_name = precision
+        self.precision, self.dtype = _PRECISIONS[precision]
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.seed, self.action_source, self.with_obs = int(seed), action_source, bool(with_obs)
+        self.n_envs = int(len(np.atleast_1d(population["t_epoch"])))
+        self.n_houses = self.flat.n_houses
+        self.n_comm = self.flat.n_comm
+        self.n_features = self.flat.obs_width()
+        self.step_index = 0
+        self._keep = []  # replay tensors referenced by the last launch
+        self._comm = None
+        self._per_env_table = False
+        if comm_table is None:
+            comm_table = self.flat.explicit_comm_table() if self.flat.comm_mode_name != "random_fixed" else None
+        self._alloc()
+        self.load_population(population)
+        if comm_table is not None:
+            self.set_comm_table(comm_table)
+        self._table = None
+        if self.flat.base_power_mode == _lib.BASE["interpolation"]:
+            if interp_table is None:
+                interp_table = load_interp_table(self.flat)
+            self.set_interp_table(interp_table)
+        self._build_structs()
+
+    # ------------------------------------------------------------------ memory
+    def _alloc(self):
+        e, n, dev, r = self.n_envs, self.n_houses, self.device, self.dtype
+        f64, i32 = torch.float64, torch.int32
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
+        self.raw = {k: z(e, n, dtype=f64) for k in ("ua", "cm", "ca", "hm", "cap", "target", "deadband")}
+        self.lockout_dur = z(e, n, dtype=i32)
+        self.coef_a, self.coef_b, self.coef_c = z(e, n, 4, dtype=r), z(e, n, 4, dtype=r), z(e, n, 2, dtype=r)
+        self.interp_key = z(e, n, dtype=i32)
+        self.temps = z(e, n, 2, dtype=r)
+        self.hvac = z(e, n, dtype=i32)
+        self.env = {k: z(e, dtype=f64) for k in ("phase", "od_temp", "solar_gain", "solar_next", "artificial_ratio",
+                                                "max_power", "base_power", "signal", "cluster_power", "perlin_seed")}
+        self.t_epoch = z(e, dtype=torch.int64)
+        self.time_since_interp = z(e, dtype=i32)
+        self.actions = z(e, n, dtype=torch.uint8)
+        self.obs = z(e, n, self.n_features, dtype=r) if self.with_obs else None
+        self.reward = z(e, n, dtype=r)
+        self._pinned = None
+
+    def load_population(self, pop):
+        """Uploads a population dict (see population.py) and resets the step counter."""
+        e, n, dev = self.n_envs, self.n_houses, self.device
+
+        def house(key, dtype):
+            a = np.asarray(pop[key]).reshape(e, n)
+            return torch.as_tensor(np.ascontiguousarray(a)).to(device=dev, dtype=dtype)
+
+        def env(key, dtype):
+            a = np.asarray(pop[key]).reshape(e)
+            return torch.as_tensor(np.ascontiguousarray(a)).to(device=dev, dtype=dtype)
+
+        for k in self.raw:
+            self.raw[k].copy_(house(k, torch.float64))
+        self.lockout_dur.copy_(house("lockout_dur", torch.int32))
+        self.temps[..., 0].copy_(house("t_air", self.dtype))
+        self.temps[..., 1].copy_(house("t_mass", self.dtype))
+        sso, on, lock = house("sso", torch.int32), house("on", torch.int32), house("lockout", torch.int32)
+        self.hvac.copy_((sso << 2) | ((lock != 0).int() << 1) | (on != 0).int())
+        for k in self.env:
+            if k == "solar_next":
+                continue
+            if k in pop:
+                self.env[k].copy_(env(k, torch.float64))
+        self.t_epoch.copy_(env("t_epoch", torch.int64))
+        self.time_since_interp.copy_(env("time_since_interp", torch.int32))
+        self.step_index = 0
+        self._precomputed = False
+
+    def set_comm_table(self, table):
+        """int32 [N, C] shared by all envs, or [E, N, C] per env (random_fixed / random_sample)."""
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(table, dtype=np.int32))).to(self.device)
+        if t.dim() == 3:
+            if t.shape != (self.n_envs, self.n_houses, self.n_comm):
+                raise ValueError("per-env comm table must be [E, N, C]")
+            self._per_env_table = True
+        elif t.shape != (self.n_houses, self.n_comm):
+            raise ValueError("comm table must be [N, C] = [%d, %d], got %s" % (self.n_houses, self.n_comm, tuple(t.shape)))
+        else:
+            self._per_env_table = False
+        self._comm = t.contiguous()
+        if hasattr(self, "cfg"):
+            self._build_structs()
+
+    def set_interp_table(self, table):
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(table).reshape(-1)))
+        expect = int(np.prod([len(self.flat.interp_grid[k]) for k in INTERP_KEYS]))
+        if t.numel() != expect:
+            raise ValueError("interpolation table has %d entries, the grid needs %d" % (t.numel(), expect))
+        self._table = t.to(device=self.device, dtype=self.dtype).contiguous()
+
+    # ------------------------------------------------------------------ C structs
+    def _build_structs(self):
+        self.cfg = self.flat.to_struct(self.n_envs, self.precision, self.device.index, self.seed, self.action_source,
+                                       per_env_table=self._per_env_table)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        h = _lib.MdrHouses()
+        for k in ("ua", "cm", "ca", "hm", "cap", "target", "deadband"):
+            setattr(h, k, p(self.raw[k]))
+        h.lockout_dur, h.coef_a, h.coef_b, h.coef_c = p(self.lockout_dur), p(self.coef_a), p(self.coef_b), p(self.coef_c)
+        h.interp_key, h.temps, h.hvac = p(self.interp_key), p(self.temps), p(self.hvac)
+        self.houses_s = h
+        e = _lib.MdrEnvs()
+        e.t_epoch, e.time_since_interp = p(self.t_epoch), p(self.time_since_interp)
+        for k in self.env:
+            setattr(e, k, p(self.env[k]))
+        e.metrics = None
+        self.envs_s = e
+        self.in_s = _lib.MdrStepInputs()
+        self.out_s = _lib.MdrOutputs()
+        self.out_s.obs, self.out_s.reward = p(self.obs), p(self.reward)
+        self._refs = (C.byref(self.cfg), C.byref(self.houses_s), C.byref(self.envs_s), C.byref(self.in_s),
+                      C.byref(self.out_s))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, x, dtype, shape=None):
+        if x is None:
+            return None
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.asarray(x)))
+        t = t.to(device=self.device, dtype=dtype).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            t = t.reshape(shape)
+        return t
+
+    def _set_inputs(self, actions=None, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None, comm=None):
+        e, n, c = self.n_envs, self.n_houses, self.n_comm
+        if actions is not None:
+            if isinstance(actions, torch.Tensor) and actions.dtype == torch.uint8 and actions.is_contiguous() \
+                    and actions.device == self.device and actions.numel() == e * n:
+                act = actions
+            else:
+                a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+                act = (a.to(self.device) != 0).to(torch.uint8).reshape(e, n).contiguous()
+        else:
+            act = self.actions
+        od = self._dev(od_noise, torch.float64, (e,))
+        sn = self._dev(signal_noise, torch.float64, (e,))
+        ids = self._dev(interp_ids, torch.int32, (e, self.flat.interp_nb_agents))
+        mk = self._dev(msg_keep, torch.uint8, (e, n, c))
+        cm = self._dev(comm, torch.int32)
+        if cm is None:
+            cm = self._comm
+        elif cm.dim() == 2 and self._per_env_table:
+            cm = cm.expand(e, n, c).contiguous()
+        self._keep = [act, od, sn, ids, mk, cm, self._table]
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        s = self.in_s
+        s.actions, s.od_noise, s.signal_noise, s.interp_ids = p(act), p(od), p(sn), p(ids)
+        s.msg_keep, s.comm_table, s.interp_table = p(mk), p(cm), p(self._table)
+        s.step_index = self.step_index
+
+    # ------------------------------------------------------------------ API
+    def precompute(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mdr_precompute(self._refs[0], self._refs[1], self._stream()), "mdr_precompute")
+        self._precomputed = True
+
+    def reset_tensor(self, *, signal_noise=None, interp_ids=None, msg_keep=None, comm=None):
+        """Initial grid signal + initial observation for the loaded population
+        (MADemandResponseEnv.build_environment tail :133 and reset :163-172)."""
+        self.precompute()
+        self._set_inputs(None, None, signal_noise, interp_ids, msg_keep, comm)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mdr_reset(*self._refs, self._stream()), "mdr_reset")
+        return self.obs
+
+    def observe_tensor(self, *, msg_keep=None, comm=None):
+        """Observation of the current state; nothing advances."""
+        if not self._precomputed:
+            self.precompute()
+        self._set_inputs(None, None, None, None, msg_keep, comm)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mdr_observe(*self._refs, self._stream()), "mdr_observe")
+        return self.obs
+
+    def step_tensor(self, actions=None, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None,
+                    comm=None, n_steps=1):
+        """One env step for every cluster.  `actions` [E, N] (nonzero = ON) unless the env was
+        built with an on-device action source.  Replay arguments feed host-drawn randomness
+        (parity mode); when omitted the kernel draws from Philox / evaluates its own perlin."""
+        if not self._precomputed:
+            self.precompute()
+        self._set_inputs(actions, od_noise, signal_noise, interp_ids, msg_keep, comm)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mdr_step(*self._refs, int(n_steps), self._stream()), "mdr_step")
+        self.step_index += int(n_steps)
+        return self.obs, self.reward, self.env["cluster_power"], self.env["signal"]
+
+    def run(self, n_steps):
+        """`n_steps` steps with the on-device action source (one launch per step, issued from C)."""
+        if self.action_source == "array":
+            raise ValueError("run() needs action_source='bangbang' or 'random'")
+        return self.step_tensor(None, n_steps=n_steps)
+
+    def step_host(self, host_actions, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None, comm=None):
+        """End-to-end step with HOST buffers (what the dict API and the e2e benchmark call):
+        H2D of the uint8 actions, the fused step, D2H of obs / reward / power / signal into pinned
+        host memory, stream synchronised.  Returns numpy views of the pinned buffers."""
+        if not self._precomputed:
+            self.precompute()
+        e, n = self.n_envs, self.n_houses
+        if self._pinned is None:
+            pin = lambda *s, dtype: torch.empty(*s, dtype=dtype, pin_memory=True)
+            self._pinned = dict(actions=pin(e, n, dtype=torch.uint8),
+                                obs=pin(e, n, self.n_features, dtype=self.dtype) if self.with_obs else None,
+                                reward=pin(e, n, dtype=self.dtype), power=pin(e, dtype=torch.float64),
+                                signal=pin(e, dtype=torch.float64))
+        pb = self._pinned
+        pb["actions"].numpy()[...] = np.asarray(host_actions).reshape(e, n) != 0
+        self._set_inputs(None, od_noise, signal_noise, interp_ids, msg_keep, comm)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mdr_step_host(*self._refs, p(pb["actions"]), p(pb["obs"]), p(pb["reward"]),
+                                              p(pb["power"]), p(pb["signal"]), self._stream()), "mdr_step_host")
+        self.step_index += 1
+        return (None if pb["obs"] is None else pb["obs"].numpy(), pb["reward"].numpy(), pb["power"].numpy(),
+                pb["signal"].numpy())
+
+    # ------------------------------------------------------------------ views of the state
+    @property
+    def t_air(self):
+        return self.temps[..., 0]
+
+    @property
+    def t_mass(self):
+        return self.temps[..., 1]
+
+    @property
+    def hvac_on(self):
+        return self.hvac & 1
+
+    @property
+    def hvac_lockout(self):
+        return (self.hvac >> 1) & 1
+
+    @property
+    def seconds_since_off(self):
+        return self.hvac >> 2
+
+    def launch_geometry(self):
+        g, t, c, s = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t()
+        _lib.check(self.lib.mdr_launch_geometry(self._refs[0], int(self.with_obs), C.byref(g), C.byref(t), C.byref(c),
+                                                C.byref(s)), "mdr_launch_geometry")
+        return dict(envs_per_cta=g.value, threads=t.value, ctas=c.value, smem_bytes=s.value)
+
+    # ------------------------------------------------------------------ checkpoint / copy
+    _STATE = ("coef_a", "coef_b", "coef_c", "interp_key", "temps", "hvac", "lockout_dur", "t_epoch",
+              "time_since_interp", "actions", "reward")
+
+    def state_dict(self):
+        sd = {k: getattr(self, k).clone() for k in self._STATE}
+        sd.update({"raw." + k: v.clone() for k, v in self.raw.items()})
+        sd.update({"env." + k: v.clone() for k, v in self.env.items()})
+        if self.obs is not None:
+            sd["obs"] = self.obs.clone()
+        if self._comm is not None:
+            sd["comm"] = self._comm.clone()
+        sd["step_index"] = self.step_index
+        return sd
+
+    def load_state_dict(self, sd):
+        for k in self._STATE:
+            getattr(self, k).copy_(sd[k])
+        for k in self.raw:
+            self.raw[k].copy_(sd["raw." + k])
+        for k in self.env:
+            self.env[k].copy_(sd["env." + k])
+        if self.obs is not None and "obs" in sd:
+            self.obs.copy_(sd["obs"])
+        if "comm" in sd:
+            self.set_comm_table(sd["comm"].cpu().numpy())
+        self.step_index = int(sd["step_index"])
+        self._precomputed = True
+
+    def __deepcopy__(self, memo):
+        new = object.__new__(type(self))
+        memo[id(self)] = new
+        skip = {"lib", "cfg", "houses_s", "envs_s", "in_s", "out_s", "_refs", "_keep", "_pinned"}
+        for k, v in self.__dict__.items():
+            if k in skip:
+                continue
+            if isinstance(v, torch.Tensor):
+                new.__dict__[k] = v.clone()
+            elif isinstance(v, dict) and all(isinstance(x, torch.Tensor) for x in v.values()):
+                new.__dict__[k] = {kk: vv.clone() for kk, vv in v.items()}
+            elif k == "flat":
+                new.__dict__[k] = v
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        new.lib, new._keep, new._pinned = self.lib, [], None
+        new._build_structs()
+        return new

@@ -81,8 +81,9 @@ def snapshot(env):
 class Recorder:
     """Wraps the draw sources the reference consumes while stepping."""
 
-    def __init__(self, env, np_seed):
+    def __init__(self, perlin_cls, np_seed):
         self.gauss, self.choices, self.samples, self.rands, self.perlin = [], [], [], [], []
+        self.perlin_cls = perlin_cls
         self._g, self._c, self._s = random.gauss, random.choices, random.sample
         self._r = np.random.rand
         self.rng = np.random.default_rng(np_seed)
@@ -110,16 +111,14 @@ class Recorder:
 
         random.gauss, random.choices, random.sample = gauss, choices, sample
         np.random.rand = rand
-        if hasattr(env.power_grid, "perlin"):
-            p = env.power_grid.perlin
-            orig = p.calculate_noise
+        self._p = orig = perlin_cls.calculate_noise
 
-            def calc(x):
-                v = orig(x)
-                rec.perlin.append(v)
-                return v
+        def calc(self_, x):
+            v = orig(self_, x)
+            rec.perlin.append(v)
+            return v
 
-            p.calculate_noise = calc
+        perlin_cls.calculate_noise = calc
 
     def drain(self):
         out = (self.gauss, self.choices, self.samples, self.rands, self.perlin)
@@ -129,6 +128,7 @@ class Recorder:
     def close(self):
         random.gauss, random.choices, random.sample = self._g, self._c, self._s
         np.random.rand = self._r
+        self.perlin_cls.calculate_noise = self._p
 
 
 def set_path(cfg, path, value):
@@ -272,7 +272,7 @@ def _c1(cfg):
                 check=[0, 1, 2, 9, 19, 39, 59, 74, 75, 79], obs_steps=[0, 75])
 
 
-def run_case(name, Env, norm, cfg):
+def run_case(name, Env, norm, cfg, perlin_cls):
     spec = CASES[name](cfg)
     c = spec["config"]
     gp = c["default_env_prop"]["power_grid_prop"]
@@ -290,10 +290,16 @@ def run_case(name, Env, norm, cfg):
     steps = spec["steps"]
 
     random.seed(spec["seed"])
-    env = Env(c)
-    obs = env.reset()
-    rec = Recorder(env, np_seed=spec["seed"] + 1000)
+    rec = Recorder(perlin_cls, np_seed=spec["seed"] + 1000)
     try:
+        env = Env(c)
+        obs = env.reset()
+        # draws of the last build_environment: the initial PowerGrid.step (:133) consumed the last
+        # perlin value and, when N > interp_nb_agents, the last k=100 random.choices
+        _, choices0, _, _, perlin0 = rec.drain()
+        init_sig_noise = perlin0[-1] if perlin0 else 0.0
+        big = [ch for ch in choices0 if len(ch) == 100]
+        init_interp_ids = np.array(big[-1], np.int32) if big else -np.ones(100, np.int32)
         # reset() drew its message drops from the unseeded np.random: regenerate the initial
         # observation under the recorder so that the drops are known
         snap = snapshot(env)
@@ -373,6 +379,7 @@ def run_case(name, Env, norm, cfg):
         actions=A, od_noise=od_noise, sig_noise=sig_noise, interp_ids=interp_ids, msg_keep=msg_keep,
         check_steps=np.array(check, np.int64), obs_steps=np.array(obs_steps, np.int64),
         power=power, signal=signal, od_temp=od_temp, solar=solar, obs0=obs0, init_keep=init_keep,
+        init_sig_noise=np.float64(init_sig_noise), init_interp_ids=init_interp_ids,
         obs=np.stack(obs_rec) if obs_rec else np.zeros((0, n, obs0.shape[1])),
         t_air=np.array(out["t_air"]), t_mass=np.array(out["t_mass"]),
         on=np.array(out["on"], np.uint8), lockout=np.array(out["lockout"], np.uint8),
@@ -392,10 +399,10 @@ def run_case(name, Env, norm, cfg):
 
 
 def main(argv):
-    Env, norm, cfg, _ = ref_stubs.import_reference()
+    Env, norm, cfg, ref_utils = ref_stubs.import_reference()
     names = argv[1:] or list(CASES)
     for name in names:
-        run_case(name, Env, norm, cfg)
+        run_case(name, Env, norm, cfg, ref_utils.Perlin)
 
 
 if __name__ == "__main__":

@@ -184,3 +184,41 @@ def test_oracle_matches_reference_trace(name):
             np.testing.assert_allclose(obs[0], g.obs[oi], rtol=0, atol=1e-10)
             oi += 1
     assert ci == len(g.check_steps) and oi == len(g.obs_steps)
+
+
+@pytest.mark.parametrize("name", ["interp_150_sinus_solar", "interp_40_perlin", "c1_1000_fp64", "c0_bangbang_50"])
+def test_oracle_initial_grid_step(name):
+    """PowerGrid.step(start_datetime) in build_environment (:133): from signal 0 and
+    time_since_last_interp = period + 1 the oracle must land on the reference's snapshot."""
+    g = gu.Golden(name)
+    snap = g.batched_snap()
+    period = g.config["default_env_prop"]["power_grid_prop"]["base_power_parameters"]["interpolation"]["interp_update_period"]
+    snap["signal"], snap["base_power"] = np.zeros(1), np.zeros(1)
+    snap["time_since_interp"] = np.array([period + 1])
+    interp = orc.PowerInterp(gu.synthetic_table(), gu.INTERP_GRID, gu.INTERP_KEYS) if g.uses_interp else None
+    env = orc.OracleEnv(g.config, snap, comm_table=g.comm, interp=interp)
+    ids = g.init_interp_ids if g.init_interp_ids[0] >= 0 else None
+    sig = env.grid_step(0, orc.to_datetime(env.s["t_epoch"][0]), float(g.init_sig_noise), ids)
+    assert sig == pytest.approx(float(g.snap["signal"]), rel=1e-14)
+    assert env.s["base_power"][0] == pytest.approx(float(g.snap["base_power"]), rel=1e-14)
+
+
+@pytest.mark.parametrize("name", ["c0_bangbang_50", "tiny_3_comm_clipped"])
+def test_scalar_port_matches_reference_trace(name):
+    """The per-object python port used as the CPU baseline walks the reference trajectory."""
+    from oracle import mdr_oracle_scalar as sc
+    g = gu.Golden(name)
+    env = sc.ScalarEnv(g.config, g.snap)
+    ci = oi = 0
+    for t in range(g.steps):
+        obs, rew, done, info = env.step({i: bool(g.actions[t][i]) for i in range(g.n)}, g.od_noise[t], g.sig_noise[t])
+        assert info["cluster_hvac_power"] == g.power[t]
+        assert env.signal == pytest.approx(g.signal[t], rel=1e-13)
+        if t in g.check_steps:
+            np.testing.assert_allclose([env.houses[i].t_air for i in range(g.n)], g.t_air[ci], rtol=0, atol=1e-10)
+            assert [int(env.houses[i].hvac.seconds_since_off) for i in range(g.n)] == list(g.sso[ci])
+            np.testing.assert_allclose([rew[i] for i in range(g.n)], g.reward[ci], rtol=1e-10, atol=1e-10)
+            ci += 1
+        if t in g.obs_steps:
+            np.testing.assert_allclose(np.array([env.norm_state(obs[i]) for i in range(g.n)]), g.obs[oi], rtol=0, atol=1e-10)
+            oi += 1

@@ -1,0 +1,212 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA step path, called through the
+C ABI, against (1) the golden traces recorded from the unmodified reference and (2) the numpy
+oracle on seeded random inputs.
+
+Tolerances (BASELINE.json north_star): HVAC on/off, lockout, seconds_since_off and neighbour
+indices bit-exact; temperatures, power, signal, rewards, observations within 1e-9 absolute in
+fp64 mode and 1e-4 relative in fp32 mode (with an absolute floor of 1e-4 x the quantity's
+natural scale where the value itself is ~0).
+"""
+import copy
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle import mdr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp64": dict(rtol=0.0, atol=1e-9), "fp32": dict(rtol=1e-4, atol=2e-4)}
+# watts-scale quantities (up to 6e6 W): 1e-9 absolute is ~1 ulp of fp64 there
+TOL_W = {"fp64": dict(rtol=1e-15, atol=1e-9), "fp32": dict(rtol=1e-4, atol=1e-2)}
+
+
+def _env_from_golden(g, precision, **kw):
+    import mdr_b200
+    pop = g.batched_snap()
+    pop["perlin_seed"] = np.zeros(1)
+    table = gu.synthetic_table() if g.uses_interp else None
+    return mdr_b200.VecDemandResponseEnv(g.config, pop, precision=precision, interp_table=table, comm_table=g.comm, **kw)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", gu.names())
+def test_trace_matches_reference(name, precision):
+    g = gu.Golden(name)
+    env = _env_from_golden(g, precision)
+    tol, tolw = TOL[precision], TOL_W[precision]
+    init_comm = g.z.get("init_comm")
+    obs0 = env.observe_tensor(msg_keep=g.init_keep[None], comm=None if init_comm is None else init_comm[None])
+    np.testing.assert_allclose(obs0[0].cpu().numpy(), g.obs0, **tol)
+    ci = oi = 0
+    for t in range(g.steps):
+        ids = g.interp_ids[t][None] if g.interp_ids[t][0] >= 0 else None
+        comm = None if g.comm_t is None else g.comm_t[t][None]
+        obs, rew, p, s = env.step_tensor(g.actions[t][None], od_noise=g.od_noise[t:t + 1],
+                                         signal_noise=g.sig_noise[t:t + 1], interp_ids=ids,
+                                         msg_keep=g.msg_keep[t][None], comm=comm)
+        assert float(p[0]) == g.power[t], (t, float(p[0]), g.power[t])
+        np.testing.assert_allclose(float(s[0]), g.signal[t], err_msg="signal step %d" % t, **tolw)
+        np.testing.assert_allclose(float(env.env["od_temp"][0]), g.od_temp[t], rtol=0, atol=1e-12)
+        if t in g.check_steps:
+            assert np.array_equal(env.hvac_on[0].cpu().numpy(), g.on[ci]), t
+            assert np.array_equal(env.hvac_lockout[0].cpu().numpy(), g.lockout[ci]), t
+            assert np.array_equal(env.seconds_since_off[0].cpu().numpy(), g.sso[ci]), t
+            np.testing.assert_allclose(env.t_air[0].cpu().numpy(), g.t_air[ci], err_msg="t_air step %d" % t, **tol)
+            np.testing.assert_allclose(env.t_mass[0].cpu().numpy(), g.t_mass[ci], err_msg="t_mass step %d" % t, **tol)
+            np.testing.assert_allclose(rew[0].cpu().numpy(), g.reward[ci], err_msg="reward step %d" % t, **tol)
+            ci += 1
+        if t in g.obs_steps:
+            np.testing.assert_allclose(obs[0].cpu().numpy(), g.obs[oi], err_msg="obs step %d" % t, **tol)
+            oi += 1
+    assert ci == len(g.check_steps) and oi == len(g.obs_steps)
+
+
+@pytest.mark.parametrize("name", ["interp_150_sinus_solar", "interp_40_perlin", "c1_1000_fp64", "c0_bangbang_50",
+                                  "hetero_37_solar_lockout"])
+def test_reset_reproduces_initial_signal(name):
+    """mdr_reset = PowerGrid.step(start_datetime) of build_environment (:133): from the pre-reset state
+    (signal 0, time_since_last_interp = period + 1) it must land on the reference's snapshot."""
+    import mdr_b200
+    g = gu.Golden(name)
+    pop = g.batched_snap()
+    pop["perlin_seed"] = np.zeros(1)
+    period = g.config["default_env_prop"]["power_grid_prop"]["base_power_parameters"]["interpolation"]["interp_update_period"]
+    pop["signal"] = np.zeros(1)
+    pop["base_power"] = np.zeros(1)
+    pop["time_since_interp"] = np.array([period + 1])
+    env = mdr_b200.VecDemandResponseEnv(g.config, pop, precision="fp64", comm_table=g.comm,
+                                        interp_table=gu.synthetic_table() if g.uses_interp else None)
+    ids = g.init_interp_ids[None] if g.init_interp_ids[0] >= 0 else None
+    init_comm = g.z.get("init_comm")
+    obs = env.reset_tensor(signal_noise=np.array([float(g.init_sig_noise)]), interp_ids=ids, msg_keep=g.init_keep[None],
+                           comm=None if init_comm is None else init_comm[None])
+    np.testing.assert_allclose(float(env.env["signal"][0]), float(g.snap["signal"]), **TOL_W["fp64"])
+    np.testing.assert_allclose(float(env.env["base_power"][0]), float(g.snap["base_power"]), **TOL_W["fp64"])
+    if g.uses_interp:
+        assert int(env.time_since_interp[0]) == 0
+    np.testing.assert_allclose(obs[0].cpu().numpy(), g.obs0, rtol=0, atol=1e-9)
+
+
+def _random_case(n_envs, n, seed, interp, solar, steps, penalty="individual_L2", signal="sinusoidals", defect=0.0):
+    import mdr_b200
+    cfg = mdr_b200.make_default_config()
+    ep = cfg["default_env_prop"]
+    ep["cluster_prop"]["nb_agents"] = n
+    ep["cluster_prop"]["comm_defect_prob"] = defect
+    ep["power_grid_prop"]["base_power_mode"] = "interpolation" if interp else "constant"
+    ep["power_grid_prop"]["signal_mode"] = signal
+    ep["reward_prop"]["temp_penalty_mode"] = penalty
+    cfg["default_house_prop"]["solar_gain_bool"] = solar
+    cfg["default_house_prop"]["deadband"] = 0.5
+    flat = mdr_b200.FlatConfig(cfg)
+    pop = mdr_b200.synthetic_population(flat, n_envs, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    c = flat.n_comm
+    draws = dict(
+        actions=rng.integers(0, 2, (steps, n_envs, n)).astype(np.uint8),
+        od_noise=rng.normal(0, 0.5, (steps, n_envs)),
+        sig_noise=rng.uniform(-0.5, 0.5, (steps, n_envs)),
+        ids=rng.integers(0, n, (steps, n_envs, flat.interp_nb_agents)).astype(np.int32),
+        keep=(rng.random((steps, n_envs, n, c)) > defect).astype(np.uint8),
+    )
+    return cfg, flat, pop, draws
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("n_envs,n,interp,solar,penalty,signal", [
+    (7, 50, False, False, "individual_L2", "perlin"),       # c2 shape (several envs per CTA, ragged last CTA)
+    (5, 100, True, True, "individual_L2", "sinusoidals"),   # c4 shape with on-device interpolation
+    (3, 160, True, False, "common_L2", "regular_steps"),    # N > interp_nb_agents: sampled ids
+    (2, 1000, True, False, "mixture", "perlin"),            # c1 shape, one env per CTA, 1024 threads
+    (33, 3, False, True, "common_max", "flat"),             # tiny clusters, clipped neighbour count
+    (1, 1024, False, False, "individual_L2", "perlin"),     # maximum houses per env
+    (4, 1, False, False, "individual_L2", "perlin"),        # single-house clusters: no messages
+])
+def test_batched_envs_match_oracle(n_envs, n, interp, solar, penalty, signal, precision):
+    import mdr_b200
+    steps = 90 if interp else 24
+    cfg, flat, pop, d = _random_case(n_envs, n, 100 + n, interp, solar, steps, penalty, signal, defect=0.2 if n == 50 else 0.0)
+    table = gu.synthetic_table() if interp else None
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, interp_table=table)
+    snap = {k: v for k, v in pop.items() if k != "perlin_seed"}
+    oracle = orc.OracleEnv(cfg, snap, interp=orc.PowerInterp(table, gu.INTERP_GRID, gu.INTERP_KEYS) if interp else None)
+    # reset: initial signal on both sides
+    for e in range(n_envs):
+        oracle.grid_step(e, orc.to_datetime(oracle.s["t_epoch"][e]), d["sig_noise"][0, e], d["ids"][0, e])
+    obs = env.reset_tensor(signal_noise=d["sig_noise"][0], interp_ids=d["ids"][0], msg_keep=d["keep"][0])
+    tol, tolw = TOL[precision], TOL_W[precision]
+    np.testing.assert_allclose(env.env["signal"].cpu().numpy(), oracle.s["signal"], **tolw)
+    np.testing.assert_allclose(obs.cpu().numpy(), oracle.obs(d["keep"][0]), **tol)
+    for t in range(steps):
+        o_obs, o_rew, o_p, o_s = oracle.step(d["actions"][t], d["od_noise"][t], d["sig_noise"][t], d["ids"][t], d["keep"][t])
+        obs, rew, p, s = env.step_tensor(d["actions"][t], od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t],
+                                         interp_ids=d["ids"][t], msg_keep=d["keep"][t])
+        assert np.array_equal(env.hvac_on.cpu().numpy(), oracle.s["on"]), t
+        assert np.array_equal(env.hvac_lockout.cpu().numpy(), oracle.s["lockout"]), t
+        assert np.array_equal(env.seconds_since_off.cpu().numpy(), oracle.s["sso"]), t
+        assert np.array_equal(p.cpu().numpy(), o_p), t
+        np.testing.assert_allclose(s.cpu().numpy(), o_s, err_msg="signal %d" % t, **tolw)
+        np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], err_msg="t_air %d" % t, **tol)
+        np.testing.assert_allclose(env.t_mass.cpu().numpy(), oracle.s["t_mass"], err_msg="t_mass %d" % t, **tol)
+        np.testing.assert_allclose(rew.cpu().numpy(), o_rew, err_msg="reward %d" % t, **tol)
+        np.testing.assert_allclose(obs.cpu().numpy(), o_obs, err_msg="obs %d" % t, **tol)
+    assert np.array_equal(env.t_epoch.cpu().numpy(), oracle.s["t_epoch"])
+
+
+def test_fp64_long_trace_stays_within_1e9():
+    """2 500 steps (~2.8 h simulated): rounding differences between the affine 2x2 update and the
+    reference's closed form must not accumulate past 1e-9."""
+    import mdr_b200
+    steps = 2500
+    cfg, flat, pop, d = _random_case(2, 64, 77, False, True, steps)
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp64")
+    oracle = orc.OracleEnv(cfg, {k: v for k, v in pop.items() if k != "perlin_seed"})
+    env.reset_tensor(signal_noise=d["sig_noise"][0])
+    worst = 0.0
+    for t in range(steps):
+        oracle.step(d["actions"][t], d["od_noise"][t], d["sig_noise"][t])
+        env.step_tensor(d["actions"][t], od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t])
+        if t % 250 == 249 or t == steps - 1:
+            worst = max(worst, float(np.abs(env.t_air.cpu().numpy() - oracle.s["t_air"]).max()),
+                        float(np.abs(env.t_mass.cpu().numpy() - oracle.s["t_mass"]).max()))
+            assert np.array_equal(env.seconds_since_off.cpu().numpy(), oracle.s["sso"])
+    assert worst < 1e-9, worst
+
+
+def test_host_buffer_entry_point_matches_tensor_path():
+    import mdr_b200
+    cfg, flat, pop, d = _random_case(6, 50, 9, False, False, 5)
+    a = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32")
+    b = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32")
+    a.reset_tensor(signal_noise=d["sig_noise"][0])
+    b.reset_tensor(signal_noise=d["sig_noise"][0])
+    for t in range(5):
+        obs, rew, p, s = a.step_tensor(d["actions"][t], od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t])
+        h_obs, h_rew, h_p, h_s = b.step_host(d["actions"][t], od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t])
+        assert np.array_equal(obs.cpu().numpy(), h_obs) and np.array_equal(rew.cpu().numpy(), h_rew)
+        assert np.array_equal(p.cpu().numpy(), h_p) and np.array_equal(s.cpu().numpy(), h_s)
+
+
+def test_checkpoint_and_deepcopy():
+    import mdr_b200
+    cfg, flat, pop, d = _random_case(3, 40, 21, False, False, 8)
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp64")
+    env.reset_tensor(signal_noise=d["sig_noise"][0])
+    for t in range(4):
+        env.step_tensor(d["actions"][t], od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t])
+    sd = env.state_dict()
+    twin = copy.deepcopy(env)
+    outs = []
+    for e_ in (env, twin):
+        for t in range(4, 8):
+            o = e_.step_tensor(d["actions"][t], od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t])
+        outs.append([x.clone() for x in o] + [e_.temps.clone(), e_.hvac.clone()])
+    env.load_state_dict(sd)
+    for t in range(4, 8):
+        o = env.step_tensor(d["actions"][t], od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t])
+    outs.append([x.clone() for x in o] + [env.temps.clone(), env.hvac.clone()])
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert (x == y).all()
