@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDR_ABI_VERSION 3
+#define MDR_ABI_VERSION 4
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
@@ -145,7 +145,6 @@ typedef struct MdrEnvs {
   const double *phase;       /* ClusterHouses.phase, :789-792 */
   double *od_temp;           /* ClusterHouses.current_OD_temp, :793,1037 */
   double *solar_gain;        /* SingleHouse.current_solar_gain used by the last update, :694 */
-  double *solar_next;        /* gain the next step will use (= house_solar_gain(t + dt)) */
   const double *artificial_ratio; /* PowerGrid.artificial_ratio, :1116 */
   const double *max_power;   /* ClusterHouses.max_power, :796-802 */
   double *base_power;        /* PowerGrid.base_power */

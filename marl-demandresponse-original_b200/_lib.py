@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-MDR_ABI_VERSION = 3
+MDR_ABI_VERSION = 4
 MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
@@ -45,7 +45,7 @@ class MdrHouses(C.Structure):
 
 
 class MdrEnvs(C.Structure):
-    _fields_ = [(n, _vp) for n in ("t_epoch", "phase", "od_temp", "solar_gain", "solar_next", "artificial_ratio",
+    _fields_ = [(n, _vp) for n in ("t_epoch", "phase", "od_temp", "solar_gain", "artificial_ratio",
                                    "max_power", "base_power", "signal", "cluster_power", "time_since_interp",
                                    "perlin_seed", "metrics")]
 

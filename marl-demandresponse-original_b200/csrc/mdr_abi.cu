@@ -189,7 +189,7 @@ static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, cons
   if (!e->t_epoch || !e->phase || !e->od_temp || !e->artificial_ratio || !e->max_power || !e->base_power ||
       !e->signal || !e->cluster_power)
     return MDR_ERR_NULL;
-  if (c->solar_gain && (!e->solar_gain || !e->solar_next)) return MDR_ERR_NULL;
+  if (c->solar_gain && !e->solar_gain) return MDR_ERR_NULL;
   const bool interp = c->base_power_mode == MDR_BASE_INTERPOLATION;
   if (interp && (!e->time_since_interp || !in->interp_table)) return MDR_ERR_NULL;
   if (c->signal_mode == MDR_SIG_PERLIN && !in->signal_noise && !e->perlin_seed) return MDR_ERR_NULL;
@@ -200,7 +200,7 @@ static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, cons
   if (out->obs && !aligned16(out->obs)) return MDR_ERR_ALIGN;
   if (e->metrics) return MDR_ERR_UNSUPPORTED;  // reserved
   k.t_epoch = e->t_epoch; k.phase = e->phase; k.od_temp = e->od_temp; k.solar_gain = e->solar_gain;
-  k.solar_next = e->solar_next; k.artificial_ratio = e->artificial_ratio; k.max_power = e->max_power;
+  k.artificial_ratio = e->artificial_ratio; k.max_power = e->max_power;
   k.base_power = e->base_power; k.signal = e->signal; k.cluster_power = e->cluster_power;
   k.time_since_interp = e->time_since_interp; k.perlin_seed = e->perlin_seed;
   k.actions = in->actions; k.od_noise = in->od_noise; k.signal_noise = in->signal_noise;

@@ -25,7 +25,7 @@ namespace mdr {
 // ----------------------------------------------------------------------------------------
 struct EnvScratch {
   double P, od_new, rew_sig, pen_mean, pen_max, hour_s, date;
-  double f_sig, f_pow, f_od, f_sin_day, f_cos_day, f_sin_hr, f_cos_hr, f_solar;
+  double f_sig, f_pow, f_od, f_sin_day, f_cos_day, f_sin_hr, f_cos_hr, f_solar, gain_now;
   int due, pad;
 };
 
@@ -231,6 +231,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
   EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + L.off_env);
   R* s_stage = reinterpret_cast<R*>(smem_raw + L.off_stage);
 
+  // ---------------- phase 0 (solar gain on): gain of this step, one lane per env ----------
+  if (p.solar) {
+    for (int le2 = warp; le2 < genvs; le2 += nwarps)
+      if (lane == 0) {
+        // SingleHouse.update_temperature evaluates house_solar_gain at the NEW datetime (:694)
+        const Calendar cal = calendar_from_epoch(p.t_epoch[env0 + le2] + p.dt);
+        s_env[le2].gain_now = reset ? 0.0 : solar_gain(cal, p.window_area, p.shading_coeff);
+      }
+    __syncthreads();
+  }
+
   // ---------------- phase A: per house -------------------------------------------------
   R ta = 0, tm = 0, target = 0, deadband = 0, lockdur_r = 1, p_on = 0, pen = 0;
   int on = 0, lock = 0, sso = 0;
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       on = new_on;
       // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature
       const R od_old = (R)p.od_temp[e];
-      const R gain = p.solar ? (R)p.solar_next[e] : (R)0;
+      const R gain = p.solar ? (R)s_env[le].gain_now : (R)0;
       const R qa = (on ? cb.y : (R)0) + gain;
       const R tss = od_old + qa * cb.x;
       const R x = tt.x - tss, y = tt.y - tss;
@@ -353,12 +364,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       const double sp = ((acc - s_old) / N) * ((acc - s_old) / N);
       es.rew_sig = p.alpha_sig * sp / p.norm_sig_penalty;
       p.cluster_power[e2] = acc;
-      // solar gain of this step (for the obs) and of the next one (for the next update)
+      // solar gain used by this step's update (SingleHouse.current_solar_gain, for the obs)
       double gain_now = 0.0;
       if (p.solar) {
-        gain_now = reset ? 0.0 : p.solar_next[e2];
-        Calendar nxt = calendar_from_epoch(t + p.dt);
-        p.solar_next[e2] = solar_gain(nxt, p.window_area, p.shading_coeff);
+        gain_now = es.gain_now;
         p.solar_gain[e2] = gain_now;
       }
       es.f_solar = gain_now / 1000;

@@ -26,7 +26,7 @@ struct KernelParams {
   // per-env arrays
   int64_t* t_epoch;
   const double* phase;
-  double *od_temp, *solar_gain, *solar_next;
+  double *od_temp, *solar_gain;
   const double *artificial_ratio, *max_power;
   double *base_power, *signal, *cluster_power;
   int32_t* time_since_interp;

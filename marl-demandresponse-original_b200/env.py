@@ -147,7 +147,10 @@ class MADemandResponseEnv:
                             artificial_ratio=float(pop["artificial_ratio"][0]))
         # PowerGrid.step(start_datetime) at :133 -- interpolation ids are drawn first (:1214), then perlin
         ids, noise = self._grid_draws(self.datetime)
-        self._vec.reset_tensor(signal_noise=noise, interp_ids=ids)
+        placeholder = None
+        if flat.comm_mode_name == "random_sample":  # neighbour sets are only drawn when an observation is made
+            placeholder = np.zeros((1, flat.n_houses, flat.n_comm), np.int32)
+        self._vec.reset_tensor(signal_noise=noise, interp_ids=ids, comm=placeholder)
         self._pull_state()
         self.cluster = _ClusterView(self)
         self.power_grid = _PowerGridView(self)

@@ -83,7 +83,7 @@ class VecDemandResponseEnv:
         self.interp_key = z(e, n, dtype=i32)
         self.temps = z(e, n, 2, dtype=r)
         self.hvac = z(e, n, dtype=i32)
-        self.env = {k: z(e, dtype=f64) for k in ("phase", "od_temp", "solar_gain", "solar_next", "artificial_ratio",
+        self.env = {k: z(e, dtype=f64) for k in ("phase", "od_temp", "solar_gain", "artificial_ratio",
                                                 "max_power", "base_power", "signal", "cluster_power", "perlin_seed")}
         self.t_epoch = z(e, dtype=torch.int64)
         self.time_since_interp = z(e, dtype=i32)
@@ -112,8 +112,6 @@ class VecDemandResponseEnv:
         sso, on, lock = house("sso", torch.int32), house("on", torch.int32), house("lockout", torch.int32)
         self.hvac.copy_((sso << 2) | ((lock != 0).int() << 1) | (on != 0).int())
         for k in self.env:
-            if k == "solar_next":
-                continue
             if k in pop:
                 self.env[k].copy_(env(k, torch.float64))
         self.t_epoch.copy_(env("t_epoch", torch.int64))

@@ -293,6 +293,12 @@ class OracleEnv:
         self.reward_prop = env_prop["reward_prop"]
         self.dt = int(env_prop["time_step"])
         self.s = {k: np.array(v, copy=True) for k, v in snap.items()}
+        # the reference never noises COP / latent fraction: default them from the config when absent
+        for k, name in (("cop", "COP"), ("latent", "latent_cooling_fraction")):
+            if k not in self.s:
+                self.s[k] = np.full(np.shape(self.s["cap"]), float(self.hvac_def[name]))
+        if "solar_gain" not in self.s:
+            self.s["solar_gain"] = np.zeros(np.shape(self.s["t_epoch"]))
         for k in HOUSE_KEYS_F:
             self.s[k] = np.atleast_2d(np.asarray(self.s[k], dtype=np.float64))
         for k in HOUSE_KEYS_I:

@@ -127,6 +127,6 @@ def test_production_mode_device_rng_is_reproducible_and_plausible():
     assert torch.equal(env.env["od_temp"], twin.env["od_temp"]) and torch.equal(env.temps, twin.temps)
     assert not torch.equal(env.env["od_temp"], other.env["od_temp"])
     od = torch.stack(od)  # [T, E]; default temp_std 0.5 around a 28..34 sinusoid
-    assert 27.0 < float(od.min()) and float(od.max()) < 37.0
+    assert 25.0 < float(od.min()) and float(od.max()) < 37.5
     resid = od[1:] - od[:-1]
     assert 0.4 < float(resid.std()) < 1.0  # difference of two N(0, 0.5) draws: std ~0.71
