@@ -66,6 +66,8 @@ extern "C" int mdr_validate(const MdrConfig* c) {
   if (c->n_sinusoids < 0 || c->n_sinusoids > MDR_MAX_SINUSOIDS) return MDR_ERR_SHAPE;
   if (c->n_features != mdr_obs_width(c)) return MDR_ERR_SHAPE;
   if (c->n_houses > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
+  /* 32-bit house / observation indexing inside the kernel */
+  if ((double)c->n_envs * c->n_houses * (c->n_features > 0 ? c->n_features : 1) >= 4294967296.0) return MDR_ERR_UNSUPPORTED;
   if (c->base_power_mode == MDR_BASE_INTERPOLATION) {
     if (c->interp_nb_agents < 1 || c->interp_nb_agents > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_SHAPE;
     for (int d = 0; d < MDR_INTERP_DIMS; ++d)
@@ -86,29 +88,37 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
     for (int k = gmax; k >= 1; --k)
       if (((size_t)k * N * F * rb) % 16 == 0) { G = k; break; }
   }
-  const int threads = ((G * N + 31) / 32) * 32;
-  const int nwarps = threads / 32;
+  const int house_threads = ((G * N + 31) / 32) * 32;
+  const int house_warps = house_threads / 32;
+  // a dedicated prologue warp when the CTA has room for one, else warp 0 runs the prologue first
+  const bool extra = house_threads + 32 <= 1024;
+  const int threads = house_threads + (extra ? 32 : 0);
+  const int nwarps = house_warps;  // staging tiles exist for the house warps only
+  const int part_stride = (N + 31) / 32 + 1;
   const bool need_val = c->base_power_mode == MDR_BASE_INTERPOLATION;
   const bool need_pen = c->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2;
-  int blocks_per_sm = 896 / threads;
+  int blocks_per_sm = 1024 / threads;
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   const size_t budget = (size_t)MDR_MAX_SMEM_BYTES / blocks_per_sm - 1024;
   int rpp = 0;
   size_t smem = 0;
   for (int r = 32; r >= 1; r >>= 1) {
-    smem = mdr::step_smem_bytes(rb, threads, G, nwarps, r, F, need_val, need_pen, has_obs);
+    smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride);
     if (smem <= budget) { rpp = r; break; }
   }
   if (rpp == 0) {
     for (int r = 32; r >= 1; r >>= 1) {
-      smem = mdr::step_smem_bytes(rb, threads, G, nwarps, r, F, need_val, need_pen, has_obs);
+      smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride);
       if (smem <= (size_t)MDR_MAX_SMEM_BYTES) { rpp = r; break; }
     }
   }
   if (rpp == 0) return MDR_ERR_UNSUPPORTED;
   g->envs_per_cta = G;
   g->threads = threads;
-  g->hmax = threads;
+  g->hmax = house_threads;
+  g->house_warps = house_warps;
+  g->pro_warp = extra ? house_warps : 0;
+  g->part_stride = part_stride;
   g->ctas = (E + G - 1) / G;
   g->rows_per_pass = rpp;
   g->smem_bytes = smem;
@@ -145,6 +155,10 @@ static void fill_config(KernelParams& k, const MdrConfig* c) {
   const int agents = c->obs_norm_agents > 0 ? c->obs_norm_agents : c->n_houses;
   k.inv_norm_sig_agents = 1.0 / (c->norm_reg_sig * agents);
   k.cop_over_def_cap = c->hvac_cop / c->def_cap;
+  k.inv_perlin_period = c->perlin_period > 0 ? 1.0 / c->perlin_period : 0.0;
+  k.inv_n = 1.0 / c->n_houses;
+  k.k_temp = c->alpha_temp / c->norm_temp_penalty;
+  k.k_sig = c->alpha_sig / c->norm_sig_penalty;
   k.def_ua = c->def_ua; k.def_cm = c->def_cm; k.def_ca = c->def_ca; k.def_hm = c->def_hm;
   k.def_cop = c->def_cop; k.def_latent = c->def_latent; k.def_cap = c->def_cap;
   k.hvac_cop = c->hvac_cop; k.hvac_latent = c->hvac_latent;
@@ -241,6 +255,13 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   k.G = g.envs_per_cta;
   k.hmax = g.hmax;
   k.rows_per_pass = g.rows_per_pass;
+  k.div_magic = (unsigned)(4294967296ull / (unsigned)cfg->n_houses) + 1u;
+  k.house_warps = g.house_warps;
+  k.pro_warp = g.pro_warp;
+  k.part_stride = g.part_stride;
+  mdr::step_smem_layout(&k, cfg->precision, g.hmax, g.envs_per_cta, g.house_warps, g.rows_per_pass, cfg->n_features,
+                        cfg->base_power_mode == MDR_BASE_INTERPOLATION,
+                        cfg->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2, out->obs != nullptr, cfg->n_comm, g.part_stride);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);
   for (int i = 0; i < n_steps; ++i) {

@@ -50,54 +50,65 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {  // (0, 1), 53 b
   return ((double)(v & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-__device__ __forceinline__ double philox_normal(uint32_t entity, uint64_t step, uint32_t stream, uint64_t key) {
-  const uint4 r = philox4x32(entity, (uint32_t)step, (uint32_t)(step >> 32), stream, key);
-  const double u1 = u01(r.x, r.y), u2 = u01(r.z, r.w);
-  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+// standard normal from one Philox draw (production-mode outdoor-temperature noise; single
+// precision Box-Muller is ample for a 0.5 K noise term and keeps the per-env prologue short)
+__device__ __forceinline__ double normal_from(const uint4 r) {
+  const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return (double)(sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2));
 }
 
 // ---------------------------------------------------------------------------------------
 // Calendar (proleptic Gregorian, naive datetime like the reference's `datetime` objects)
 // ---------------------------------------------------------------------------------------
 struct Calendar {
-  int year, month, day, yday;  // yday = tm_yday (1-based)
+  int year, month, day, yday;  // yday = tm_yday (1-based); only valid after calendar_date()
   int hour, minute, second, sod;
+  int days;                    // whole days since 1970-01-01
 };
 
-__device__ __forceinline__ int64_t days_from_civil(int64_t y, int m, int d) {
+// All 32-bit: t is the naive epoch second as uint32 (valid until 2106; validated on the host),
+// so every division is by a compile-time constant (mul-shift), never a 64-bit software divide.
+__device__ __forceinline__ Calendar calendar_time(uint32_t t) {
+  Calendar c;
+  const uint32_t days = t / 86400u;
+  const uint32_t sod = t - days * 86400u;
+  c.days = (int)days;
+  c.sod = (int)sod;
+  c.hour = (int)(sod / 3600u);
+  c.minute = (int)((sod - (uint32_t)c.hour * 3600u) / 60u);
+  c.second = (int)(sod - (uint32_t)c.hour * 3600u - (uint32_t)c.minute * 60u);
+  c.year = c.month = c.day = c.yday = 0;
+  return c;
+}
+
+__device__ __forceinline__ int days_from_civil(int y, int m, int d) {
   y -= m <= 2;
-  const int64_t era = (y >= 0 ? y : y - 399) / 400;
-  const int64_t yoe = y - era * 400;
-  const int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
-  const int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  const int era = y / 400;  // y >= 1970 here
+  const int yoe = y - era * 400;
+  const int doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const int doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
   return era * 146097 + doe - 719468;
 }
 
-__device__ __forceinline__ Calendar calendar_from_epoch(int64_t t) {
-  Calendar c;
-  int64_t days = t / 86400;
-  int64_t rem = t - days * 86400;
-  if (rem < 0) { rem += 86400; days -= 1; }
-  c.sod = (int)rem;
-  c.hour = c.sod / 3600;
-  c.minute = (c.sod - c.hour * 3600) / 60;
-  c.second = c.sod - c.hour * 3600 - c.minute * 60;
-  const int64_t z = days + 719468;
-  const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
-  const int64_t doe = z - era * 146097;
-  const int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-  const int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
-  const int64_t mp = (5 * doy + 2) / 153;
-  c.day = (int)(doy - (153 * mp + 2) / 5 + 1);
-  c.month = (int)(mp < 10 ? mp + 3 : mp - 9);
-  const int64_t y = yoe + era * 400 + (c.month <= 2);
-  c.year = (int)y;
-  c.yday = (int)(days - days_from_civil(y, 1, 1)) + 1;
-  return c;
+// fills year / month / day / yday (needed only for solar gain, the day-of-year features and the
+// interpolation point when solar gain is on)
+__device__ __forceinline__ void calendar_date(Calendar& c) {
+  const int z = c.days + 719468;
+  const int era = z / 146097;
+  const int doe = z - era * 146097;
+  const int yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  const int doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const int mp = (5 * doy + 2) / 153;
+  c.day = doy - (153 * mp + 2) / 5 + 1;
+  c.month = mp < 10 ? mp + 3 : mp - 9;
+  c.year = yoe + era * 400 + (c.month <= 2);
+  c.yday = c.days - days_from_civil(c.year, 1, 1) + 1;
 }
 
 // utils.py:1277-1350 -- CIBSE solar cooling load polynomial, same term order.
 __device__ __forceinline__ double solar_gain(const Calendar& c, double window_area, double shading_coeff) {
+  // c must have been completed with calendar_date()
   const double x = c.hour + c.minute / 60.0 - 7.5;
   double scl = 0.0;
   if (!(x < 0 || x > 10)) {
@@ -120,29 +131,20 @@ __device__ __forceinline__ double solar_gain(const Calendar& c, double window_ar
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double perlin_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
 
-__device__ __forceinline__ double perlin_octave(double x, int octaves, uint32_t oct_id, uint64_t key) {
+// one lattice term of one octave: lane = 2*octave + corner.  Summing the terms of all lanes gives
+// utils.Perlin.calculate_noise (weights 1/2^j for the first nb-1 octaves, 1/(2^nb - 1) for the last).
+__device__ __forceinline__ double perlin_term(double x, int j, int corner, int nb_octaves, int octaves_step,
+                                              const uint4 r) {
+  const int octaves = (1 << j) * octaves_step;
   const double xo = x * octaves;
-  const double f = floor(xo);
-  const int64_t i0 = (int64_t)f;
-  double v = 0.0;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int64_t i = i0 + k;
-    const uint4 r = philox4x32((uint32_t)i, (uint32_t)((uint64_t)i >> 32), oct_id, STREAM_PERLIN, key);
-    const double g = 2.0 * u01(r.x, r.y) - 1.0;
-    const double d = xo - (double)i;
-    v += perlin_fade(1.0 - fabs(d)) * g * d;
-  }
-  return v;
+  const double d = xo - (floor(xo) + corner);
+  const double g = 2.0 * u01(r.x, r.y) - 1.0;
+  const double wgt = j == nb_octaves - 1 ? 1.0 / (double)((1 << nb_octaves) - 1) : 1.0 / (double)(1 << j);
+  return perlin_fade(1.0 - fabs(d)) * g * d * wgt;
 }
 
-__device__ __forceinline__ double perlin_noise(double x, int nb_octaves, int octaves_step, uint64_t key) {
-  double noise = 0.0;
-  for (int j = 0; j < nb_octaves - 1; ++j)
-    noise += perlin_octave(x, (1 << j) * octaves_step, (uint32_t)j, key) / (double)(1 << j);
-  noise += perlin_octave(x, (1 << (nb_octaves - 1)) * octaves_step, (uint32_t)(nb_octaves - 1), key) /
-           (double)((1 << nb_octaves) - 1);
-  return noise;
+__device__ __forceinline__ uint32_t perlin_lattice(double x, int j, int corner, int octaves_step) {
+  return (uint32_t)((int)floor(x * ((1 << j) * octaves_step)) + corner);
 }
 
 // ---------------------------------------------------------------------------------------

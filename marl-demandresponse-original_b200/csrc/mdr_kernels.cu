@@ -24,24 +24,26 @@ namespace mdr {
 
 // ----------------------------------------------------------------------------------------
 struct EnvScratch {
-  double P, od_new, rew_sig, pen_mean, pen_max, hour_s, date;
+  double P, od_new, rew_sig, pen_mean, pen_max, hour_s, date, s_old, sig_new, sig_noise, base;
   double f_sig, f_pow, f_od, f_sin_day, f_cos_day, f_sin_hr, f_cos_hr, f_solar, gain_now;
-  int due, pad;
+  uint32_t t_new;
+  int due, tsi, time_sec;
 };
 
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // shared-memory carve-up (must match between host sizing and the kernel)
 struct SmemLayout {
   size_t off_msg, off_pw, off_val, off_pen, off_env, off_stage, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarps, int rows_per_pass,
-                                                  int n_features, bool need_val, bool need_pen, bool has_obs) {
+// hmax = threads per CTA (>= G*N); the message window holds G*(N+C) entries (wrap-around halos)
+inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarps, int rows_per_pass, int n_features,
+                              bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride) {
   SmemLayout L;
   size_t o = 0;
-  L.off_msg = o; o += align16((size_t)hmax * 4 * real_bytes);
-  L.off_pw = o;  o += align16((size_t)hmax * real_bytes);
+  L.off_msg = o; o += align16((size_t)(hmax + genvs_max * n_comm) * 4 * real_bytes);
+  L.off_pw = o;  o += align16((size_t)genvs_max * part_stride * sizeof(double));
   L.off_val = o; o += need_val ? align16((size_t)hmax * sizeof(double)) : 0;
   L.off_pen = o; o += need_pen ? align16((size_t)hmax * sizeof(double)) : 0;
   L.off_env = o; o += align16((size_t)genvs_max * sizeof(EnvScratch));
@@ -107,14 +109,13 @@ __device__ __noinline__ double interp_eval(const KernelParams& p, int key, doubl
 }
 
 // PowerGrid.step signal shapes, env/MA_DemandResponse.py:1257-1314
-__device__ __forceinline__ double grid_signal(const KernelParams& p, double base, const Calendar& cal, double noise,
+__device__ __forceinline__ double grid_signal(const KernelParams& p, double base, int time_sec, double noise,
                                               double ratio, double max_power) {
   double sig;
   const double two_pi = 2.0 * 3.141592653589793;
   if (p.signal_mode == MDR_SIG_FLAT) {
     sig = base;
   } else if (p.signal_mode == MDR_SIG_SINUSOIDALS) {
-    const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
     sig = base;
     for (int i = 0; i < p.n_sinusoids; ++i) {
       const double amp = mul_rn(base, p.sin_ratios[i]);
@@ -123,7 +124,6 @@ __device__ __forceinline__ double grid_signal(const KernelParams& p, double base
   } else if (p.signal_mode == MDR_SIG_REGULAR_STEPS) {
     const double amplitude = p.steps_amplitude_per_hvac * p.N;
     const double r = base / amplitude;
-    const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
     const double arg = fmod((double)time_sec, p.steps_period) - mul_rn(1.0 - r, p.steps_period);
     sig = amplitude * (arg >= 0.0 ? 1.0 : 0.0);  // np.heaviside(arg, 1)
   } else {                                         // perlin family
@@ -198,76 +198,191 @@ __global__ void precompute_kernel(const __grid_constant__ KernelParams p) {
 }
 
 // ----------------------------------------------------------------------------------------
+// per-env prologue: everything of the step that does not depend on the houses' new state
+// (clock, outdoor temperature, noise draws, solar gain, grid signal when no refresh is due).
+// One THREAD per env, executed by a dedicated warp of the CTA concurrently with the house
+// warps' global loads and thermal update, so its latency (fp64 sin, Philox) is off the
+// critical path.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void env_prologue(const KernelParams& p, EnvScratch& es, int e2, bool reset, bool observe_only) {
+  // all per-env loads up front (independent, so their latencies overlap)
+  const uint32_t t = (uint32_t)p.t_epoch[e2] + (reset ? 0u : (uint32_t)p.dt);
+  const double od_prev = p.od_temp[e2];
+  const double s_old = p.signal[e2];
+  const double phase = p.phase[e2];
+  const double ratio = p.artificial_ratio[e2], max_power = p.max_power[e2];
+  const bool perlin = p.signal_mode == MDR_SIG_PERLIN;
+  const bool draw_od = !reset && p.od_noise == nullptr;
+  const bool draw_perlin = perlin && !observe_only && p.signal_noise == nullptr;
+  double od_noise = (!reset && !draw_od) ? p.od_noise[e2] : 0.0;
+  double sig_noise = (perlin && !draw_perlin && !observe_only) ? p.signal_noise[e2] : 0.0;
+  const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
+  double base = p.avg_power_per_hvac * p.N;  // PowerGrid.step :1248-1249
+  int tsi = 0;
+  if (interp_mode) {
+    base = p.base_power[e2];
+    tsi = p.time_since_interp[e2];
+  }
+  const double solar_prev = (observe_only && p.solar) ? p.solar_gain[e2] : 0.0;
+
+  Calendar cal = calendar_time(t);
+  if (p.solar || (p.state_flags & MDR_STATE_DAY)) calendar_date(cal);
+  if (draw_od) od_noise = p.temp_std * normal_from(philox4x32((uint32_t)e2, (uint32_t)p.step_index,
+                                                             (uint32_t)(p.step_index >> 32), STREAM_OD, p.seed));
+  if (draw_perlin) {
+    // utils.Perlin.calculate_noise (utils.py:1247-1253) with Philox lattice gradients
+    const double x = (double)cal.sod * p.inv_perlin_period;  // time.mktime(...) % 86400 with TZ=UTC, :1297
+    const uint64_t key = p.seed ^ (uint64_t)__double_as_longlong(p.perlin_seed[e2]);
+    const int nb = p.perlin_nb_octaves;
+    const double w_last = 1.0 / (double)((1 << nb) - 1);
+    double noise = 0.0;
+    for (int j = 0; j < nb; ++j) {
+      const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
+      const double fl = floor(xo);
+      double v = 0.0;
+#pragma unroll
+      for (int corner = 0; corner < 2; ++corner) {
+        const uint4 r = philox4x32((uint32_t)((int)fl + corner), 0u, (uint32_t)j, STREAM_PERLIN, key);
+        const double d = xo - (fl + corner);
+        v += perlin_fade(1.0 - fabs(d)) * (2.0 * u01(r.x, r.y) - 1.0) * d;
+      }
+      noise += v * (j == nb - 1 ? w_last : scalbn(1.0, -j));
+    }
+    sig_noise = noise;
+  }
+  double od_new = od_prev;
+  if (!reset) {
+    // ClusterHouses.compute_OD_temp, :1070-1081
+    const double amplitude = (p.day_temp - p.night_temp) / 2, bias = (p.day_temp + p.night_temp) / 2;
+    const double delay = -6 + phase;
+    const double time_day = cal.hour + cal.minute / 60.0;
+    od_new = amplitude * sin(2 * 3.141592653589793 * (time_day + delay) / 24) + bias;
+    od_new += od_noise;
+  }
+  es.t_new = t;
+  es.od_new = od_new;
+  es.f_od = (od_new - 20) * 0.2;
+  es.sig_noise = sig_noise;
+  // SingleHouse.update_temperature evaluates house_solar_gain at the NEW datetime (:694)
+  double gain = (p.solar && !reset) ? solar_gain(cal, p.window_area, p.shading_coeff) : 0.0;
+  if (observe_only) gain = solar_prev;
+  es.gain_now = gain;
+  es.f_solar = gain * 1e-3;
+  es.hour_s = p.solar ? (double)cal.sod : 0.0;  // interpolatePower point, :1198-1207
+  es.date = p.solar ? (double)cal.yday : 0.0;
+  es.time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
+  if (p.state_flags & MDR_STATE_DAY) {
+    es.f_sin_day = sin(cal.yday * 2 * 3.141592653589793 / 365);
+    es.f_cos_day = cos(cal.yday * 2 * 3.141592653589793 / 365);
+  }
+  if (p.state_flags & MDR_STATE_HOUR) {
+    es.f_sin_hr = sin(cal.hour * 2 * 3.141592653589793 / 24);
+    es.f_cos_hr = cos(cal.hour * 2 * 3.141592653589793 / 24);
+  }
+  // PowerGrid.step, :1250-1255: the signal is final now unless an interpolation refresh is due
+  int due = 0;
+  if (interp_mode && !observe_only) {
+    tsi += p.dt;
+    due = tsi >= p.interp_update_period;
+    if (due) tsi = 0;
+  }
+  es.tsi = tsi;
+  es.due = due;
+  es.s_old = s_old;
+  es.base = base;
+  double sig = s_old;
+  if (!observe_only && !due) sig = grid_signal(p, base, es.time_sec, sig_noise, ratio, max_power);
+  es.sig_new = sig;
+  es.f_sig = sig * p.inv_norm_sig_agents;
+}
+
+// segmented warp reduction over lanes with equal `key` (keys are contiguous runs): afterwards the
+// first lane of every run holds the run's sum (fixed shuffle order => deterministic)
+__device__ __forceinline__ double segmented_sum(double v, int key, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double tv = __shfl_down_sync(0xffffffffu, v, o);
+    const int tk = __shfl_down_sync(0xffffffffu, key, o);
+    if (lane + o < 32 && tk == key) v += tv;
+  }
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------
 // the fused step kernel
 // ----------------------------------------------------------------------------------------
-template <typename R, int kMaxThreads>
+template <typename R, int kMaxThreads, bool kFast, int kC>
 __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(const __grid_constant__ KernelParams p) {
   using T2 = typename Vec<R>::T2;
   using T4 = typename Vec<R>::T4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
 
+  // kFast: implicit `neighbours` messages, default state/message flags, individual_L2 penalty, no
+  // message drops -- the configuration of BASELINE configs 0-4; everything else takes the generic
+  // instantiation.  kC > 0 fixes the message count at compile time (unrolled window).
+  const int comm_mode = kFast ? MDR_COMM_NEIGHBOURS : p.comm_mode;
+  const int state_flags = kFast ? 0 : p.state_flags;
+  const int msg_flags = kFast ? 0 : p.msg_flags;
+  const int pen_mode = kFast ? MDR_PEN_INDIVIDUAL_L2 : p.temp_penalty_mode;
+  const bool has_keep = kFast ? false : p.msg_keep != nullptr;
+  const bool has_defect = kFast ? false : p.comm_defect_prob > 0.0;
+
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int N = p.N;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int N = p.N, C = kC > 0 ? kC : p.C;
   const int env0 = blockIdx.x * p.G;
   const int genvs = min(p.G, p.E - env0);
   const int H = genvs * N;
   const bool active = tid < H;
-  const int le = active ? tid / N : 0;
+  const int le = active ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
   const int li = tid - le * N;
   const int e = env0 + le;
-  const size_t h = (size_t)env0 * N + tid;
-  const bool reset = p.is_reset != 0;          // 1 = reset (grid step + obs), 2 = observe only
+  const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
+  const bool reset = p.is_reset != 0;  // 1 = reset (grid step + obs), 2 = observe only
   const bool observe_only = p.is_reset == 2;
   const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
-  const bool need_pen = p.temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2;
+  const bool need_pen = pen_mode != MDR_PEN_INDIVIDUAL_L2;
 
-  const SmemLayout L = smem_layout((int)sizeof(R), p.hmax, p.G, nwarps, p.rows_per_pass, p.F, interp_mode, need_pen,
-                                   p.obs != nullptr);
-  T4* s_msg = reinterpret_cast<T4*>(smem_raw + L.off_msg);
-  R* s_pw = reinterpret_cast<R*>(smem_raw + L.off_pw);
-  double* s_val = reinterpret_cast<double*>(smem_raw + L.off_val);
-  double* s_pen = reinterpret_cast<double*>(smem_raw + L.off_pen);
-  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + L.off_env);
-  R* s_stage = reinterpret_cast<R*>(smem_raw + L.off_stage);
+  T4* s_msg = reinterpret_cast<T4*>(smem_raw + p.off_msg);  // per env: [half halo | N houses | halo]
+  double* s_part = reinterpret_cast<double*>(smem_raw + p.off_pw);  // [G][part_stride] warp partial power sums
+  double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
+  double* s_pen = reinterpret_cast<double*>(smem_raw + p.off_pen);
+  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
+  R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
 
-  // ---------------- phase 0 (solar gain on): gain of this step, one lane per env ----------
-  if (p.solar) {
-    for (int le2 = warp; le2 < genvs; le2 += nwarps)
-      if (lane == 0) {
-        // SingleHouse.update_temperature evaluates house_solar_gain at the NEW datetime (:694)
-        const Calendar cal = calendar_from_epoch(p.t_epoch[env0 + le2] + p.dt);
-        s_env[le2].gain_now = reset ? 0.0 : solar_gain(cal, p.window_area, p.shading_coeff);
-      }
-    __syncthreads();
+  // ---------------- phase A loads: issued first so that they overlap the env prologue ------
+  T2 tt = make2((R)0, (R)0);
+  T4 ca4 = make4((R)0, (R)0, (R)0, (R)0), cb = ca4;
+  T2 cc = make2((R)0, (R)1);
+  int hv = 0, cmd = 0;
+  if (active) {
+    tt = reinterpret_cast<const T2*>(p.temps)[h];
+    hv = p.hvac[h];
+    cb = reinterpret_cast<const T4*>(p.coef_b)[h];
+    cc = reinterpret_cast<const T2*>(p.coef_c)[h];
+    if (!reset) {
+      ca4 = reinterpret_cast<const T4*>(p.coef_a)[h];
+      if (p.action_source == MDR_ACT_ARRAY) cmd = p.actions[h];
+    }
   }
 
+  // ---------------- phase 0: per-env prologue by the prologue warp, one lane per env --------
+  if (warp == p.pro_warp)
+    for (int le2 = lane; le2 < genvs; le2 += 32) env_prologue(p, s_env[le2], env0 + le2, reset, observe_only);
+  if (p.solar) __syncthreads();  // the thermal update needs this step's solar gain
+
   // ---------------- phase A: per house -------------------------------------------------
-  R ta = 0, tm = 0, target = 0, deadband = 0, lockdur_r = 1, p_on = 0, pen = 0;
-  int on = 0, lock = 0, sso = 0;
-  int any_due = 0;
+  const R target = cb.w, p_on = cb.z, deadband = cc.x, lockdur_r = cc.y;
+  int on = hv & 1, lock = (hv >> 1) & 1, sso = hv >> 2;
+  R pen = 0;
+  const int half = C >> 1;
+  const int ns = N + C;  // shared-memory stride of one env's message window
+  R pw = 0;
   if (active) {
-    T2 tt = reinterpret_cast<const T2*>(p.temps)[h];
-    const int hv = p.hvac[h];
-    const T4 cb = reinterpret_cast<const T4*>(p.coef_b)[h];
-    const T2 cc = reinterpret_cast<const T2*>(p.coef_c)[h];
-    target = cb.w;
-    p_on = cb.z;
-    deadband = cc.x;
-    lockdur_r = cc.y;
-    on = hv & 1;
-    lock = (hv >> 1) & 1;
-    sso = hv >> 2;
     if (!reset) {
-      const T4 ca4 = reinterpret_cast<const T4*>(p.coef_a)[h];
-      int cmd;
-      if (p.action_source == MDR_ACT_ARRAY) {
-        cmd = p.actions[h] != 0;
-      } else if (p.action_source == MDR_ACT_BANGBANG) {
-        cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61 on the previous observation
-      } else {
-        cmd = philox4x32((uint32_t)h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
-      }
+      if (p.action_source == MDR_ACT_ARRAY) cmd = cmd != 0;
+      else if (p.action_source == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
+      else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
       const int lockdur = (int)lockdur_r;
@@ -288,31 +403,49 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       reinterpret_cast<T2*>(p.temps)[h] = tt;
       p.hvac[h] = (sso << 2) | (lock << 1) | on;
     }
-    ta = tt.x;
-    tm = tt.y;
-    const R pw = on ? p_on : (R)0;
-    s_pw[tid] = pw;
+    pw = on ? p_on : (R)0;
     const R inv_norm = (R)p.inv_norm_reg_sig;
-    s_msg[tid] = make4((ta - target) * (R)0.2, (R)sso, pw * inv_norm, p_on * inv_norm);
+    const T4 m = make4((tt.x - target) * (R)0.2, (R)sso, pw * inv_norm, p_on * inv_norm);
+    T4* win = s_msg + le * ns;
+    win[half + li] = m;
+    if (li < C - half) win[half + N + li] = m;        // wrap-around halo after the last house
+    if (li >= N - half) win[li - (N - half)] = m;     // ... and before the first one
     // utils.deadbandL2, utils.py:1266-1274
     const R hi = target + deadband / 2, lo = target - deadband / 2;
-    if (hi < ta) pen = (ta - hi) * (ta - hi);
-    else if (lo > ta) pen = (lo - ta) * (lo - ta);
-    else pen = 0;
+    if (hi < tt.x) pen = (tt.x - hi) * (tt.x - hi);
+    else if (lo > tt.x) pen = (lo - tt.x) * (lo - tt.x);
     if (need_pen) s_pen[tid] = (double)pen;
-    if (interp_mode && !observe_only) any_due = (p.time_since_interp[e] + p.dt >= p.interp_update_period);
   }
-  if (interp_mode) any_due = __syncthreads_or(any_due);
-  else __syncthreads();
+  // cluster power: per-warp segmented partial sums (keyed by env), summed per thread after the barrier
+  if (warp < p.house_warps) {
+    const int key = active ? le : -1;
+    const double part = segmented_sum((double)pw, key, lane);
+    const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+    if (active && (lane == 0 || prev_key != key)) {
+      const int first_warp = (le * N) >> 5;
+      s_part[le * p.part_stride + (warp - first_warp)] = part;
+    }
+  }
+  int any_due = 0;
+  if (interp_mode) {
+    __syncthreads();
+    any_due = __syncthreads_or(active ? s_env[le].due : 0);
+  } else {
+    __syncthreads();
+  }
 
-  // ---------------- phase B: per env (one warp each) ------------------------------------
-  for (int le2 = warp; le2 < genvs; le2 += nwarps) {
-    const int e2 = env0 + le2;
-    double acc = 0.0;
-    for (int i = lane; i < N; i += 32) acc += (double)s_pw[le2 * N + i];
-    acc = warp_sum(acc);
-    double pmean = 0.0, pmax = 0.0;
-    if (need_pen) {
+  // every thread now knows its env's power: sum the warp partials in warp order
+  double P = 0.0;
+  if (active) {
+    const int first_warp = (le * N) >> 5, last_warp = (le * N + N - 1) >> 5;
+    for (int w = 0; w <= last_warp - first_warp; ++w) P += s_part[le * p.part_stride + w];
+  }
+
+  // ---------------- phase B (generic penalty modes only): mean / max of the penalties --------
+  if (need_pen) {
+    const int nwarps = blockDim.x >> 5;
+    for (int le2 = warp; le2 < genvs; le2 += nwarps) {
+      double pmean = 0.0, pmax = 0.0;
       for (int i = lane; i < N; i += 32) {
         const double v = s_pen[le2 * N + i];
         pmean += v / N;
@@ -320,87 +453,29 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       }
       pmean = warp_sum(pmean);
       pmax = warp_max(pmax);
+      if (lane == 0) {
+        s_env[le2].pen_mean = pmean;
+        s_env[le2].pen_max = pmax;
+      }
     }
-    if (lane == 0) {
-      EnvScratch& es = s_env[le2];
-      int64_t t = p.t_epoch[e2];
-      if (!reset) t += p.dt;
-      const Calendar cal = calendar_from_epoch(t);
-      const double s_old = p.signal[e2];
-      double od_new = p.od_temp[e2];
-      if (!reset) {
-        // ClusterHouses.compute_OD_temp, :1070-1081
-        const double noise = p.od_noise ? p.od_noise[e2]
-                                        : p.temp_std * philox_normal((uint32_t)e2, p.step_index, STREAM_OD, p.seed);
-        const double amplitude = (p.day_temp - p.night_temp) / 2, bias = (p.day_temp + p.night_temp) / 2;
-        const double delay = -6 + p.phase[e2];
-        const double time_day = cal.hour + cal.minute / 60.0;
-        od_new = amplitude * sin(2 * 3.141592653589793 * (time_day + delay) / 24) + bias;
-        od_new += noise;
-        p.od_temp[e2] = od_new;
-        p.t_epoch[e2] = t;
-      }
-      es.P = acc;
-      es.od_new = od_new;
-      es.pen_mean = pmean;
-      es.pen_max = pmax;
-      es.f_pow = acc * p.inv_norm_sig_agents;
-      es.f_od = (od_new - 20) / 5;
-      if (p.state_flags & MDR_STATE_DAY) {
-        es.f_sin_day = sin(cal.yday * 2 * 3.141592653589793 / 365);
-        es.f_cos_day = cos(cal.yday * 2 * 3.141592653589793 / 365);
-      }
-      if (p.state_flags & MDR_STATE_HOUR) {
-        es.f_sin_hr = sin(cal.hour * 2 * 3.141592653589793 / 24);
-        es.f_cos_hr = cos(cal.hour * 2 * 3.141592653589793 / 24);
-      }
-      es.due = 0;
-      if (observe_only) {
-        es.f_solar = p.solar ? p.solar_gain[e2] / 1000 : 0.0;
-        es.f_sig = s_old * p.inv_norm_sig_agents;
-        continue;
-      }
-      // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
-      const double sp = ((acc - s_old) / N) * ((acc - s_old) / N);
-      es.rew_sig = p.alpha_sig * sp / p.norm_sig_penalty;
-      p.cluster_power[e2] = acc;
-      // solar gain used by this step's update (SingleHouse.current_solar_gain, for the obs)
-      double gain_now = 0.0;
-      if (p.solar) {
-        gain_now = es.gain_now;
-        p.solar_gain[e2] = gain_now;
-      }
-      es.f_solar = gain_now / 1000;
-      if (p.solar) {  // interpolatePower point, :1198-1207
-        es.hour_s = (double)cal.sod;
-        es.date = (double)cal.yday;
-      } else {
-        es.hour_s = 0.0;
-        es.date = 0.0;
-      }
-      int due = 0;
-      double base = p.avg_power_per_hvac * N;  // PowerGrid.step :1248-1249
-      if (interp_mode) {
-        const int tsi = p.time_since_interp[e2] + p.dt;
-        due = tsi >= p.interp_update_period;
-        base = p.base_power[e2];
-        if (!due) p.time_since_interp[e2] = tsi;
-      }
-      es.due = due;
-      if (!due) {
-        double noise = 0.0;
-        if (p.signal_mode == MDR_SIG_PERLIN)
-          noise = p.signal_noise ? p.signal_noise[e2]
-                                 : perlin_noise((double)cal.sod / p.perlin_period, p.perlin_nb_octaves,
-                                                p.perlin_octaves_step, p.seed ^ __double_as_longlong(p.perlin_seed[e2]));
-        const double sig = grid_signal(p, base, cal, noise, p.artificial_ratio[e2], p.max_power[e2]);
-        p.base_power[e2] = base;
-        p.signal[e2] = sig;
-        es.f_sig = sig * p.inv_norm_sig_agents;
-      }
+    __syncthreads();
+  }
+
+  // per-env state written back by the env's first house thread
+  if (active && li == 0 && !observe_only) {
+    const EnvScratch& es = s_env[le];
+    p.cluster_power[e] = P;
+    if (!reset) {
+      p.od_temp[e] = es.od_new;
+      p.t_epoch[e] = (int64_t)es.t_new;
+    }
+    if (p.solar) p.solar_gain[e] = es.gain_now;
+    if (!es.due) {
+      p.base_power[e] = es.base;
+      p.signal[e] = es.sig_new;
+      if (interp_mode) p.time_since_interp[e] = es.tsi;
     }
   }
-  __syncthreads();
 
   // ---------------- phases C/D: interpolation refresh (every interp_update_period) -------
   if (any_due) {
@@ -424,25 +499,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
                                   es.date);
     }
     __syncthreads();
-    for (int le2 = warp; le2 < genvs; le2 += nwarps) {
-      EnvScratch& es = s_env[le2];
-      if (lane == 0 && es.due) {
-        const int e2 = env0 + le2;
-        double base = 0.0;
-        for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le2 * N + i]);  // id order, :1218-1232
-        if (N > nb) base = mul_rn(base, (double)N / (double)nb);
-        const Calendar cal = calendar_from_epoch(p.t_epoch[e2]);
-        double noise = 0.0;
-        if (p.signal_mode == MDR_SIG_PERLIN)
-          noise = p.signal_noise ? p.signal_noise[e2]
-                                 : perlin_noise((double)cal.sod / p.perlin_period, p.perlin_nb_octaves,
-                                                p.perlin_octaves_step, p.seed ^ __double_as_longlong(p.perlin_seed[e2]));
-        const double sig = grid_signal(p, base, cal, noise, p.artificial_ratio[e2], p.max_power[e2]);
-        p.base_power[e2] = base;
-        p.time_since_interp[e2] = 0;
-        p.signal[e2] = sig;
-        es.f_sig = sig * p.inv_norm_sig_agents;
-      }
+    if (active && li == 0 && s_env[le].due) {
+      EnvScratch& es = s_env[le];
+      double base = 0.0;
+      for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);  // id order, :1218-1232
+      if (N > nb) base = mul_rn(base, (double)N / (double)nb);
+      const double sig = grid_signal(p, base, es.time_sec, es.sig_noise, p.artificial_ratio[e], p.max_power[e]);
+      p.base_power[e] = base;
+      p.time_since_interp[e] = 0;
+      p.signal[e] = sig;
+      es.f_sig = sig * p.inv_norm_sig_agents;
     }
     __syncthreads();
   }
@@ -451,46 +517,49 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
   if (active && !reset && p.reward != nullptr) {
     const EnvScratch& es = s_env[le];
     double tp = (double)pen;
-    if (p.temp_penalty_mode == MDR_PEN_COMMON_L2) tp = es.pen_mean;
-    else if (p.temp_penalty_mode == MDR_PEN_COMMON_MAX) tp = es.pen_max;
-    else if (p.temp_penalty_mode == MDR_PEN_MIXTURE)
+    if (pen_mode == MDR_PEN_COMMON_L2) tp = es.pen_mean;
+    else if (pen_mode == MDR_PEN_COMMON_MAX) tp = es.pen_max;
+    else if (pen_mode == MDR_PEN_MIXTURE)
       tp = (p.mix_alpha_ind * tp + p.mix_alpha_common * es.pen_mean + p.mix_alpha_max * es.pen_max) /
            (p.mix_alpha_ind + p.mix_alpha_common + p.mix_alpha_max);
-    reinterpret_cast<R*>(p.reward)[h] = (R)(-1.0 * (p.alpha_temp * tp / p.norm_temp_penalty + es.rew_sig));
+    // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
+    const double dn = (P - es.s_old) * p.inv_n;
+    reinterpret_cast<R*>(p.reward)[h] = (R)(-(tp * p.k_temp + dn * dn * p.k_sig));
   }
 
   if (p.obs == nullptr) return;
-  const int F = p.F, C = p.C;
+  if (warp >= p.house_warps) return;
+  const int F = p.F;
   const int rpp = p.rows_per_pass;
-  R* stage = s_stage + (size_t)warp * rpp * F;
+  R* stage = s_stage + warp * rpp * F;
   const int wrow0 = warp * 32;
   const int nrows_w = max(0, min(32, H - wrow0));
-  R* gobs = reinterpret_cast<R*>(p.obs) + ((size_t)env0 * N + wrow0) * F;
+  R* gobs = reinterpret_cast<R*>(p.obs) + (size_t)((unsigned)env0 * (unsigned)N + (unsigned)wrow0) * F;
   bool issued = false;
   for (int pass0 = 0; pass0 < nrows_w; pass0 += rpp) {
     const int nr = min(rpp, nrows_w - pass0);
     if (lane >= pass0 && lane < pass0 + nr) {
       const EnvScratch& es = s_env[le];
-      R* row = stage + (size_t)(lane - pass0) * F;
+      R* row = stage + (lane - pass0) * F;
       const R inv_lock = (R)1 / lockdur_r;
-      int c = 0;
       // own features, utils.normStateDict order (utils.py:774-840)
-      row[c++] = (ta - 20) * (R)0.2;
-      row[c++] = (tm - 20) * (R)0.2;
-      row[c++] = (target - 20) * (R)0.2;
-      if (p.state_flags & MDR_STATE_THERMAL) row[c++] = (R)es.f_od;
+      row[0] = (tt.x - 20) * (R)0.2;
+      row[1] = (tt.y - 20) * (R)0.2;
+      row[2] = (target - 20) * (R)0.2;
+      int c = 3;
+      if (state_flags & MDR_STATE_THERMAL) row[c++] = (R)es.f_od;
       row[c++] = deadband;
-      if (p.state_flags & MDR_STATE_DAY) { row[c++] = (R)es.f_sin_day; row[c++] = (R)es.f_cos_day; }
-      if (p.state_flags & MDR_STATE_HOUR) { row[c++] = (R)es.f_sin_hr; row[c++] = (R)es.f_cos_hr; }
-      if (p.state_flags & MDR_STATE_SOLAR) row[c++] = (R)es.f_solar;
+      if (state_flags & MDR_STATE_DAY) { row[c++] = (R)es.f_sin_day; row[c++] = (R)es.f_cos_day; }
+      if (state_flags & MDR_STATE_HOUR) { row[c++] = (R)es.f_sin_hr; row[c++] = (R)es.f_cos_hr; }
+      if (state_flags & MDR_STATE_SOLAR) row[c++] = (R)es.f_solar;
       row[c++] = p_on * (R)p.cop_over_def_cap;
-      if (p.state_flags & MDR_STATE_THERMAL) {
+      if (state_flags & MDR_STATE_THERMAL) {
         row[c++] = (R)(p.ua[h] / p.def_ua);
         row[c++] = (R)(p.cm[h] / p.def_cm);
         row[c++] = (R)(p.ca[h] / p.def_ca);
         row[c++] = (R)(p.hm[h] / p.def_hm);
       }
-      if (p.state_flags & MDR_STATE_HVAC) {
+      if (state_flags & MDR_STATE_HVAC) {
         row[c++] = (R)(p.hvac_cop / p.def_cop);
         row[c++] = (R)(p.hvac_latent / p.def_latent);
       }
@@ -499,44 +568,54 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       row[c++] = (R)sso * inv_lock;
       row[c++] = (R)1;
       row[c++] = (R)es.f_sig;
-      row[c++] = (R)es.f_pow;
+      row[c++] = (R)(P * p.inv_norm_sig_agents);
       // messages, SingleHouse.message :624-662 normalised as utils.py:842-868
-      const int half = C >> 1;
-      for (int k = 0; k < C; ++k) {
-        int j;
-        if (p.comm_mode == MDR_COMM_NEIGHBOURS) {  // :816-828
-          j = k < half ? li - half + k : li + 1 + (k - half);
-          if (j < 0) j += N;
-          if (j >= N) j -= N;
-        } else {
-          const size_t base = p.comm_mode == MDR_COMM_TABLE_PER_ENV ? (size_t)e * N * C : 0;
-          j = p.comm_table[base + (size_t)li * C + k];
+      R* mrow = row + c;
+      if (kFast) {
+        // neighbours (:816-828) = the C window entries around this house, skipping itself
+        const T4* win = s_msg + le * ns + li;
+#pragma unroll
+        for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
+          const T4 m = win[k + (k >= half ? 1 : 0)];
+          mrow[4 * k + 0] = m.x;
+          mrow[4 * k + 1] = m.y * inv_lock;
+          mrow[4 * k + 2] = m.z;
+          mrow[4 * k + 3] = m.w;
         }
-        T4 m = s_msg[le * N + j];
-        bool keep = true;
-        if (p.msg_keep) keep = p.msg_keep[h * C + k] != 0;
-        else if (p.comm_defect_prob > 0.0) {
-          const uint4 r = philox4x32((uint32_t)h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
-                                     STREAM_MSG + 16 * (uint32_t)k, p.seed);
-          keep = u01(r.x, r.y) > p.comm_defect_prob;
-        }
-        const R kf = keep ? (R)1 : (R)0;
-        row[c++] = m.x * kf;
-        row[c++] = m.y * inv_lock * kf;
-        row[c++] = m.z * kf;
-        row[c++] = m.w * kf;
-        if (p.msg_flags) {
-          const size_t hj = (size_t)e * N + j;
-          if (p.msg_flags & MDR_MSG_THERMAL) {
-            row[c++] = (R)(p.ua[hj] / p.def_ua) * kf;
-            row[c++] = (R)(p.cm[hj] / p.def_cm) * kf;
-            row[c++] = (R)(p.ca[hj] / p.def_ca) * kf;
-            row[c++] = (R)(p.hm[hj] / p.def_hm) * kf;
+      } else {
+        const size_t tbase = comm_mode == MDR_COMM_TABLE_PER_ENV ? (size_t)e * N * C : 0;
+        for (int k = 0; k < C; ++k) {
+          int j;
+          if (comm_mode == MDR_COMM_NEIGHBOURS) {
+            j = k < half ? li - half + k : li + 1 + (k - half);
+            if (j < 0) j += N;
+            if (j >= N) j -= N;
+          } else {
+            j = p.comm_table[tbase + (size_t)li * C + k];
           }
-          if (p.msg_flags & MDR_MSG_HVAC) {
-            row[c++] = (R)(p.hvac_cop / p.def_cop) * kf;
-            row[c++] = (R)(p.hvac_latent / p.def_latent) * kf;
-            row[c++] = (R)(p.cap[hj] / p.def_cap) * kf;
+          const T4 m = s_msg[le * ns + half + j];
+          bool keep = true;
+          if (has_keep) keep = p.msg_keep[(size_t)h * C + k] != 0;
+          else if (has_defect) {
+            const uint4 r = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                                       STREAM_MSG + 16 * (uint32_t)k, p.seed);
+            keep = u01(r.x, r.y) > p.comm_defect_prob;
+          }
+          const R kf = keep ? (R)1 : (R)0;
+          mrow[0] = m.x * kf; mrow[1] = m.y * inv_lock * kf; mrow[2] = m.z * kf; mrow[3] = m.w * kf;
+          mrow += 4;
+          if (msg_flags) {
+            const size_t hj = (size_t)e * N + j;
+            if (msg_flags & MDR_MSG_THERMAL) {
+              mrow[0] = (R)(p.ua[hj] / p.def_ua) * kf; mrow[1] = (R)(p.cm[hj] / p.def_cm) * kf;
+              mrow[2] = (R)(p.ca[hj] / p.def_ca) * kf; mrow[3] = (R)(p.hm[hj] / p.def_hm) * kf;
+              mrow += 4;
+            }
+            if (msg_flags & MDR_MSG_HVAC) {
+              mrow[0] = (R)(p.hvac_cop / p.def_cop) * kf; mrow[1] = (R)(p.hvac_latent / p.def_latent) * kf;
+              mrow[2] = (R)(p.cap[hj] / p.def_cap) * kf;
+              mrow += 3;
+            }
           }
         }
       }
@@ -574,26 +653,35 @@ static cudaError_t launch_precompute(const KernelParams& kp, cudaStream_t stream
   return cudaGetLastError();
 }
 
-template <typename R, int kMaxThreads>
+template <typename R, int kMaxThreads, bool kFast, int kC>
 static cudaError_t launch_step_t(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(step_kernel<R, kMaxThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           MDR_MAX_SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(step_kernel<R, kMaxThreads, kFast, kC>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
-  step_kernel<R, kMaxThreads><<<g.ctas, g.threads, g.smem_bytes, stream>>>(kp);
+  step_kernel<R, kMaxThreads, kFast, kC><<<g.ctas, g.threads, g.smem_bytes, stream>>>(kp);
   return cudaGetLastError();
+}
+
+template <typename R, bool kFast, int kC>
+static cudaError_t launch_step_f(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  if (g.threads <= 256) return launch_step_t<R, 256, kFast, kC>(kp, g, stream);
+  if (g.threads <= 512) return launch_step_t<R, 512, kFast, kC>(kp, g, stream);
+  return launch_step_t<R, 1024, kFast, kC>(kp, g, stream);
 }
 
 template <typename R>
 static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  if (g.threads <= 256) return launch_step_t<R, 256>(kp, g, stream);
-  if (g.threads <= 512) return launch_step_t<R, 512>(kp, g, stream);
-  return launch_step_t<R, 1024>(kp, g, stream);
+  const bool fast = kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 && kp.msg_flags == 0 &&
+                    kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
+                    !(kp.comm_defect_prob > 0.0);
+  if (fast && kp.C == 10) return launch_step_f<R, true, 10>(kp, g, stream);
+  return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
 
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream) {
@@ -604,9 +692,15 @@ cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int preci
   return precision == MDR_F32 ? launch_step_r<float>(kp, g, stream) : launch_step_r<double>(kp, g, stream);
 }
 
-size_t step_smem_bytes(int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass, int n_features, bool need_val,
-                       bool need_pen, bool has_obs) {
-  return smem_layout(real_bytes, hmax, genvs, nwarps, rows_per_pass, n_features, need_val, need_pen, has_obs).total;
+size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
+                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride) {
+  const SmemLayout L = smem_layout(real_bytes, hmax, genvs, nwarps, rows_per_pass, n_features, need_val, need_pen, has_obs,
+                                   n_comm, part_stride);
+  if (kp) {
+    kp->off_msg = (int)L.off_msg; kp->off_pw = (int)L.off_pw; kp->off_val = (int)L.off_val;
+    kp->off_pen = (int)L.off_pen; kp->off_env = (int)L.off_env; kp->off_stage = (int)L.off_stage;
+  }
+  return L.total;
 }
 
 }  // namespace mdr

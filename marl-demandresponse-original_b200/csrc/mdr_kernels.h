@@ -14,6 +14,9 @@ namespace mdr {
 struct KernelParams {
   // shape / geometry
   int E, N, C, F, G, hmax, rows_per_pass, dt;
+  int off_msg, off_pw, off_val, off_pen, off_env, off_stage;  // shared-memory carve-up (bytes)
+  int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
+  unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)
   int is_reset, comm_mode, state_flags, msg_flags, temp_penalty_mode, solar, base_power_mode, signal_mode;
   int n_sinusoids, interp_update_period, interp_nb_agents, perlin_nb_octaves, perlin_octaves_step, action_source;
   // per-house arrays
@@ -42,7 +45,7 @@ struct KernelParams {
   uint64_t step_index, seed;
   // scalars
   double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
-  double inv_norm_reg_sig, inv_norm_sig_agents, cop_over_def_cap;
+  double inv_norm_reg_sig, inv_norm_sig_agents, cop_over_def_cap, inv_perlin_period, inv_n, k_temp, k_sig;
   double def_ua, def_cm, def_ca, def_hm, def_cop, def_latent, def_cap, hvac_cop, hvac_latent;
   double day_temp, night_temp, temp_std, window_area, shading_coeff, avg_power_per_hvac;
   double sin_periods[MDR_MAX_SINUSOIDS], sin_ratios[MDR_MAX_SINUSOIDS];
@@ -52,12 +55,12 @@ struct KernelParams {
 };
 
 struct Geometry {
-  int envs_per_cta, threads, ctas, rows_per_pass, hmax;
+  int envs_per_cta, threads, ctas, rows_per_pass, hmax, house_warps, pro_warp, part_stride;
   size_t smem_bytes;
 };
 
-size_t step_smem_bytes(int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass, int n_features, bool need_val,
-                       bool need_pen, bool has_obs);
+size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
+                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride);
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);
 cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream);
 
