@@ -157,6 +157,9 @@ static void fill_config(KernelParams& k, const MdrConfig* c) {
   k.cop_over_def_cap = c->hvac_cop / c->def_cap;
   k.inv_perlin_period = c->perlin_period > 0 ? 1.0 / c->perlin_period : 0.0;
   k.inv_n = 1.0 / c->n_houses;
+  k.od_amplitude = (c->day_temp - c->night_temp) / 2;
+  k.od_bias = (c->day_temp + c->night_temp) / 2;
+  k.two_pi_over_24 = 2 * 3.141592653589793 / 24;
   k.k_temp = c->alpha_temp / c->norm_temp_penalty;
   k.k_sig = c->alpha_sig / c->norm_sig_penalty;
   k.def_ua = c->def_ua; k.def_cm = c->def_cm; k.def_ca = c->def_ca; k.def_hm = c->def_hm;
@@ -256,6 +259,11 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   k.hmax = g.hmax;
   k.rows_per_pass = g.rows_per_pass;
   k.div_magic = (unsigned)(4294967296ull / (unsigned)cfg->n_houses) + 1u;
+  {
+    int L = 16;  // 2*nb_octaves + 1 = 11 Philox draws per env in production mode
+    while (L > 1 && L * g.envs_per_cta > 32) L >>= 1;
+    k.pro_lanes = L;
+  }
   k.house_warps = g.house_warps;
   k.pro_warp = g.pro_warp;
   k.part_stride = g.part_stride;

@@ -20,6 +20,10 @@
 
 #include "mdr_device.cuh"
 
+#ifndef MDR_BLOCKS_256
+#define MDR_BLOCKS_256 3  // resident 256-thread CTAs per SM the compiler must allow (register cap 85)
+#endif
+
 namespace mdr {
 
 // ----------------------------------------------------------------------------------------
@@ -204,7 +208,10 @@ __global__ void precompute_kernel(const __grid_constant__ KernelParams p) {
 // warps' global loads and thermal update, so its latency (fp64 sin, Philox) is off the
 // critical path.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ void env_prologue(const KernelParams& p, EnvScratch& es, int e2, bool reset, bool observe_only) {
+__device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& es, int e2, int sub, int L, bool valid,
+                                            bool reset, bool observe_only) {
+  // `L` lanes (a power of two) cooperate on one env: the Philox draws of the production mode are
+  // spread over them; everything else is computed redundantly and written by sub-lane 0.
   // all per-env loads up front (independent, so their latencies overlap)
   const uint32_t t = (uint32_t)p.t_epoch[e2] + (reset ? 0u : (uint32_t)p.dt);
   const double od_prev = p.od_temp[e2];
@@ -227,58 +234,50 @@ __device__ __forceinline__ void env_prologue(const KernelParams& p, EnvScratch& 
 
   Calendar cal = calendar_time(t);
   if (p.solar || (p.state_flags & MDR_STATE_DAY)) calendar_date(cal);
-  if (draw_od) od_noise = p.temp_std * normal_from(philox4x32((uint32_t)e2, (uint32_t)p.step_index,
-                                                             (uint32_t)(p.step_index >> 32), STREAM_OD, p.seed));
-  if (draw_perlin) {
-    // utils.Perlin.calculate_noise (utils.py:1247-1253) with Philox lattice gradients
-    const double x = (double)cal.sod * p.inv_perlin_period;  // time.mktime(...) % 86400 with TZ=UTC, :1297
-    const uint64_t key = p.seed ^ (uint64_t)__double_as_longlong(p.perlin_seed[e2]);
+  if (draw_od || draw_perlin) {  // warp-uniform
+    // utils.Perlin.calculate_noise (utils.py:1247-1253) with Philox lattice gradients: draw d < 2*nb is
+    // lattice corner (d & 1) of octave (d >> 1); the last draw is the outdoor-temperature normal
     const int nb = p.perlin_nb_octaves;
-    const double w_last = 1.0 / (double)((1 << nb) - 1);
-    double noise = 0.0;
-    for (int j = 0; j < nb; ++j) {
-      const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
-      const double fl = floor(xo);
-      double v = 0.0;
-#pragma unroll
-      for (int corner = 0; corner < 2; ++corner) {
-        const uint4 r = philox4x32((uint32_t)((int)fl + corner), 0u, (uint32_t)j, STREAM_PERLIN, key);
-        const double d = xo - (fl + corner);
-        v += perlin_fade(1.0 - fabs(d)) * (2.0 * u01(r.x, r.y) - 1.0) * d;
+    const int n_perlin = draw_perlin ? 2 * nb : 0;
+    const int n_draws = n_perlin + (draw_od ? 1 : 0);
+    const double x = (double)cal.sod * p.inv_perlin_period;  // time.mktime(...) % 86400 with TZ=UTC, :1297
+    const uint64_t pkey = draw_perlin ? p.seed ^ (uint64_t)__double_as_longlong(p.perlin_seed[e2]) : 0;
+    double terms = 0.0, normal = 0.0;
+    for (int d = sub; d < n_draws; d += L) {
+      if (d < n_perlin) {
+        const int j = d >> 1, corner = d & 1;
+        const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
+        const double fl = floor(xo);
+        const uint4 r = philox4x32((uint32_t)((int)fl + corner), 0u, (uint32_t)j, STREAM_PERLIN, pkey);
+        const double dist = xo - (fl + corner);
+        const float fd = 1.0f - fabsf((float)dist);
+        const float fade = fd * fd * fd * (fd * (fd * 6.0f - 15.0f) + 10.0f);
+        const float g = 2.0f * (((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f)) - 1.0f;
+        const float wgt = j == nb - 1 ? 1.0f / (float)((1 << nb) - 1) : 1.0f / (float)(1 << j);
+        terms += (double)(fade * g * wgt) * dist;
+      } else {
+        normal = normal_from(philox4x32((uint32_t)e2, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_OD,
+                                        p.seed));
       }
-      noise += v * (j == nb - 1 ? w_last : scalbn(1.0, -j));
     }
-    sig_noise = noise;
+    for (int o = L >> 1; o > 0; o >>= 1) {
+      terms += __shfl_xor_sync(0xffffffffu, terms, o);
+      normal += __shfl_xor_sync(0xffffffffu, normal, o);
+    }
+    if (draw_perlin) sig_noise = terms;
+    if (draw_od) od_noise = p.temp_std * normal;
   }
   double od_new = od_prev;
   if (!reset) {
-    // ClusterHouses.compute_OD_temp, :1070-1081
-    const double amplitude = (p.day_temp - p.night_temp) / 2, bias = (p.day_temp + p.night_temp) / 2;
-    const double delay = -6 + phase;
-    const double time_day = cal.hour + cal.minute / 60.0;
-    od_new = amplitude * sin(2 * 3.141592653589793 * (time_day + delay) / 24) + bias;
+    // ClusterHouses.compute_OD_temp, :1070-1081 (amplitude, bias and 2*pi/24 folded on the host)
+    const double time_day = cal.hour + cal.minute * (1.0 / 60.0);
+    od_new = p.od_amplitude * sin(p.two_pi_over_24 * (time_day + (-6 + phase))) + p.od_bias;
     od_new += od_noise;
   }
-  es.t_new = t;
-  es.od_new = od_new;
-  es.f_od = (od_new - 20) * 0.2;
-  es.sig_noise = sig_noise;
   // SingleHouse.update_temperature evaluates house_solar_gain at the NEW datetime (:694)
   double gain = (p.solar && !reset) ? solar_gain(cal, p.window_area, p.shading_coeff) : 0.0;
   if (observe_only) gain = solar_prev;
-  es.gain_now = gain;
-  es.f_solar = gain * 1e-3;
-  es.hour_s = p.solar ? (double)cal.sod : 0.0;  // interpolatePower point, :1198-1207
-  es.date = p.solar ? (double)cal.yday : 0.0;
-  es.time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
-  if (p.state_flags & MDR_STATE_DAY) {
-    es.f_sin_day = sin(cal.yday * 2 * 3.141592653589793 / 365);
-    es.f_cos_day = cos(cal.yday * 2 * 3.141592653589793 / 365);
-  }
-  if (p.state_flags & MDR_STATE_HOUR) {
-    es.f_sin_hr = sin(cal.hour * 2 * 3.141592653589793 / 24);
-    es.f_cos_hr = cos(cal.hour * 2 * 3.141592653589793 / 24);
-  }
+  const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
   // PowerGrid.step, :1250-1255: the signal is final now unless an interpolation refresh is due
   int due = 0;
   if (interp_mode && !observe_only) {
@@ -286,22 +285,82 @@ __device__ __forceinline__ void env_prologue(const KernelParams& p, EnvScratch& 
     due = tsi >= p.interp_update_period;
     if (due) tsi = 0;
   }
-  es.tsi = tsi;
-  es.due = due;
-  es.s_old = s_old;
-  es.base = base;
   double sig = s_old;
-  if (!observe_only && !due) sig = grid_signal(p, base, es.time_sec, sig_noise, ratio, max_power);
-  es.sig_new = sig;
-  es.f_sig = sig * p.inv_norm_sig_agents;
+  if (!observe_only && !due) sig = grid_signal(p, base, time_sec, sig_noise, ratio, max_power);
+  if (sub == 0 && valid) {
+    es.t_new = t;
+    es.od_new = od_new;
+    es.f_od = (od_new - 20) * 0.2;
+    es.sig_noise = sig_noise;
+    es.gain_now = gain;
+    es.f_solar = gain * 1e-3;
+    es.hour_s = p.solar ? (double)cal.sod : 0.0;  // interpolatePower point, :1198-1207
+    es.date = p.solar ? (double)cal.yday : 0.0;
+    es.time_sec = time_sec;
+    if (p.state_flags & MDR_STATE_DAY) {
+      es.f_sin_day = sin(cal.yday * 2 * 3.141592653589793 / 365);
+      es.f_cos_day = cos(cal.yday * 2 * 3.141592653589793 / 365);
+    }
+    if (p.state_flags & MDR_STATE_HOUR) {
+      es.f_sin_hr = sin(cal.hour * 2 * 3.141592653589793 / 24);
+      es.f_cos_hr = cos(cal.hour * 2 * 3.141592653589793 / 24);
+    }
+    es.tsi = tsi;
+    es.due = due;
+    es.s_old = s_old;
+    es.base = base;
+    es.sig_new = sig;
+    es.f_sig = sig * p.inv_norm_sig_agents;
+  }
+  return valid ? due : 0;
+}
+
+// CTA barriers as PTX: the dedicated prologue warp and the house warps arrive at barrier 0 from
+// different program points (warp-uniform control flow, equal arrival counts)
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ int cta_or(int pred) {
+  int r;
+  asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; bar.red.or.pred q, 0, p; selp.s32 %0, 1, 0, q; }"
+               : "=r"(r)
+               : "r"(pred)
+               : "memory");
+  return r;
+}
+
+// Body of the dedicated prologue warp (and, when the CTA has no spare warp, of warp 0 before it
+// turns to its houses).  Kept out of line so that none of its register pressure or call-saved
+// state leaks into the house warps' code path.
+__device__ __noinline__ int prologue_warp_main(const KernelParams& p, bool reset, bool observe_only, bool dedicated) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
+  const int lane = threadIdx.x & 31;
+  const int env0 = blockIdx.x * p.G;
+  const int genvs = min(p.G, p.E - env0);
+  const int L = p.pro_lanes, groups = 32 / L;
+  const int sub = lane & (L - 1), grp = lane / L;
+  int my_due = 0;
+  for (int first = 0; first < genvs; first += groups) {  // warp-uniform trip count
+    const int le2 = first + grp;
+    const bool valid = le2 < genvs;
+    const int lec = valid ? le2 : genvs - 1;
+    my_due |= env_prologue(p, s_env[lec], env0 + lec, sub, L, valid, reset, observe_only);
+  }
+  if (!dedicated) return my_due;
+  // barrier sequence of the house warps (see step_kernel)
+  if (p.solar) cta_sync();
+  const int due = p.base_power_mode == MDR_BASE_INTERPOLATION ? cta_or(my_due) : (cta_sync(), 0);
+  if (p.temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2) cta_sync();
+  if (due) { cta_sync(); cta_sync(); }
+  return 0;
 }
 
 // segmented warp reduction over lanes with equal `key` (keys are contiguous runs): afterwards the
 // first lane of every run holds the run's sum (fixed shuffle order => deterministic)
-__device__ __forceinline__ double segmented_sum(double v, int key, int lane) {
+template <typename R>
+__device__ __forceinline__ R segmented_sum(R v, int key, int lane) {
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const double tv = __shfl_down_sync(0xffffffffu, v, o);
+    const R tv = __shfl_down_sync(0xffffffffu, v, o);
     const int tk = __shfl_down_sync(0xffffffffu, key, o);
     if (lane + o < 32 && tk == key) v += tv;
   }
@@ -312,7 +371,7 @@ __device__ __forceinline__ double segmented_sum(double v, int key, int lane) {
 // the fused step kernel
 // ----------------------------------------------------------------------------------------
 template <typename R, int kMaxThreads, bool kFast, int kC>
-__global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(kMaxThreads, kMaxThreads == 256 ? MDR_BLOCKS_256 : 1024 / kMaxThreads) step_kernel(const __grid_constant__ KernelParams p) {
   using T2 = typename Vec<R>::T2;
   using T4 = typename Vec<R>::T4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -329,6 +388,21 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  // the fast instantiation is only launched for plain steps (never for reset / observe)
+  const bool reset = kFast ? false : p.is_reset != 0;  // 1 = reset (grid step + obs), 2 = observe only
+  const bool observe_only = kFast ? false : p.is_reset == 2;
+
+  // ---------------- phase 0: per-env prologue, one lane per env ------------------------------
+  // Normally a dedicated extra warp (no houses) runs it concurrently with the house warps'
+  // loads + thermal update and then only takes part in the barriers.  When the CTA has no room
+  // for an extra warp (N > 992) warp 0 runs it before loading its houses.
+  if (warp >= p.house_warps) {
+    prologue_warp_main(p, reset, observe_only, true);
+    return;
+  }
+  int my_due = 0;
+  if (warp == p.pro_warp) my_due = prologue_warp_main(p, reset, observe_only, false);
+
   const int N = p.N, C = kC > 0 ? kC : p.C;
   const int env0 = blockIdx.x * p.G;
   const int genvs = min(p.G, p.E - env0);
@@ -338,8 +412,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
   const int li = tid - le * N;
   const int e = env0 + le;
   const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
-  const bool reset = p.is_reset != 0;  // 1 = reset (grid step + obs), 2 = observe only
-  const bool observe_only = p.is_reset == 2;
   const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
   const bool need_pen = pen_mode != MDR_PEN_INDIVIDUAL_L2;
 
@@ -350,7 +422,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
   EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
   R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
 
-  // ---------------- phase A loads: issued first so that they overlap the env prologue ------
+  // ---------------- phase A loads ----------------------------------------------------------
   T2 tt = make2((R)0, (R)0);
   T4 ca4 = make4((R)0, (R)0, (R)0, (R)0), cb = ca4;
   T2 cc = make2((R)0, (R)1);
@@ -365,11 +437,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       if (p.action_source == MDR_ACT_ARRAY) cmd = p.actions[h];
     }
   }
-
-  // ---------------- phase 0: per-env prologue by the prologue warp, one lane per env --------
-  if (warp == p.pro_warp)
-    for (int le2 = lane; le2 < genvs; le2 += 32) env_prologue(p, s_env[le2], env0 + le2, reset, observe_only);
-  if (p.solar) __syncthreads();  // the thermal update needs this step's solar gain
+  if (p.solar) cta_sync();  // the thermal update needs this step's solar gain
 
   // ---------------- phase A: per house -------------------------------------------------
   const R target = cb.w, p_on = cb.z, deadband = cc.x, lockdur_r = cc.y;
@@ -417,22 +485,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
     if (need_pen) s_pen[tid] = (double)pen;
   }
   // cluster power: per-warp segmented partial sums (keyed by env), summed per thread after the barrier
-  if (warp < p.house_warps) {
+  {
     const int key = active ? le : -1;
-    const double part = segmented_sum((double)pw, key, lane);
+    const double part = (double)segmented_sum<R>(pw, key, lane);
     const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
     if (active && (lane == 0 || prev_key != key)) {
       const int first_warp = (le * N) >> 5;
       s_part[le * p.part_stride + (warp - first_warp)] = part;
     }
   }
-  int any_due = 0;
-  if (interp_mode) {
-    __syncthreads();
-    any_due = __syncthreads_or(active ? s_env[le].due : 0);
-  } else {
-    __syncthreads();
-  }
+  const int any_due = interp_mode ? cta_or(my_due) : (cta_sync(), 0);
 
   // every thread now knows its env's power: sum the warp partials in warp order
   double P = 0.0;
@@ -443,7 +505,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
 
   // ---------------- phase B (generic penalty modes only): mean / max of the penalties --------
   if (need_pen) {
-    const int nwarps = blockDim.x >> 5;
+    const int nwarps = p.house_warps;
     for (int le2 = warp; le2 < genvs; le2 += nwarps) {
       double pmean = 0.0, pmax = 0.0;
       for (int i = lane; i < N; i += 32) {
@@ -458,7 +520,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
         s_env[le2].pen_max = pmax;
       }
     }
-    __syncthreads();
+    cta_sync();
   }
 
   // per-env state written back by the env's first house thread
@@ -498,7 +560,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       s_val[tid] = interp_eval<R>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, es.od_new - tg, es.hour_s,
                                   es.date);
     }
-    __syncthreads();
+    cta_sync();
     if (active && li == 0 && s_env[le].due) {
       EnvScratch& es = s_env[le];
       double base = 0.0;
@@ -510,7 +572,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
       p.signal[e] = sig;
       es.f_sig = sig * p.inv_norm_sig_agents;
     }
-    __syncthreads();
+    cta_sync();
   }
 
   // ---------------- phase E: reward + observation ----------------------------------------
@@ -528,7 +590,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1024 / kMaxThreads) step_kernel(c
   }
 
   if (p.obs == nullptr) return;
-  if (warp >= p.house_warps) return;
   const int F = p.F;
   const int rpp = p.rows_per_pass;
   R* stage = s_stage + warp * rpp * F;
@@ -677,7 +738,7 @@ static cudaError_t launch_step_f(const KernelParams& kp, const Geometry& g, cuda
 
 template <typename R>
 static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  const bool fast = kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 && kp.msg_flags == 0 &&
+  const bool fast = kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 && kp.msg_flags == 0 &&
                     kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
                     !(kp.comm_defect_prob > 0.0);
   if (fast && kp.C == 10) return launch_step_f<R, true, 10>(kp, g, stream);

@@ -15,6 +15,7 @@ struct KernelParams {
   // shape / geometry
   int E, N, C, F, G, hmax, rows_per_pass, dt;
   int off_msg, off_pw, off_val, off_pen, off_env, off_stage;  // shared-memory carve-up (bytes)
+  int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
   unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)
   int is_reset, comm_mode, state_flags, msg_flags, temp_penalty_mode, solar, base_power_mode, signal_mode;
@@ -45,7 +46,7 @@ struct KernelParams {
   uint64_t step_index, seed;
   // scalars
   double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
-  double inv_norm_reg_sig, inv_norm_sig_agents, cop_over_def_cap, inv_perlin_period, inv_n, k_temp, k_sig;
+  double inv_norm_reg_sig, inv_norm_sig_agents, cop_over_def_cap, inv_perlin_period, inv_n, k_temp, k_sig, od_amplitude, od_bias, two_pi_over_24;
   double def_ua, def_cm, def_ca, def_hm, def_cop, def_latent, def_cap, hvac_cop, hvac_latent;
   double day_temp, night_temp, temp_std, window_area, shading_coeff, avg_power_per_hvac;
   double sin_periods[MDR_MAX_SINUSOIDS], sin_ratios[MDR_MAX_SINUSOIDS];
