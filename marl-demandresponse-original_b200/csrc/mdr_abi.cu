@@ -2,6 +2,7 @@
 // error mapping.  No allocation, no global mutable state besides a per-device "attribute set"
 // latch inside the launcher, no stream synchronisation except in mdr_step_host.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mdr_kernels.h"
@@ -80,7 +81,9 @@ extern "C" int mdr_validate(const MdrConfig* c) {
 static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
   if (N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
-  int gmax = 256 / N;
+  const char* tt_env = getenv("MDR_TARGET_THREADS");  // tuning knob: house threads per CTA
+  const int target_threads = tt_env ? atoi(tt_env) : 256;
+  int gmax = target_threads / N;
   if (gmax < 1) gmax = 1;
   if (gmax > E) gmax = E;
   int G = gmax;
@@ -97,7 +100,7 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   const int part_stride = (N + 31) / 32 + 1;
   const bool need_val = c->base_power_mode == MDR_BASE_INTERPOLATION;
   const bool need_pen = c->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2;
-  int blocks_per_sm = 1024 / threads;
+  int blocks_per_sm = 768 / threads;
   if (blocks_per_sm < 1) blocks_per_sm = 1;
   const size_t budget = (size_t)MDR_MAX_SMEM_BYTES / blocks_per_sm - 1024;
   int rpp = 0;
@@ -263,6 +266,13 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     int L = 16;  // 2*nb_octaves + 1 = 11 Philox draws per env in production mode
     while (L > 1 && L * g.envs_per_cta > 32) L >>= 1;
     k.pro_lanes = L;
+  }
+  k.total_houses = (unsigned)cfg->n_envs * (unsigned)cfg->n_houses;
+  {
+    // distance = the CTAs resident on the whole GPU (148 SMs x CTAs per SM), in houses
+    const char* env = getenv("MDR_PREFETCH_CTAS");
+    int ctas = env ? atoi(env) : 148 * (g.threads <= 256 ? 3 : (g.threads <= 512 ? 2 : 1));
+    k.prefetch_houses = (unsigned)ctas * (unsigned)g.envs_per_cta * (unsigned)cfg->n_houses;
   }
   k.house_warps = g.house_warps;
   k.pro_warp = g.pro_warp;

@@ -164,6 +164,8 @@ __device__ __forceinline__ double warp_max(double v) {
 // ---------------------------------------------------------------------------------------
 // bulk (TMA) shared -> global store of a contiguous, 16-byte aligned tile (SASS: UBLKCP)
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {

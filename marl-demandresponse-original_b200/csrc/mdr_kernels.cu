@@ -318,6 +318,7 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
 // CTA barriers as PTX: the dedicated prologue warp and the house warps arrive at barrier 0 from
 // different program points (warp-uniform control flow, equal arrival counts)
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void house_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 __device__ __forceinline__ int cta_or(int pred) {
   int r;
   asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; bar.red.or.pred q, 0, p; selp.s32 %0, 1, 0, q; }"
@@ -371,7 +372,7 @@ __device__ __forceinline__ R segmented_sum(R v, int key, int lane) {
 // the fused step kernel
 // ----------------------------------------------------------------------------------------
 template <typename R, int kMaxThreads, bool kFast, int kC>
-__global__ void __launch_bounds__(kMaxThreads, kMaxThreads == 256 ? MDR_BLOCKS_256 : 1024 / kMaxThreads) step_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_256 * (256 / kMaxThreads) : 1024 / kMaxThreads) step_kernel(const __grid_constant__ KernelParams p) {
   using T2 = typename Vec<R>::T2;
   using T4 = typename Vec<R>::T4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -423,6 +424,20 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads == 256 ? MDR_BLOCKS_2
   R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
 
   // ---------------- phase A loads ----------------------------------------------------------
+  // L2 prefetch of the tile a CTA `prefetch_ctas` further down the grid will load (about one CTA
+  // lifetime from now): its reads then hit L2 instead of queueing behind the observation write
+  // stream in HBM.  Fire-and-forget, no registers.
+  if (kFast && p.prefetch_houses != 0) {
+    const unsigned hp = h + p.prefetch_houses;
+    if (hp < p.total_houses) {
+      prefetch_l2(reinterpret_cast<const T2*>(p.temps) + hp);
+      prefetch_l2(p.hvac + hp);
+      prefetch_l2(reinterpret_cast<const T4*>(p.coef_a) + hp);
+      prefetch_l2(reinterpret_cast<const T4*>(p.coef_b) + hp);
+      prefetch_l2(reinterpret_cast<const T2*>(p.coef_c) + hp);
+      if (p.action_source == MDR_ACT_ARRAY) prefetch_l2(p.actions + hp);
+    }
+  }
   T2 tt = make2((R)0, (R)0);
   T4 ca4 = make4((R)0, (R)0, (R)0, (R)0), cb = ca4;
   T2 cc = make2((R)0, (R)1);
@@ -494,13 +509,54 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads == 256 ? MDR_BLOCKS_2
       s_part[le * p.part_stride + (warp - first_warp)] = part;
     }
   }
-  const int any_due = interp_mode ? cta_or(my_due) : (cta_sync(), 0);
+  // Fast path with a dedicated prologue warp: the house warps first meet on their own barrier (1),
+  // sum the power and assemble their observation rows, and only then join the prologue warp on
+  // barrier 0 -- its fp64 latency is hidden behind the row assembly.
+  const bool deferred = kFast && p.pro_warp >= p.house_warps && p.obs != nullptr;
+  int any_due = 0;
+  if (deferred) house_sync(p.house_warps * 32);
+  else any_due = interp_mode ? cta_or(my_due) : (cta_sync(), 0);
 
   // every thread now knows its env's power: sum the warp partials in warp order
   double P = 0.0;
   if (active) {
     const int first_warp = (le * N) >> 5, last_warp = (le * N + N - 1) >> 5;
     for (int w = 0; w <= last_warp - first_warp; ++w) P += s_part[le * p.part_stride + w];
+  }
+
+  const int F = p.F;
+  const int rpp = p.rows_per_pass;
+  R* stage = s_stage + warp * rpp * F;
+  const int wrow0 = warp * 32;
+  const int nrows_w = max(0, min(32, H - wrow0));
+  const R inv_lock = (R)1 / lockdur_r;
+  // fast-path row: [T_air, T_mass, target, deadband, cap, on, lockout, sso, 1, signal, power | C x 4 messages]
+  auto fast_row = [&](R* row) {
+    row[0] = (tt.x - 20) * (R)0.2;
+    row[1] = (tt.y - 20) * (R)0.2;
+    row[2] = (target - 20) * (R)0.2;
+    row[3] = deadband;
+    row[4] = p_on * (R)p.cop_over_def_cap;
+    row[5] = (R)on;
+    row[6] = (R)lock;
+    row[7] = (R)sso * inv_lock;
+    row[8] = (R)1;
+    row[10] = (R)(P * p.inv_norm_sig_agents);
+    // neighbours (:816-828) = the C window entries around this house, skipping itself
+    const T4* win = s_msg + le * ns + li;
+    R* mrow = row + 11;
+#pragma unroll
+    for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
+      const T4 m = win[k + (k >= half ? 1 : 0)];
+      mrow[4 * k + 0] = m.x;
+      mrow[4 * k + 1] = m.y * inv_lock;
+      mrow[4 * k + 2] = m.z;
+      mrow[4 * k + 3] = m.w;
+    }
+  };
+  if (deferred) {
+    if (lane < min(rpp, nrows_w)) fast_row(stage + lane * F);
+    any_due = interp_mode ? cta_or(my_due) : (cta_sync(), 0);
   }
 
   // ---------------- phase B (generic penalty modes only): mean / max of the penalties --------
@@ -590,19 +646,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads == 256 ? MDR_BLOCKS_2
   }
 
   if (p.obs == nullptr) return;
-  const int F = p.F;
-  const int rpp = p.rows_per_pass;
-  R* stage = s_stage + warp * rpp * F;
-  const int wrow0 = warp * 32;
-  const int nrows_w = max(0, min(32, H - wrow0));
   R* gobs = reinterpret_cast<R*>(p.obs) + (size_t)((unsigned)env0 * (unsigned)N + (unsigned)wrow0) * F;
   bool issued = false;
   for (int pass0 = 0; pass0 < nrows_w; pass0 += rpp) {
     const int nr = min(rpp, nrows_w - pass0);
-    if (lane >= pass0 && lane < pass0 + nr) {
+    if (kFast) {
+      if (lane >= pass0 && lane < pass0 + nr) {
+        R* row = stage + (lane - pass0) * F;
+        if (!(deferred && pass0 == 0)) fast_row(row);
+        row[9] = (R)s_env[le].f_sig;
+      }
+    } else if (lane >= pass0 && lane < pass0 + nr) {
       const EnvScratch& es = s_env[le];
       R* row = stage + (lane - pass0) * F;
-      const R inv_lock = (R)1 / lockdur_r;
       // own features, utils.normStateDict order (utils.py:774-840)
       row[0] = (tt.x - 20) * (R)0.2;
       row[1] = (tt.y - 20) * (R)0.2;
@@ -632,18 +688,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads == 256 ? MDR_BLOCKS_2
       row[c++] = (R)(P * p.inv_norm_sig_agents);
       // messages, SingleHouse.message :624-662 normalised as utils.py:842-868
       R* mrow = row + c;
-      if (kFast) {
-        // neighbours (:816-828) = the C window entries around this house, skipping itself
-        const T4* win = s_msg + le * ns + li;
-#pragma unroll
-        for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
-          const T4 m = win[k + (k >= half ? 1 : 0)];
-          mrow[4 * k + 0] = m.x;
-          mrow[4 * k + 1] = m.y * inv_lock;
-          mrow[4 * k + 2] = m.z;
-          mrow[4 * k + 3] = m.w;
-        }
-      } else {
+      {
         const size_t tbase = comm_mode == MDR_COMM_TABLE_PER_ENV ? (size_t)e * N * C : 0;
         for (int k = 0; k < C; ++k) {
           int j;
@@ -731,6 +776,7 @@ static cudaError_t launch_step_t(const KernelParams& kp, const Geometry& g, cuda
 
 template <typename R, bool kFast, int kC>
 static cudaError_t launch_step_f(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  if (g.threads <= 128) return launch_step_t<R, 128, kFast, kC>(kp, g, stream);
   if (g.threads <= 256) return launch_step_t<R, 256, kFast, kC>(kp, g, stream);
   if (g.threads <= 512) return launch_step_t<R, 512, kFast, kC>(kp, g, stream);
   return launch_step_t<R, 1024, kFast, kC>(kp, g, stream);
