@@ -125,6 +125,11 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   g->ctas = (E + G - 1) / G;
   g->rows_per_pass = rpp;
   g->smem_bytes = smem;
+  g->pipe_smem_bytes = 0;
+  if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32) {
+    const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, nwarps, F, need_val, has_obs, c->n_comm, part_stride);
+    if (ps <= (size_t)MDR_MAX_SMEM_BYTES) g->pipe_smem_bytes = ps;
+  }
   return MDR_OK;
 }
 
@@ -282,8 +287,13 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
                         cfg->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2, out->obs != nullptr, cfg->n_comm, g.part_stride);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);
+  const char* no_pipe = getenv("MDR_NO_PIPELINE");
+  const bool pipe = !(no_pipe && no_pipe[0] == '1') && mdr::pipe_eligible(k, g, cfg->precision);
+  if (pipe)
+    mdr::pipe_smem_layout(&k, g.hmax, g.envs_per_cta, g.house_warps, cfg->n_features,
+                          cfg->base_power_mode == MDR_BASE_INTERPOLATION, out->obs != nullptr, cfg->n_comm, g.part_stride);
   for (int i = 0; i < n_steps; ++i) {
-    err = mdr::launch_step_any(k, g, cfg->precision, stream);
+    err = pipe ? mdr::launch_pipe(k, g, stream) : mdr::launch_step_any(k, g, cfg->precision, stream);
     if (err != cudaSuccess) return cuda_fail(err);
     k.step_index += 1;
   }

@@ -748,6 +748,298 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
 }
 
 // ----------------------------------------------------------------------------------------
+// Persistent, software-pipelined variant of the fast path (fp32, default observation layout,
+// solar gain off, plain steps).  The CTAs stay resident (SMs x CTAs/SM of them) and loop over
+// tiles of G envs:
+//   * the house threads' inputs of tile i+1 are fetched with cp.async into a second shared-memory
+//     stage while tile i is computed (each thread copies and later reads only its own record, so
+//     cp.async.wait_group is the only synchronisation the inputs need);
+//   * the dedicated prologue warp runs one tile ahead, writing a double-buffered EnvScratch;
+//   * the bulk (TMA) observation store of tile i drains while tile i+1 is loaded and updated.
+// Barrier 1 = house warps only (power partial sums), barrier 0 = all warps (prologue hand-over).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_16(void* s, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+__device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
+  const int lane = threadIdx.x & 31;
+  const int L = p.pro_lanes, groups = 32 / L;
+  const int sub = lane & (L - 1), grp = lane / L;
+  const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const int env0 = tile * p.G;
+    const int genvs = min(p.G, p.E - env0);
+    EnvScratch* buf = s_env + (it & 1) * p.G;
+    int my_due = 0;
+    for (int first = 0; first < genvs; first += groups) {
+      const int le2 = first + grp;
+      const bool valid = le2 < genvs;
+      const int lec = valid ? le2 : genvs - 1;
+      my_due |= env_prologue(p, buf[lec], env0 + lec, sub, L, valid, false, false);
+    }
+    const int due = interp_mode ? cta_or(my_due) : (cta_sync(), 0);
+    if (due) { cta_sync(); cta_sync(); }
+  }
+}
+
+template <int kC>
+__global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
+  using R = float;
+  using T2 = float2;
+  using T4 = float4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (warp >= p.house_warps) {
+    prologue_pipe_main(p);
+    return;
+  }
+  const int N = p.N, C = kC > 0 ? kC : p.C, G = p.G;
+  const int half = C >> 1, ns = N + C;
+  const int T = p.hmax;  // house threads per CTA
+  const int le = tid < G * N ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;
+  const int li = tid - le * N;
+  const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
+
+  T4* s_msg = reinterpret_cast<T4*>(smem_raw + p.off_msg);
+  double* s_part = reinterpret_cast<double*>(smem_raw + p.off_pw);
+  double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
+  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
+  R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
+  // input stage s: [coef_a T x 16][coef_b T x 16][temps T x 8][coef_c T x 8][hvac T x 4]
+  unsigned char* s_in = smem_raw + p.off_in;
+  const int in_stride = T * 52;
+  auto in_ptr = [&](int s, int off, int elem) { return s_in + s * in_stride + T * off + tid * elem; };
+  auto issue_tile = [&](int tile, int s) {
+    const int env0 = tile * G;
+    const int H = min(G, p.E - env0) * N;
+    if (tid < H) {
+      const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
+      cp_async_16(in_ptr(s, 0, 16), reinterpret_cast<const T4*>(p.coef_a) + h);
+      cp_async_16(in_ptr(s, 16, 16), reinterpret_cast<const T4*>(p.coef_b) + h);
+      cp_async_8(in_ptr(s, 32, 8), reinterpret_cast<const T2*>(p.temps) + h);
+      cp_async_8(in_ptr(s, 40, 8), reinterpret_cast<const T2*>(p.coef_c) + h);
+      cp_async_4(in_ptr(s, 48, 4), p.hvac + h);
+    }
+  };
+  // action byte and outdoor temperature of the next tile travel in registers
+  auto fetch_scalars = [&](int tile, int& cmd, R& od) {
+    const int env0 = tile * G;
+    const int H = min(G, p.E - env0) * N;
+    cmd = 0;
+    od = 0;
+    if (tid < H) {
+      const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
+      if (p.action_source == MDR_ACT_ARRAY) cmd = p.actions[h];
+      od = (R)p.od_temp[env0 + le];
+    }
+  };
+
+  int tile = blockIdx.x;
+  int cmd_next = 0;
+  R od_next = 0;
+  if (tile < p.n_tiles) {
+    issue_tile(tile, 0);
+    fetch_scalars(tile, cmd_next, od_next);
+  }
+  cp_async_commit();
+  const int F = p.F;
+  R* stage = s_stage + warp * 32 * F;
+  const int wrow0 = warp * 32;
+
+  for (int it = 0; tile < p.n_tiles; ++it, tile += gridDim.x) {
+    const int sbuf = it & 1;
+    const int env0 = tile * G;
+    const int genvs = min(G, p.E - env0);
+    const int H = genvs * N;
+    const bool active = tid < H;
+    const int e = env0 + le;
+    const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
+    int cmd = cmd_next;
+    const R od_old = od_next;
+    const int next = tile + gridDim.x;
+    if (next < p.n_tiles) {
+      issue_tile(next, sbuf ^ 1);
+      fetch_scalars(next, cmd_next, od_next);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();  // this thread's copies of the current tile have landed
+
+    // ---------------- phase A: per house ---------------------------------------------------
+    T2 tt = make2(0.f, 0.f);
+    R target = 0, p_on = 0, deadband = 0, lockdur_r = 1, pen = 0, pw = 0;
+    int on = 0, lock = 0, sso = 0;
+    if (active) {
+      const T4 ca4 = *reinterpret_cast<const T4*>(in_ptr(sbuf, 0, 16));
+      const T4 cb = *reinterpret_cast<const T4*>(in_ptr(sbuf, 16, 16));
+      tt = *reinterpret_cast<const T2*>(in_ptr(sbuf, 32, 8));
+      const T2 cc = *reinterpret_cast<const T2*>(in_ptr(sbuf, 40, 8));
+      const int hv = *reinterpret_cast<const int*>(in_ptr(sbuf, 48, 4));
+      target = cb.w; p_on = cb.z; deadband = cc.x; lockdur_r = cc.y;
+      on = hv & 1; lock = (hv >> 1) & 1; sso = hv >> 2;
+      if (p.action_source == MDR_ACT_ARRAY) cmd = cmd != 0;
+      else if (p.action_source == MDR_ACT_BANGBANG) cmd = tt.x > target;
+      else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
+      // HVAC.step, :475-492
+      const int dt = p.dt;
+      const int lockdur = (int)lockdur_r;
+      if (!on) sso += dt;
+      lock = !(on || sso >= lockdur);
+      const int new_on = lock ? 0 : cmd;
+      if (!lock && new_on) sso = 0;
+      if (!lock && !new_on && sso + dt < lockdur) lock = 1;
+      on = new_on;
+      // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature
+      const R qa = on ? cb.y : (R)0;
+      const R tss = od_old + qa * cb.x;
+      const R x = tt.x - tss, y = tt.y - tss;
+      tt.x = tt.x + (ca4.x * x + ca4.y * y);
+      tt.y = tt.y + (ca4.z * x + ca4.w * y);
+      reinterpret_cast<T2*>(p.temps)[h] = tt;
+      p.hvac[h] = (sso << 2) | (lock << 1) | on;
+      pw = on ? p_on : (R)0;
+      const R inv_norm = (R)p.inv_norm_reg_sig;
+      const T4 m = make4((tt.x - target) * 0.2f, (R)sso, pw * inv_norm, p_on * inv_norm);
+      T4* win = s_msg + le * ns;
+      win[half + li] = m;
+      if (li < C - half) win[half + N + li] = m;
+      if (li >= N - half) win[li - (N - half)] = m;
+      const R hi = target + deadband / 2, lo = target - deadband / 2;
+      if (hi < tt.x) pen = (tt.x - hi) * (tt.x - hi);
+      else if (lo > tt.x) pen = (lo - tt.x) * (lo - tt.x);
+    }
+    {
+      const int key = active ? le : -1;
+      const double part = (double)segmented_sum<R>(pw, key, lane);
+      const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+      if (active && (lane == 0 || prev_key != key)) s_part[le * p.part_stride + (warp - ((le * N) >> 5))] = part;
+    }
+    // the staging tile of this warp may still be read by the previous tile's bulk store
+    if (it > 0 && p.obs != nullptr) {
+      if (lane == 0) bulk_wait_read_all();
+      __syncwarp();
+    }
+    house_sync(p.house_warps * 32);
+
+    double P = 0.0;
+    if (active) {
+      const int first_warp = (le * N) >> 5, last_warp = (le * N + N - 1) >> 5;
+      for (int w = 0; w <= last_warp - first_warp; ++w) P += s_part[le * p.part_stride + w];
+    }
+    const int nrows_w = max(0, min(32, H - wrow0));
+    const R inv_lock = (R)1 / lockdur_r;
+    if (p.obs != nullptr && lane < nrows_w) {
+      R* row = stage + lane * F;
+      row[0] = (tt.x - 20) * 0.2f;
+      row[1] = (tt.y - 20) * 0.2f;
+      row[2] = (target - 20) * 0.2f;
+      row[3] = deadband;
+      row[4] = p_on * (R)p.cop_over_def_cap;
+      row[5] = (R)on;
+      row[6] = (R)lock;
+      row[7] = (R)sso * inv_lock;
+      row[8] = 1.f;
+      row[10] = (R)(P * p.inv_norm_sig_agents);
+      const T4* win = s_msg + le * ns + li;
+      R* mrow = row + 11;
+#pragma unroll
+      for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
+        const T4 m = win[k + (k >= half ? 1 : 0)];
+        mrow[4 * k + 0] = m.x;
+        mrow[4 * k + 1] = m.y * inv_lock;
+        mrow[4 * k + 2] = m.z;
+        mrow[4 * k + 3] = m.w;
+      }
+    }
+    // hand-over from the prologue warp (it finished this tile's EnvScratch a whole tile ago)
+    const int any_due = interp_mode ? cta_or(0) : (cta_sync(), 0);
+    EnvScratch* env_buf = s_env + sbuf * G;
+
+    if (active && li == 0) {
+      const EnvScratch& es = env_buf[le];
+      p.cluster_power[e] = P;
+      p.od_temp[e] = es.od_new;
+      p.t_epoch[e] = (int64_t)es.t_new;
+      if (!es.due) {
+        p.base_power[e] = es.base;
+        p.signal[e] = es.sig_new;
+        if (interp_mode) p.time_since_interp[e] = es.tsi;
+      }
+    }
+    if (any_due) {
+      const int nb = p.interp_nb_agents;
+      const int nsamp = N <= nb ? N : nb;
+      if (active && env_buf[le].due && li < nsamp) {
+        int src = li;
+        if (N > nb) {
+          if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
+          else {
+            const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                                       STREAM_IDS + 16 * (uint32_t)li, p.seed);
+            src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
+          }
+        }
+        const size_t hs = (size_t)e * N + src;
+        const T2 t2 = reinterpret_cast<const T2*>(p.temps)[hs];
+        const double tg = (double)reinterpret_cast<const T4*>(p.coef_b)[hs].w;
+        const EnvScratch& es = env_buf[le];
+        s_val[tid] = interp_eval<R>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, es.od_new - tg, es.hour_s,
+                                    es.date);
+      }
+      cta_sync();
+      if (active && li == 0 && env_buf[le].due) {
+        EnvScratch& es = env_buf[le];
+        double base = 0.0;
+        for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);
+        if (N > nb) base = mul_rn(base, (double)N / (double)nb);
+        const double sig = grid_signal(p, base, es.time_sec, es.sig_noise, p.artificial_ratio[e], p.max_power[e]);
+        p.base_power[e] = base;
+        p.time_since_interp[e] = 0;
+        p.signal[e] = sig;
+        es.f_sig = sig * p.inv_norm_sig_agents;
+      }
+      cta_sync();
+    }
+    if (active && p.reward != nullptr) {
+      const EnvScratch& es = env_buf[le];
+      const double dn = (P - es.s_old) * p.inv_n;
+      reinterpret_cast<R*>(p.reward)[h] = (R)(-((double)pen * p.k_temp + dn * dn * p.k_sig));
+    }
+    if (p.obs != nullptr && nrows_w > 0) {
+      if (lane < nrows_w) stage[lane * F + 9] = (R)env_buf[le].f_sig;
+      R* dst = reinterpret_cast<R*>(p.obs) + (size_t)((unsigned)env0 * (unsigned)N + (unsigned)wrow0) * F;
+      const uint32_t bytes = (uint32_t)(nrows_w * F * sizeof(R));
+      const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
+      if (bulk_ok) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store_s2g(dst, stage, bytes);
+      } else {
+        __syncwarp();
+        for (int i = lane; i < nrows_w * F; i += 32) dst[i] = stage[i];
+        __syncwarp();
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (lane == 0) bulk_wait_read_all();
+}
+
+// ----------------------------------------------------------------------------------------
 // host-side launch helpers
 // ----------------------------------------------------------------------------------------
 template <typename R>
@@ -791,12 +1083,69 @@ static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cuda
   return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
 
+template <int kC>
+static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, cudaStream_t stream) {
+  static int ctas_per_sm[64] = {};
+  static int sm_count[64] = {};
+  static int cached_threads[64] = {};
+  static size_t cached_smem[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64) return cudaErrorInvalidDevice;
+  if (sm_count[dev] == 0) {
+    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
+    if (err != cudaSuccess) return err;
+    err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (err != cudaSuccess) return err;
+  }
+  if (cached_threads[dev] != g.threads || cached_smem[dev] != g.pipe_smem_bytes) {
+    int n = 0;
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC>, g.threads, g.pipe_smem_bytes);
+    if (err != cudaSuccess) return err;
+    if (n < 1) return cudaErrorLaunchOutOfResources;
+    ctas_per_sm[dev] = n;
+    cached_threads[dev] = g.threads;
+    cached_smem[dev] = g.pipe_smem_bytes;
+  }
+  KernelParams kp = kp_in;
+  kp.n_tiles = g.ctas;
+  int grid = sm_count[dev] * ctas_per_sm[dev];
+  if (grid > g.ctas) grid = g.ctas;
+  step_pipe_kernel<kC><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  return kp.C == 10 ? launch_pipe_t<10>(kp, g, stream) : launch_pipe_t<0>(kp, g, stream);
+}
+
+bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision) {
+  return precision == MDR_F32 && kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 &&
+         kp.msg_flags == 0 && kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
+         !(kp.comm_defect_prob > 0.0) && !kp.solar && g.pro_warp >= g.house_warps && g.threads <= 256 &&
+         g.rows_per_pass == 32 && g.pipe_smem_bytes > 0;
+}
+
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream) {
   return precision == MDR_F32 ? launch_precompute<float>(kp, stream) : launch_precompute<double>(kp, stream);
 }
 
 cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream) {
   return precision == MDR_F32 ? launch_step_r<float>(kp, g, stream) : launch_step_r<double>(kp, g, stream);
+}
+
+// layout of the pipelined kernel: the classic layout with a double EnvScratch plus two input stages
+size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int nwarps, int n_features, bool need_val, bool has_obs,
+                        int n_comm, int part_stride) {
+  SmemLayout L = smem_layout(4, hmax, 2 * genvs, nwarps, 32, n_features, need_val, false, has_obs, n_comm, part_stride);
+  const size_t off_in = L.total;
+  const size_t total = off_in + align16((size_t)2 * hmax * 52);
+  if (kp) {
+    kp->off_msg = (int)L.off_msg; kp->off_pw = (int)L.off_pw; kp->off_val = (int)L.off_val;
+    kp->off_pen = (int)L.off_pen; kp->off_env = (int)L.off_env; kp->off_stage = (int)L.off_stage;
+    kp->off_in = (int)off_in;
+  }
+  return total;
 }
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
