@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDR_ABI_VERSION 4
+#define MDR_ABI_VERSION 5
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
@@ -186,9 +186,11 @@ int mdr_obs_width(const MdrConfig *cfg);
    (env/MA_DemandResponse.py:249,324,898,1169,1306). */
 int mdr_validate(const MdrConfig *cfg);
 
-/* Launch geometry the step kernel will use (for tests and the roofline report). */
+/* Launch geometry the step kernel will use (for tests and the roofline report).  `ctas` counts the
+   G-env tiles; `pipelined` is 1 when a plain production-mode step of this configuration runs the
+   persistent software-pipelined kernel (grid = SMs x resident CTAs, looping over the tiles). */
 int mdr_launch_geometry(const MdrConfig *cfg, int has_obs, int32_t *envs_per_cta, int32_t *threads,
-                        int32_t *ctas, size_t *smem_bytes);
+                        int32_t *ctas, size_t *smem_bytes, int32_t *pipelined);
 
 /* Replaces the per-step recomputation of a,b,c,r1,r2,A3,A4,exp(r*dt) in
    SingleHouse.update_temperature (:704-735) and HVAC.get_Q/power_consumption (:494-523):

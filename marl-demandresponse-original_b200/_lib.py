@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-MDR_ABI_VERSION = 4
+MDR_ABI_VERSION = 5
 MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
@@ -95,7 +95,7 @@ def load(build_if_missing: bool = True):
     P = C.POINTER
     lib.mdr_obs_width.argtypes = [P(MdrConfig)]
     lib.mdr_validate.argtypes = [P(MdrConfig)]
-    lib.mdr_launch_geometry.argtypes = [P(MdrConfig), C.c_int, P(_i32), P(_i32), P(_i32), P(C.c_size_t)]
+    lib.mdr_launch_geometry.argtypes = [P(MdrConfig), C.c_int, P(_i32), P(_i32), P(_i32), P(C.c_size_t), P(_i32)]
     lib.mdr_precompute.argtypes = [P(MdrConfig), P(MdrHouses), _vp]
     step_args = [P(MdrConfig), P(MdrHouses), P(MdrEnvs), P(MdrStepInputs), P(MdrOutputs)]
     lib.mdr_reset.argtypes = step_args + [_vp]

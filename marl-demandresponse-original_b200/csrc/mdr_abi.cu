@@ -78,6 +78,8 @@ extern "C" int mdr_validate(const MdrConfig* c) {
   return MDR_OK;
 }
 
+static void fill_config(KernelParams& k, const MdrConfig* c);
+
 static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
   if (N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
@@ -134,7 +136,7 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
 }
 
 extern "C" int mdr_launch_geometry(const MdrConfig* cfg, int has_obs, int32_t* envs_per_cta, int32_t* threads,
-                                   int32_t* ctas, size_t* smem_bytes) {
+                                   int32_t* ctas, size_t* smem_bytes, int32_t* pipelined) {
   int st = mdr_validate(cfg);
   if (st != MDR_OK) return st;
   Geometry g;
@@ -143,7 +145,12 @@ extern "C" int mdr_launch_geometry(const MdrConfig* cfg, int has_obs, int32_t* e
   if (envs_per_cta) *envs_per_cta = g.envs_per_cta;
   if (threads) *threads = g.threads;
   if (ctas) *ctas = g.ctas;
-  if (smem_bytes) *smem_bytes = g.smem_bytes;
+  KernelParams k;
+  fill_config(k, cfg);
+  const char* no_pipe = getenv("MDR_NO_PIPELINE");
+  const bool pipe = !(no_pipe && no_pipe[0] == '1') && mdr::pipe_eligible(k, g, cfg->precision);
+  if (smem_bytes) *smem_bytes = pipe ? g.pipe_smem_bytes : g.smem_bytes;
+  if (pipelined) *pipelined = pipe ? 1 : 0;
   return MDR_OK;
 }
 

@@ -837,7 +837,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     }
   };
   // action byte and outdoor temperature of the next tile travel in registers
-  auto fetch_scalars = [&](int tile, int& cmd, R& od) {
+  // (kept as loaded -- converting here would stall on the load instead of letting it fly)
+  auto fetch_scalars = [&](int tile, int& cmd, double& od) {
     const int env0 = tile * G;
     const int H = min(G, p.E - env0) * N;
     cmd = 0;
@@ -845,13 +846,13 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     if (tid < H) {
       const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
       if (p.action_source == MDR_ACT_ARRAY) cmd = p.actions[h];
-      od = (R)p.od_temp[env0 + le];
+      od = p.od_temp[env0 + le];
     }
   };
 
   int tile = blockIdx.x;
   int cmd_next = 0;
-  R od_next = 0;
+  double od_next = 0;
   if (tile < p.n_tiles) {
     issue_tile(tile, 0);
     fetch_scalars(tile, cmd_next, od_next);
@@ -870,7 +871,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const int e = env0 + le;
     const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
     int cmd = cmd_next;
-    const R od_old = od_next;
+    const R od_old = (R)od_next;
     const int next = tile + gridDim.x;
     if (next < p.n_tiles) {
       issue_tile(next, sbuf ^ 1);

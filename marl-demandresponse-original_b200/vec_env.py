@@ -292,10 +292,11 @@ class VecDemandResponseEnv:
         return self.hvac >> 2
 
     def launch_geometry(self):
-        g, t, c, s = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t()
+        g, t, c, s, pl = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t(), C.c_int32()
         _lib.check(self.lib.mdr_launch_geometry(self._refs[0], int(self.with_obs), C.byref(g), C.byref(t), C.byref(c),
-                                                C.byref(s)), "mdr_launch_geometry")
-        return dict(envs_per_cta=g.value, threads=t.value, ctas=c.value, smem_bytes=s.value)
+                                                C.byref(s), C.byref(pl)), "mdr_launch_geometry")
+        return dict(envs_per_cta=g.value, threads=t.value, tiles=c.value, smem_bytes=s.value,
+                    kernel="mdr::step_pipe_kernel (persistent, software-pipelined)" if pl.value else "mdr::step_kernel")
 
     # ------------------------------------------------------------------ checkpoint / copy
     _STATE = ("coef_a", "coef_b", "coef_c", "interp_key", "temps", "hvac", "lockout_dur", "t_epoch",

@@ -79,8 +79,15 @@ def test_launch_geometry():
         for prec in (_lib.F32, _lib.F64):
             s = flat.to_struct(e, prec, 0)
             g, t, c, sm = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_size_t()
+            pl = ctypes.c_int32()
             assert lib.mdr_launch_geometry(ctypes.byref(s), 1, ctypes.byref(g), ctypes.byref(t), ctypes.byref(c),
-                                           ctypes.byref(sm)) == 0
+                                           ctypes.byref(sm), ctypes.byref(pl)) == 0
+            assert pl.value == 0  # solar gain is on in the shipped default -> classic kernel
+            cfg2 = __import__('copy').deepcopy(cfg)
+            cfg2['default_house_prop']['solar_gain_bool'] = False
+            s2 = mdr_b200.FlatConfig(cfg2).to_struct(e, prec, 0)
+            assert lib.mdr_launch_geometry(ctypes.byref(s2), 1, None, None, None, None, ctypes.byref(pl)) == 0
+            assert pl.value == (1 if (prec == _lib.F32 and n <= 100) else 0)  # persistent pipelined kernel
             assert g.value * n <= t.value <= 1024 and t.value % 32 == 0
             assert c.value == -(-e // g.value)
             assert sm.value <= 227 * 1024
