@@ -279,13 +279,6 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     while (L > 1 && L * g.envs_per_cta > 32) L >>= 1;
     k.pro_lanes = L;
   }
-  k.total_houses = (unsigned)cfg->n_envs * (unsigned)cfg->n_houses;
-  {
-    // distance = the CTAs resident on the whole GPU (148 SMs x CTAs per SM), in houses
-    const char* env = getenv("MDR_PREFETCH_CTAS");
-    int ctas = env ? atoi(env) : 148 * (g.threads <= 256 ? 3 : (g.threads <= 512 ? 2 : 1));
-    k.prefetch_houses = (unsigned)ctas * (unsigned)g.envs_per_cta * (unsigned)cfg->n_houses;
-  }
   k.house_warps = g.house_warps;
   k.pro_warp = g.pro_warp;
   k.part_stride = g.part_stride;

@@ -131,22 +131,6 @@ __device__ __forceinline__ double solar_gain(const Calendar& c, double window_ar
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double perlin_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
 
-// one lattice term of one octave: lane = 2*octave + corner.  Summing the terms of all lanes gives
-// utils.Perlin.calculate_noise (weights 1/2^j for the first nb-1 octaves, 1/(2^nb - 1) for the last).
-__device__ __forceinline__ double perlin_term(double x, int j, int corner, int nb_octaves, int octaves_step,
-                                              const uint4 r) {
-  const int octaves = (1 << j) * octaves_step;
-  const double xo = x * octaves;
-  const double d = xo - (floor(xo) + corner);
-  const double g = 2.0 * u01(r.x, r.y) - 1.0;
-  const double wgt = j == nb_octaves - 1 ? 1.0 / (double)((1 << nb_octaves) - 1) : 1.0 / (double)(1 << j);
-  return perlin_fade(1.0 - fabs(d)) * g * d * wgt;
-}
-
-__device__ __forceinline__ uint32_t perlin_lattice(double x, int j, int corner, int octaves_step) {
-  return (uint32_t)((int)floor(x * ((1 << j) * octaves_step)) + corner);
-}
-
 // ---------------------------------------------------------------------------------------
 // warp reductions (fixed shuffle tree => run-to-run deterministic)
 // ---------------------------------------------------------------------------------------
@@ -164,8 +148,6 @@ __device__ __forceinline__ double warp_max(double v) {
 // ---------------------------------------------------------------------------------------
 // bulk (TMA) shared -> global store of a contiguous, 16-byte aligned tile (SASS: UBLKCP)
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
-
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {

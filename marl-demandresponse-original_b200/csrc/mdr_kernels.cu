@@ -424,20 +424,6 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
 
   // ---------------- phase A loads ----------------------------------------------------------
-  // L2 prefetch of the tile a CTA `prefetch_ctas` further down the grid will load (about one CTA
-  // lifetime from now): its reads then hit L2 instead of queueing behind the observation write
-  // stream in HBM.  Fire-and-forget, no registers.
-  if (kFast && p.prefetch_houses != 0) {
-    const unsigned hp = h + p.prefetch_houses;
-    if (hp < p.total_houses) {
-      prefetch_l2(reinterpret_cast<const T2*>(p.temps) + hp);
-      prefetch_l2(p.hvac + hp);
-      prefetch_l2(reinterpret_cast<const T4*>(p.coef_a) + hp);
-      prefetch_l2(reinterpret_cast<const T4*>(p.coef_b) + hp);
-      prefetch_l2(reinterpret_cast<const T2*>(p.coef_c) + hp);
-      if (p.action_source == MDR_ACT_ARRAY) prefetch_l2(p.actions + hp);
-    }
-  }
   T2 tt = make2((R)0, (R)0);
   T4 ca4 = make4((R)0, (R)0, (R)0, (R)0), cb = ca4;
   T2 cc = make2((R)0, (R)1);
