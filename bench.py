@@ -36,8 +36,11 @@ WORKLOADS = {
                desc="BASELINE config 4 per-GPU shard: 16384 envs x 100 houses, on-device interpolation"),
     "c2": dict(envs=4096, houses=50, interp=False, action_source="array", obs=True,
                desc="BASELINE config 2: 4096 envs x 50 houses (PPO/MAPPO rollout shape)"),
-    "c3": dict(envs=1000, houses=1000, interp=False, action_source="bangbang", obs=False,
-               desc="BASELINE config 3: 1M houses (1000 x 1000), on-device bang-bang, no per-step observation"),
+    "c3": dict(envs=10000, houses=100, interp=False, action_source="bangbang", obs=False,
+               desc="BASELINE config 3: 1M houses (10000 clusters x 100), heterogeneous parameters + lockout, on-device "
+                    "bang-bang, no per-step observation"),
+    "c3big": dict(envs=1000, houses=1000, interp=False, action_source="bangbang", obs=False,
+                  desc="BASELINE config 3 as 1000 clusters x 1000 houses (one cluster per CTA, generic kernel)"),
 }
 
 

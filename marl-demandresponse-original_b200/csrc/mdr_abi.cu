@@ -84,7 +84,7 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
   if (N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
   const char* tt_env = getenv("MDR_TARGET_THREADS");  // tuning knob: house threads per CTA
-  const int target_threads = tt_env ? atoi(tt_env) : 256;
+  const int target_threads = tt_env ? atoi(tt_env) : 224;  // + 32 for the prologue warp = 256
   int gmax = target_threads / N;
   if (gmax < 1) gmax = 1;
   if (gmax > E) gmax = E;
@@ -129,7 +129,7 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   g->smem_bytes = smem;
   g->pipe_smem_bytes = 0;
   if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32) {
-    const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, nwarps, F, need_val, has_obs, c->n_comm, part_stride);
+    const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride);
     if (ps <= (size_t)MDR_MAX_SMEM_BYTES) g->pipe_smem_bytes = ps;
   }
   return MDR_OK;
@@ -290,7 +290,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   const char* no_pipe = getenv("MDR_NO_PIPELINE");
   const bool pipe = !(no_pipe && no_pipe[0] == '1') && mdr::pipe_eligible(k, g, cfg->precision);
   if (pipe)
-    mdr::pipe_smem_layout(&k, g.hmax, g.envs_per_cta, g.house_warps, cfg->n_features,
+    mdr::pipe_smem_layout(&k, g.hmax, g.envs_per_cta, cfg->n_houses, cfg->n_features,
                           cfg->base_power_mode == MDR_BASE_INTERPOLATION, out->obs != nullptr, cfg->n_comm, g.part_stride);
   for (int i = 0; i < n_steps; ++i) {
     err = pipe ? mdr::launch_pipe(k, g, stream) : mdr::launch_step_any(k, g, cfg->precision, stream);

@@ -758,18 +758,49 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
+// mbarrier hand-over between the prologue warp (producer of EnvScratch) and the house warps
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// shared-memory control block of the pipelined kernel (at off_ctl)
+struct PipeCtl {
+  uint64_t full[2];   // prologue -> house warps: EnvScratch buffer b is ready   (count 1)
+  uint64_t empty[2];  // house warps -> prologue: buffer b may be overwritten     (count house_warps)
+  int tile_due[2];    // any env of the tile has an interpolation refresh due
+  int pad[2];
+};
+
 __device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
+  PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
   const int lane = threadIdx.x & 31;
   const int L = p.pro_lanes, groups = 32 / L;
   const int sub = lane & (L - 1), grp = lane / L;
-  const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
   int it = 0;
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    if (it >= 2) mbar_wait(&ctl->empty[b], ((it >> 1) & 1) ^ 1);  // house warps are done with tile it-2
     const int env0 = tile * p.G;
     const int genvs = min(p.G, p.E - env0);
-    EnvScratch* buf = s_env + (it & 1) * p.G;
+    EnvScratch* buf = s_env + b * p.G;
     int my_due = 0;
     for (int first = 0; first < genvs; first += groups) {
       const int le2 = first + grp;
@@ -777,8 +808,10 @@ __device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
       const int lec = valid ? le2 : genvs - 1;
       my_due |= env_prologue(p, buf[lec], env0 + lec, sub, L, valid, false, false);
     }
-    const int due = interp_mode ? cta_or(my_due) : (cta_sync(), 0);
-    if (due) { cta_sync(); cta_sync(); }
+    my_due = __any_sync(0xffffffffu, my_due);
+    if (lane == 0) ctl->tile_due[b] = my_due;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl->full[b]);
   }
 }
 
@@ -790,6 +823,15 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  if (tid == 0) {
+    mbar_init(&ctl->full[0], 1);
+    mbar_init(&ctl->full[1], 1);
+    mbar_init(&ctl->empty[0], p.house_warps);
+    mbar_init(&ctl->empty[1], p.house_warps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   if (warp >= p.house_warps) {
     prologue_pipe_main(p);
     return;
@@ -797,12 +839,13 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   const int N = p.N, C = kC > 0 ? kC : p.C, G = p.G;
   const int half = C >> 1, ns = N + C;
   const int T = p.hmax;  // house threads per CTA
+  const int house_threads = p.house_warps * 32;
   const int le = tid < G * N ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;
   const int li = tid - le * N;
   const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
 
-  T4* s_msg = reinterpret_cast<T4*>(smem_raw + p.off_msg);
-  double* s_part = reinterpret_cast<double*>(smem_raw + p.off_pw);
+  T4* s_msg_all = reinterpret_cast<T4*>(smem_raw + p.off_msg);        // two windows [G*(N+C)]
+  double* s_part_all = reinterpret_cast<double*>(smem_raw + p.off_pw);  // two [G][part_stride]
   double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
   EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
   R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
@@ -845,8 +888,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   }
   cp_async_commit();
   const int F = p.F;
-  R* stage = s_stage + warp * 32 * F;
   const int wrow0 = warp * 32;
+  R* stage = s_stage + wrow0 * F;  // the tile's rows are contiguous in shared memory, like in HBM
 
   for (int it = 0; tile < p.n_tiles; ++it, tile += gridDim.x) {
     const int sbuf = it & 1;
@@ -856,6 +899,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const bool active = tid < H;
     const int e = env0 + le;
     const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
+    T4* s_msg = s_msg_all + sbuf * (G * ns);
+    double* s_part = s_part_all + sbuf * (G * p.part_stride);
     int cmd = cmd_next;
     const R od_old = (R)od_next;
     const int next = tile + gridDim.x;
@@ -920,7 +965,9 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       if (lane == 0) bulk_wait_read_all();
       __syncwarp();
     }
-    house_sync(p.house_warps * 32);
+    // the only CTA-wide rendezvous of a tile: message window + power partials are complete.
+    // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
+    house_sync(house_threads);
 
     double P = 0.0;
     if (active) {
@@ -952,9 +999,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         mrow[4 * k + 3] = m.w;
       }
     }
-    // hand-over from the prologue warp (it finished this tile's EnvScratch a whole tile ago)
-    const int any_due = interp_mode ? cta_or(0) : (cta_sync(), 0);
+    // hand-over from the prologue warp: it produced this tile's EnvScratch one tile ago
+    mbar_wait(&ctl->full[sbuf], (it >> 1) & 1);
     EnvScratch* env_buf = s_env + sbuf * G;
+    const int any_due = interp_mode ? ctl->tile_due[sbuf] : 0;
 
     if (active && li == 0) {
       const EnvScratch& es = env_buf[le];
@@ -987,7 +1035,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         s_val[tid] = interp_eval<R>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, es.od_new - tg, es.hour_s,
                                     es.date);
       }
-      cta_sync();
+      house_sync(house_threads);
       if (active && li == 0 && env_buf[le].due) {
         EnvScratch& es = env_buf[le];
         double base = 0.0;
@@ -999,7 +1047,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         p.signal[e] = sig;
         es.f_sig = sig * p.inv_norm_sig_agents;
       }
-      cta_sync();
+      house_sync(house_threads);
     }
     if (active && p.reward != nullptr) {
       const EnvScratch& es = env_buf[le];
@@ -1021,6 +1069,9 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         __syncwarp();
       }
     }
+    // this warp is done with EnvScratch buffer `sbuf`: let the prologue warp reuse it for tile it+2
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl->empty[sbuf]);
   }
   cp_async_wait<0>();
   if (lane == 0) bulk_wait_read_all();
@@ -1121,18 +1172,23 @@ cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int preci
   return precision == MDR_F32 ? launch_step_r<float>(kp, g, stream) : launch_step_r<double>(kp, g, stream);
 }
 
-// layout of the pipelined kernel: the classic layout with a double EnvScratch plus two input stages
-size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int nwarps, int n_features, bool need_val, bool has_obs,
+// layout of the pipelined kernel: message window, power partials and EnvScratch double buffered, one
+// contiguous staging tile for the tile's G*N observation rows, two cp.async input stages
+size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int n_features, bool need_val, bool has_obs,
                         int n_comm, int part_stride) {
-  SmemLayout L = smem_layout(4, hmax, 2 * genvs, nwarps, 32, n_features, need_val, false, has_obs, n_comm, part_stride);
-  const size_t off_in = L.total;
-  const size_t total = off_in + align16((size_t)2 * hmax * 52);
+  size_t o = 0;
+  const size_t off_msg = o;   o += align16((size_t)2 * genvs * (n_houses + n_comm) * 4 * sizeof(float));
+  const size_t off_pw = o;    o += align16((size_t)2 * genvs * part_stride * sizeof(double));
+  const size_t off_val = o;   o += need_val ? align16((size_t)hmax * sizeof(double)) : 0;
+  const size_t off_env = o;   o += align16((size_t)2 * genvs * sizeof(EnvScratch));
+  const size_t off_ctl = o;   o += align16(sizeof(PipeCtl));
+  const size_t off_stage = o; o += has_obs ? align16((size_t)genvs * n_houses * n_features * sizeof(float)) : 0;
+  const size_t off_in = o;    o += align16((size_t)2 * hmax * 52);
   if (kp) {
-    kp->off_msg = (int)L.off_msg; kp->off_pw = (int)L.off_pw; kp->off_val = (int)L.off_val;
-    kp->off_pen = (int)L.off_pen; kp->off_env = (int)L.off_env; kp->off_stage = (int)L.off_stage;
-    kp->off_in = (int)off_in;
+    kp->off_msg = (int)off_msg; kp->off_pw = (int)off_pw; kp->off_val = (int)off_val; kp->off_pen = 0;
+    kp->off_env = (int)off_env; kp->off_stage = (int)off_stage; kp->off_in = (int)off_in; kp->off_ctl = (int)off_ctl;
   }
-  return total;
+  return o;
 }
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,

@@ -14,7 +14,7 @@ namespace mdr {
 struct KernelParams {
   // shape / geometry
   int E, N, C, F, G, hmax, rows_per_pass, dt;
-  int off_msg, off_pw, off_val, off_pen, off_env, off_stage, off_in;  // shared-memory carve-up (bytes)
+  int off_msg, off_pw, off_val, off_pen, off_env, off_stage, off_in, off_ctl;  // shared-memory carve-up (bytes)
   int n_tiles;                                                // pipelined kernel: number of G-env tiles
   int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
@@ -63,7 +63,7 @@ struct Geometry {
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
                         int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride);
-size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int nwarps, int n_features, bool need_val, bool has_obs,
+size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int n_features, bool need_val, bool has_obs,
                         int n_comm, int part_stride);
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision);
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream);
