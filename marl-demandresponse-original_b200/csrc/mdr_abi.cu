@@ -280,6 +280,9 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     k.pro_lanes = L;
   }
   k.house_warps = g.house_warps;
+  k.house_threads = g.house_warps * 32;
+  k.ns = cfg->n_houses + cfg->n_comm;
+  k.in_stride = g.hmax * 52;
   k.pro_warp = g.pro_warp;
   k.part_stride = g.part_stride;
   mdr::step_smem_layout(&k, cfg->precision, g.hmax, g.envs_per_cta, g.house_warps, g.rows_per_pass, cfg->n_features,

@@ -815,7 +815,7 @@ __device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
   }
 }
 
-template <int kC>
+template <int kC, int kAct>
 __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
   using R = float;
   using T2 = float2;
@@ -836,22 +836,27 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     prologue_pipe_main(p);
     return;
   }
-  const int N = p.N, C = kC > 0 ? kC : p.C, G = p.G;
-  const int half = C >> 1, ns = N + C;
-  const int T = p.hmax;  // house threads per CTA
-  const int house_threads = p.house_warps * 32;
+  // loop invariants are read from the parameter (constant) bank where they are used instead of
+  // being kept in registers across the tile loop
+#define N (p.N)
+#define G (p.G)
+#define T (p.hmax) /* house threads per CTA */
+#define house_threads (p.house_threads)
+#define ns (p.ns)
+  const int C = kC > 0 ? kC : p.C;
+  const int half = C >> 1;
   const int le = tid < G * N ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;
   const int li = tid - le * N;
   const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
 
   T4* s_msg_all = reinterpret_cast<T4*>(smem_raw + p.off_msg);        // two windows [G*(N+C)]
-  double* s_part_all = reinterpret_cast<double*>(smem_raw + p.off_pw);  // two [G][part_stride]
+  R* s_part_all = reinterpret_cast<R*>(smem_raw + p.off_pw);  // two [G][part_stride]
   double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
   EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
   R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
   // input stage s: [coef_a T x 16][coef_b T x 16][temps T x 8][coef_c T x 8][hvac T x 4]
   unsigned char* s_in = smem_raw + p.off_in;
-  const int in_stride = T * 52;
+#define in_stride (p.in_stride)
   auto in_ptr = [&](int s, int off, int elem) { return s_in + s * in_stride + T * off + tid * elem; };
   auto issue_tile = [&](int tile, int s) {
     const int env0 = tile * G;
@@ -874,7 +879,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     od = 0;
     if (tid < H) {
       const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
-      if (p.action_source == MDR_ACT_ARRAY) cmd = p.actions[h];
+      if (kAct == MDR_ACT_ARRAY) cmd = p.actions[h];
       od = p.od_temp[env0 + le];
     }
   };
@@ -900,7 +905,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const int e = env0 + le;
     const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
     T4* s_msg = s_msg_all + sbuf * (G * ns);
-    double* s_part = s_part_all + sbuf * (G * p.part_stride);
+    R* s_part = s_part_all + sbuf * (G * p.part_stride);
     int cmd = cmd_next;
     const R od_old = (R)od_next;
     const int next = tile + gridDim.x;
@@ -923,8 +928,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       const int hv = *reinterpret_cast<const int*>(in_ptr(sbuf, 48, 4));
       target = cb.w; p_on = cb.z; deadband = cc.x; lockdur_r = cc.y;
       on = hv & 1; lock = (hv >> 1) & 1; sso = hv >> 2;
-      if (p.action_source == MDR_ACT_ARRAY) cmd = cmd != 0;
-      else if (p.action_source == MDR_ACT_BANGBANG) cmd = tt.x > target;
+      if (kAct == MDR_ACT_ARRAY) cmd = cmd != 0;
+      else if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
       else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
@@ -956,7 +961,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     }
     {
       const int key = active ? le : -1;
-      const double part = (double)segmented_sum<R>(pw, key, lane);
+      // fp32 partial sums are exact here: integer-valued watts, at most 224 houses (< 2^24 W)
+      const R part = segmented_sum<R>(pw, key, lane);
       const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
       if (active && (lane == 0 || prev_key != key)) s_part[le * p.part_stride + (warp - ((le * N) >> 5))] = part;
     }
@@ -969,7 +975,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
     house_sync(house_threads);
 
-    double P = 0.0;
+    R P = 0;
     if (active) {
       const int first_warp = (le * N) >> 5, last_warp = (le * N + N - 1) >> 5;
       for (int w = 0; w <= last_warp - first_warp; ++w) P += s_part[le * p.part_stride + w];
@@ -987,7 +993,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       row[6] = (R)lock;
       row[7] = (R)sso * inv_lock;
       row[8] = 1.f;
-      row[10] = (R)(P * p.inv_norm_sig_agents);
+      row[10] = P * (R)p.inv_norm_sig_agents;
       const T4* win = s_msg + le * ns + li;
       R* mrow = row + 11;
 #pragma unroll
@@ -1006,7 +1012,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
 
     if (active && li == 0) {
       const EnvScratch& es = env_buf[le];
-      p.cluster_power[e] = P;
+      p.cluster_power[e] = (double)P;
       p.od_temp[e] = es.od_new;
       p.t_epoch[e] = (int64_t)es.t_new;
       if (!es.due) {
@@ -1051,8 +1057,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     }
     if (active && p.reward != nullptr) {
       const EnvScratch& es = env_buf[le];
-      const double dn = (P - es.s_old) * p.inv_n;
-      reinterpret_cast<R*>(p.reward)[h] = (R)(-((double)pen * p.k_temp + dn * dn * p.k_sig));
+      const R dn = (R)((double)P - es.s_old) * (R)p.inv_n;
+      reinterpret_cast<R*>(p.reward)[h] = -(pen * (R)p.k_temp + dn * dn * (R)p.k_sig);
     }
     if (p.obs != nullptr && nrows_w > 0) {
       if (lane < nrows_w) stage[lane * F + 9] = (R)env_buf[le].f_sig;
@@ -1075,6 +1081,12 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   }
   cp_async_wait<0>();
   if (lane == 0) bulk_wait_read_all();
+#undef N
+#undef G
+#undef T
+#undef house_threads
+#undef ns
+#undef in_stride
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1121,7 +1133,7 @@ static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cuda
   return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
 
-template <int kC>
+template <int kC, int kAct>
 static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, cudaStream_t stream) {
   static int ctas_per_sm[64] = {};
   static int sm_count[64] = {};
@@ -1131,14 +1143,14 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   cudaGetDevice(&dev);
   if (dev >= 64) return cudaErrorInvalidDevice;
   if (sm_count[dev] == 0) {
-    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
     if (err != cudaSuccess) return err;
     err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (err != cudaSuccess) return err;
   }
   if (cached_threads[dev] != g.threads || cached_smem[dev] != g.pipe_smem_bytes) {
     int n = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC>, g.threads, g.pipe_smem_bytes);
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC, kAct>, g.threads, g.pipe_smem_bytes);
     if (err != cudaSuccess) return err;
     if (n < 1) return cudaErrorLaunchOutOfResources;
     ctas_per_sm[dev] = n;
@@ -1149,12 +1161,19 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   kp.n_tiles = g.ctas;
   int grid = sm_count[dev] * ctas_per_sm[dev];
   if (grid > g.ctas) grid = g.ctas;
-  step_pipe_kernel<kC><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
+  step_pipe_kernel<kC, kAct><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
   return cudaGetLastError();
 }
 
+template <int kC>
+static cudaError_t launch_pipe_c(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY>(kp, g, stream);
+  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG>(kp, g, stream);
+  return launch_pipe_t<kC, MDR_ACT_RANDOM>(kp, g, stream);
+}
+
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  return kp.C == 10 ? launch_pipe_t<10>(kp, g, stream) : launch_pipe_t<0>(kp, g, stream);
+  return kp.C == 10 ? launch_pipe_c<10>(kp, g, stream) : launch_pipe_c<0>(kp, g, stream);
 }
 
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision) {

@@ -15,6 +15,7 @@ struct KernelParams {
   // shape / geometry
   int E, N, C, F, G, hmax, rows_per_pass, dt;
   int off_msg, off_pw, off_val, off_pen, off_env, off_stage, off_in, off_ctl;  // shared-memory carve-up (bytes)
+  int ns, house_threads, in_stride;                            // N + C, house_warps * 32, bytes of one cp.async input stage
   int n_tiles;                                                // pipelined kernel: number of G-env tiles
   int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
