@@ -128,8 +128,10 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   g->rows_per_pass = rpp;
   g->smem_bytes = smem;
   g->pipe_smem_bytes = 0;
+  g->pro_batch = 1;
   if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32) {
-    const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride);
+    g->pro_batch = mdr::pipe_pro_batch(G, has_obs);
+    const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride, g->pro_batch);
     if (ps <= (size_t)MDR_MAX_SMEM_BYTES) g->pipe_smem_bytes = ps;
   }
   return MDR_OK;
@@ -292,9 +294,16 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   if (err != cudaSuccess) return cuda_fail(err);
   const char* no_pipe = getenv("MDR_NO_PIPELINE");
   const bool pipe = !(no_pipe && no_pipe[0] == '1') && mdr::pipe_eligible(k, g, cfg->precision);
-  if (pipe)
-    mdr::pipe_smem_layout(&k, g.hmax, g.envs_per_cta, cfg->n_houses, cfg->n_features,
-                          cfg->base_power_mode == MDR_BASE_INTERPOLATION, out->obs != nullptr, cfg->n_comm, g.part_stride);
+  if (pipe) {
+    k.pro_batch = g.pro_batch;
+    int L = 16;  // lanes per env within one tile's lane group
+    while (L > 1 && L * g.envs_per_cta * g.pro_batch > 32) L >>= 1;
+    k.pro_lanes = L;
+    k.in_stride = k.hmax * 52;
+    mdr::pipe_smem_layout(&k, k.hmax, g.envs_per_cta, cfg->n_houses, cfg->n_features,
+                          cfg->base_power_mode == MDR_BASE_INTERPOLATION, out->obs != nullptr, cfg->n_comm, g.part_stride,
+                          g.pro_batch);
+  }
   for (int i = 0; i < n_steps; ++i) {
     err = pipe ? mdr::launch_pipe(k, g, stream) : mdr::launch_step_any(k, g, cfg->precision, stream);
     if (err != cudaSuccess) return cuda_fail(err);

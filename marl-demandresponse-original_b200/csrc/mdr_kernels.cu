@@ -779,43 +779,89 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
       : "memory");
 }
 
-// shared-memory control block of the pipelined kernel (at off_ctl)
+// shared-memory control block of the pipelined kernel (at off_ctl).  The EnvScratch ring has
+// kRing = 2 * kBatch slots; slot = it % kRing for the it-th tile of this CTA.
+template <int kRing>
 struct PipeCtl {
-  uint64_t full[2];   // prologue -> house warps: EnvScratch buffer b is ready   (count 1)
-  uint64_t empty[2];  // house warps -> prologue: buffer b may be overwritten     (count house_warps)
-  int tile_due[2];    // any env of the tile has an interpolation refresh due
-  int pad[2];
+  uint64_t full[kRing];   // prologue -> house warps: slot is ready            (count 1)
+  uint64_t empty[kRing];  // house warps -> prologue: slot may be overwritten   (count house_warps)
+  int tile_due[kRing];    // any env of the tile has an interpolation refresh due
 };
+inline size_t pipe_ctl_bytes(int ring) { return (size_t)ring * 20; }
 
+// The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
+// groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  When the house
+// work of a tile is short (no observation written) a deeper batch keeps the prologue's dependent
+// fp64 / Philox chains off the critical path by sheer lookahead.
+template <int kBatch>
 __device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
-  PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  constexpr int B = kBatch, ring = 2 * B;
+  PipeCtl<ring>& ctl = *reinterpret_cast<PipeCtl<ring>*>(smem_raw + p.off_ctl);
   const int lane = threadIdx.x & 31;
-  const int L = p.pro_lanes, groups = 32 / L;
-  const int sub = lane & (L - 1), grp = lane / L;
-  int it = 0;
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-    const int b = it & 1;
-    if (it >= 2) mbar_wait(&ctl->empty[b], ((it >> 1) & 1) ^ 1);  // house warps are done with tile it-2
-    const int env0 = tile * p.G;
+  if (kBatch == 1) {
+    // one tile per pass: the whole warp works on the tile's G envs, pro_lanes lanes per env
+    const int L = p.pro_lanes, groups = 32 / L;
+    const int sub = lane & (L - 1), grp = lane / L;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      if (it >= 2) mbar_wait(&ctl.empty[b], ((it >> 1) & 1) ^ 1);  // house warps are done with tile it-2
+      const int env0 = tile * p.G;
+      const int genvs = min(p.G, p.E - env0);
+      EnvScratch* buf = s_env + b * p.G;
+      int my_due = 0;
+      for (int first = 0; first < genvs; first += groups) {
+        const int le2 = first + grp;
+        const bool valid = le2 < genvs;
+        const int lec = valid ? le2 : genvs - 1;
+        my_due |= env_prologue(p, buf[lec], env0 + lec, sub, L, valid, false, false);
+      }
+      my_due = __any_sync(0xffffffffu, my_due);
+      if (lane == 0) ctl.tile_due[b] = my_due;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.full[b]);
+    }
+    return;
+  }
+  // kBatch tiles per pass: the 32 lanes are split into kBatch groups (one per tile), each group into
+  // lane sets of pro_lanes lanes per env.  When the house work of a tile is short (no observation
+  // written) the deeper lookahead keeps the prologue's dependent fp64 / Philox chains off the
+  // critical path.
+  constexpr int lanes_per_tile = 32 / B;
+  const int L = p.pro_lanes, groups = lanes_per_tile / L;  // env groups processed at once per tile
+  const int tlane = lane & (lanes_per_tile - 1);
+  const int sub = tlane & (L - 1), grp = tlane / L;
+  const int my_k = lane / lanes_per_tile;  // which tile of the pass this lane works for
+  const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
+  for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) {  // warp-uniform
+    const int it = it0 + my_k;
+    const int tile = blockIdx.x + it * gridDim.x;
+    const bool tile_valid = tile < p.n_tiles;
+    const int slot = it & (ring - 1);
+    const int use = it / ring;
+    if (tile_valid && use >= 1) mbar_wait(&ctl.empty[slot], (use & 1) ^ 1);  // house warps released the slot
+    __syncwarp();
+    const int tile_c = tile_valid ? tile : blockIdx.x;  // lanes of an absent tile compute but never write
+    const int env0 = tile_c * p.G;
     const int genvs = min(p.G, p.E - env0);
-    EnvScratch* buf = s_env + b * p.G;
+    EnvScratch* buf = s_env + slot * p.G;
     int my_due = 0;
-    for (int first = 0; first < genvs; first += groups) {
+    for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count (G, not genvs)
       const int le2 = first + grp;
-      const bool valid = le2 < genvs;
-      const int lec = valid ? le2 : genvs - 1;
+      const bool valid = tile_valid && le2 < genvs;
+      const int lec = le2 < genvs ? le2 : genvs - 1;
       my_due |= env_prologue(p, buf[lec], env0 + lec, sub, L, valid, false, false);
     }
-    my_due = __any_sync(0xffffffffu, my_due);
-    if (lane == 0) ctl->tile_due[b] = my_due;
+    const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
+    if (tile_valid && tlane == 0) ctl.tile_due[slot] = (due_ballot & group_mask) != 0;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ctl->full[b]);
+    if (tile_valid && tlane == 0) mbar_arrive(&ctl.full[slot]);
   }
 }
 
-template <int kC, int kAct>
+template <int kC, int kAct, int kBatch>
 __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
   using R = float;
   using T2 = float2;
@@ -823,17 +869,18 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  PipeCtl* ctl = reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  constexpr int kRing = 2 * kBatch;
+  PipeCtl<kRing>& ctl = *reinterpret_cast<PipeCtl<kRing>*>(smem_raw + p.off_ctl);
   if (tid == 0) {
-    mbar_init(&ctl->full[0], 1);
-    mbar_init(&ctl->full[1], 1);
-    mbar_init(&ctl->empty[0], p.house_warps);
-    mbar_init(&ctl->empty[1], p.house_warps);
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&ctl.full[i], 1);
+      mbar_init(&ctl.empty[i], p.house_warps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (warp >= p.house_warps) {
-    prologue_pipe_main(p);
+    prologue_pipe_main<kBatch>(p);
     return;
   }
   // loop invariants are read from the parameter (constant) bank where they are used instead of
@@ -1006,9 +1053,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       }
     }
     // hand-over from the prologue warp: it produced this tile's EnvScratch one tile ago
-    mbar_wait(&ctl->full[sbuf], (it >> 1) & 1);
-    EnvScratch* env_buf = s_env + sbuf * G;
-    const int any_due = interp_mode ? ctl->tile_due[sbuf] : 0;
+    const int slot = it & (kRing - 1);
+    mbar_wait(&ctl.full[slot], (it / kRing) & 1);
+    EnvScratch* env_buf = s_env + slot * G;
+    const int any_due = interp_mode ? ctl.tile_due[slot] : 0;
 
     if (active && li == 0) {
       const EnvScratch& es = env_buf[le];
@@ -1075,9 +1123,9 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         __syncwarp();
       }
     }
-    // this warp is done with EnvScratch buffer `sbuf`: let the prologue warp reuse it for tile it+2
+    // this warp is done with EnvScratch slot `slot`: let the prologue warp reuse it for tile it+ring
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ctl->empty[sbuf]);
+    if (lane == 0) mbar_arrive(&ctl.empty[slot]);
   }
   cp_async_wait<0>();
   if (lane == 0) bulk_wait_read_all();
@@ -1133,7 +1181,7 @@ static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cuda
   return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
 
-template <int kC, int kAct>
+template <int kC, int kAct, int kBatch>
 static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, cudaStream_t stream) {
   static int ctas_per_sm[64] = {};
   static int sm_count[64] = {};
@@ -1143,14 +1191,14 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   cudaGetDevice(&dev);
   if (dev >= 64) return cudaErrorInvalidDevice;
   if (sm_count[dev] == 0) {
-    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC, kAct>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC, kAct, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
     if (err != cudaSuccess) return err;
     err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (err != cudaSuccess) return err;
   }
   if (cached_threads[dev] != g.threads || cached_smem[dev] != g.pipe_smem_bytes) {
     int n = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC, kAct>, g.threads, g.pipe_smem_bytes);
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC, kAct, kBatch>, g.threads, g.pipe_smem_bytes);
     if (err != cudaSuccess) return err;
     if (n < 1) return cudaErrorLaunchOutOfResources;
     ctas_per_sm[dev] = n;
@@ -1161,20 +1209,29 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   kp.n_tiles = g.ctas;
   int grid = sm_count[dev] * ctas_per_sm[dev];
   if (grid > g.ctas) grid = g.ctas;
-  step_pipe_kernel<kC, kAct><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
+  step_pipe_kernel<kC, kAct, kBatch><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
   return cudaGetLastError();
 }
 
 template <int kC>
 static cudaError_t launch_pipe_c(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY>(kp, g, stream);
-  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG>(kp, g, stream);
-  return launch_pipe_t<kC, MDR_ACT_RANDOM>(kp, g, stream);
+  if (g.pro_batch == 1) {
+    if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, 1>(kp, g, stream);
+    if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, 1>(kp, g, stream);
+    return launch_pipe_t<kC, MDR_ACT_RANDOM, 1>(kp, g, stream);
+  }
+  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, 8>(kp, g, stream);
+  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, 8>(kp, g, stream);
+  return launch_pipe_t<kC, MDR_ACT_RANDOM, 8>(kp, g, stream);
 }
 
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
   return kp.C == 10 ? launch_pipe_c<10>(kp, g, stream) : launch_pipe_c<0>(kp, g, stream);
 }
+
+// tiles per prologue pass: 1 when the observation is written (house work per tile covers the prologue and
+// shared memory is tight), up to 8 otherwise, keeping at least one lane per env
+int pipe_pro_batch(int envs_per_cta, bool has_obs) { return (!has_obs && 8 * envs_per_cta <= 32) ? 8 : 1; }
 
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision) {
   return precision == MDR_F32 && kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 &&
@@ -1194,13 +1251,13 @@ cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int preci
 // layout of the pipelined kernel: message window, power partials and EnvScratch double buffered, one
 // contiguous staging tile for the tile's G*N observation rows, two cp.async input stages
 size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int n_features, bool need_val, bool has_obs,
-                        int n_comm, int part_stride) {
+                        int n_comm, int part_stride, int pro_batch) {
   size_t o = 0;
   const size_t off_msg = o;   o += align16((size_t)2 * genvs * (n_houses + n_comm) * 4 * sizeof(float));
   const size_t off_pw = o;    o += align16((size_t)2 * genvs * part_stride * sizeof(double));
   const size_t off_val = o;   o += need_val ? align16((size_t)hmax * sizeof(double)) : 0;
-  const size_t off_env = o;   o += align16((size_t)2 * genvs * sizeof(EnvScratch));
-  const size_t off_ctl = o;   o += align16(sizeof(PipeCtl));
+  const size_t off_env = o;   o += align16((size_t)2 * pro_batch * genvs * sizeof(EnvScratch));
+  const size_t off_ctl = o;   o += align16(pipe_ctl_bytes(2 * pro_batch));
   const size_t off_stage = o; o += has_obs ? align16((size_t)genvs * n_houses * n_features * sizeof(float)) : 0;
   const size_t off_in = o;    o += align16((size_t)2 * hmax * 52);
   if (kp) {

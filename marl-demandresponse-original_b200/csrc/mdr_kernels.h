@@ -16,6 +16,7 @@ struct KernelParams {
   int E, N, C, F, G, hmax, rows_per_pass, dt;
   int off_msg, off_pw, off_val, off_pen, off_env, off_stage, off_in, off_ctl;  // shared-memory carve-up (bytes)
   int ns, house_threads, in_stride;                            // N + C, house_warps * 32, bytes of one cp.async input stage
+  int pro_batch;                                              // pipelined kernel: tiles the prologue warp produces per pass
   int n_tiles;                                                // pipelined kernel: number of G-env tiles
   int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
@@ -58,14 +59,15 @@ struct KernelParams {
 };
 
 struct Geometry {
-  int envs_per_cta, threads, ctas, rows_per_pass, hmax, house_warps, pro_warp, part_stride;
+  int envs_per_cta, threads, ctas, rows_per_pass, hmax, house_warps, pro_warp, part_stride, pro_batch;
   size_t smem_bytes, pipe_smem_bytes;
 };
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
                         int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride);
 size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int n_features, bool need_val, bool has_obs,
-                        int n_comm, int part_stride);
+                        int n_comm, int part_stride, int pro_batch);
+int pipe_pro_batch(int envs_per_cta, bool has_obs);
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision);
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream);
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);
