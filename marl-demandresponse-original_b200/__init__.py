@@ -23,7 +23,10 @@ def __getattr__(name):
     if name == "MADemandResponseEnv":
         from .env import MADemandResponseEnv
         return MADemandResponseEnv
-    if name in ("ShardedRollout", "shard_range", "reduce_metrics"):
+    if name in ("regenerate_table", "regenerate_entries"):
+        from . import montecarlo
+        return getattr(montecarlo, name)
+    if name in ("RolloutMetrics", "shard_range", "reduce_metrics"):
         from . import sharding
         return getattr(sharding, name)
     raise AttributeError(name)

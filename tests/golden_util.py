@@ -29,7 +29,9 @@ def synthetic_table():
 
 
 def names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """trace fixtures (oracle/make_golden.py); mc_* files are table samples (oracle/make_mc_golden.py)"""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith("mc_"))
 
 
 def fix_config(cfg):
