@@ -23,6 +23,9 @@ def __getattr__(name):
     if name == "MADemandResponseEnv":
         from .env import MADemandResponseEnv
         return MADemandResponseEnv
+    if name == "DeviceRolloutCollector":
+        from .rollout import DeviceRolloutCollector
+        return DeviceRolloutCollector
     if name in ("regenerate_table", "regenerate_entries"):
         from . import montecarlo
         return getattr(montecarlo, name)

@@ -228,17 +228,36 @@ class VecDemandResponseEnv:
         return self.obs
 
     def step_tensor(self, actions=None, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None,
-                    comm=None, n_steps=1):
+                    comm=None, n_steps=1, obs_out=None, reward_out=None):
         """One env step for every cluster.  `actions` [E, N] (nonzero = ON) unless the env was
         built with an on-device action source.  Replay arguments feed host-drawn randomness
         (parity mode); when omitted the kernel draws from Philox / evaluates its own perlin."""
         if not self._precomputed:
             self.precompute()
         self._set_inputs(actions, od_noise, signal_noise, interp_ids, msg_keep, comm)
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.mdr_step(*self._refs, int(n_steps), self._stream()), "mdr_step")
+        obs, reward = self.obs, self.reward
+        if obs_out is not None or reward_out is not None:
+            # zero-copy: the kernel writes straight into the caller's rollout storage
+            obs = self._check_out(obs_out, (self.n_envs, self.n_houses, self.n_features)) if obs_out is not None else obs
+            reward = self._check_out(reward_out, (self.n_envs, self.n_houses)) if reward_out is not None else reward
+            self.out_s.obs = C.c_void_p(obs.data_ptr()) if obs is not None else None
+            self.out_s.reward = C.c_void_p(reward.data_ptr())
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mdr_step(*self._refs, int(n_steps), self._stream()), "mdr_step")
+        finally:
+            if obs_out is not None or reward_out is not None:
+                self.out_s.obs = C.c_void_p(self.obs.data_ptr()) if self.obs is not None else None
+                self.out_s.reward = C.c_void_p(self.reward.data_ptr())
         self.step_index += int(n_steps)
-        return self.obs, self.reward, self.env["cluster_power"], self.env["signal"]
+        return obs, reward, self.env["cluster_power"], self.env["signal"]
+
+    def _check_out(self, t, shape):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device and t.dtype == self.dtype
+                and t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.data_ptr() % 16 == 0):
+            raise ValueError("output tensor must be a contiguous, 16-byte aligned %s CUDA tensor of shape %s on %s"
+                             % (self.dtype, tuple(shape), self.device))
+        return t
 
     def run(self, n_steps):
         """`n_steps` steps with the on-device action source (one launch per step, issued from C)."""
