@@ -179,6 +179,9 @@ static void fill_config(KernelParams& k, const MdrConfig* c) {
   k.two_pi_over_24 = 2 * 3.141592653589793 / 24;
   k.k_temp = c->alpha_temp / c->norm_temp_penalty;
   k.k_sig = c->alpha_sig / c->norm_sig_penalty;
+  k.f_inv_norm_reg_sig = (float)k.inv_norm_reg_sig; k.f_inv_norm_sig_agents = (float)k.inv_norm_sig_agents;
+  k.f_cop_over_def_cap = (float)k.cop_over_def_cap; k.f_inv_n = (float)k.inv_n;
+  k.f_k_temp = (float)k.k_temp; k.f_k_sig = (float)k.k_sig;
   k.def_ua = c->def_ua; k.def_cm = c->def_cm; k.def_ca = c->def_ca; k.def_hm = c->def_hm;
   k.def_cop = c->def_cop; k.def_latent = c->def_latent; k.def_cap = c->def_cap;
   k.hvac_cop = c->hvac_cop; k.hvac_latent = c->hvac_latent;

@@ -17,6 +17,7 @@
 #include "mdr_kernels.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include "mdr_device.cuh"
 
@@ -33,6 +34,21 @@ struct EnvScratch {
   uint32_t t_new;
   int due, tsi, time_sec;
 };
+
+// Compact hand-over record of the pipelined kernel (prologue warp -> house warps), one per env
+// and ring slot.  64 bytes; the pipelined kernel never runs with solar gain or calendar features,
+// so the interpolation point's hour/date are 0 and need no slot here.
+struct PipeEnv {
+  double s_old;      // grid signal before this step (reward)
+  double od_new;     // outdoor temperature after this step (interpolation point)
+  double sig_noise;  // perlin value of this step (signal re-evaluated after a refresh)
+  float od_old;      // outdoor temperature the thermal update uses
+  float f_sig;       // normalised new signal = observation feature 9 (rewritten by a refresh)
+  int due;           // interpolation refresh due for this env
+  int time_sec;
+  double pad[3];
+};
+static_assert(sizeof(PipeEnv) == 64, "PipeEnv must stay 64 bytes");
 
 inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -208,8 +224,9 @@ __global__ void precompute_kernel(const __grid_constant__ KernelParams p) {
 // warps' global loads and thermal update, so its latency (fp64 sin, Philox) is off the
 // critical path.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& es, int e2, int sub, int L, bool valid,
-                                            bool reset, bool observe_only) {
+template <bool kPipe>
+__device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& es, PipeEnv& pe, int e2, int sub, int L,
+                                            bool valid, bool reset, bool observe_only) {
   // `L` lanes (a power of two) cooperate on one env: the Philox draws of the production mode are
   // spread over them; everything else is computed redundantly and written by sub-lane 0.
   // all per-env loads up front (independent, so their latencies overlap)
@@ -287,6 +304,34 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
   }
   double sig = s_old;
   if (!observe_only && !due) sig = grid_signal(p, base, time_sec, sig_noise, ratio, max_power);
+  if (kPipe) {
+    // pipelined kernel: the prologue warp owns the per-env outputs that do not depend on the houses
+    // (each env belongs to exactly one tile per launch, and the house threads take the old values
+    // from the record, so running ahead of them is safe)
+    if (sub == 0 && valid) {
+      pe.s_old = s_old;
+      pe.od_new = od_new;
+      pe.sig_noise = sig_noise;
+      pe.od_old = (float)od_prev;
+      pe.f_sig = (float)(sig * p.inv_norm_sig_agents);
+      pe.due = due;
+      pe.time_sec = time_sec;
+      p.t_epoch[e2] = (int64_t)t;
+      p.od_temp[e2] = od_new;
+      if (!due) {
+        p.base_power[e2] = base;
+        p.signal[e2] = sig;
+        if (interp_mode) p.time_since_interp[e2] = tsi;
+      } else {
+        // deferred refresh (pipe_refresh_pass, after the tile loop of the same launch): the env is
+        // marked with time_since_interp = -1 and its perlin value parked in base_power, both of
+        // which the refresh overwrites
+        p.time_since_interp[e2] = -1;
+        p.base_power[e2] = sig_noise;
+      }
+    }
+    return valid ? due : 0;
+  }
   if (sub == 0 && valid) {
     es.t_new = t;
     es.od_new = od_new;
@@ -344,7 +389,8 @@ __device__ __noinline__ int prologue_warp_main(const KernelParams& p, bool reset
     const int le2 = first + grp;
     const bool valid = le2 < genvs;
     const int lec = valid ? le2 : genvs - 1;
-    my_due |= env_prologue(p, s_env[lec], env0 + lec, sub, L, valid, reset, observe_only);
+    PipeEnv unused;
+    my_due |= env_prologue<false>(p, s_env[lec], unused, env0 + lec, sub, L, valid, reset, observe_only);
   }
   if (!dedicated) return my_due;
   // barrier sequence of the house warps (see step_kernel)
@@ -740,9 +786,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
 //   * the house threads' inputs of tile i+1 are fetched with cp.async into a second shared-memory
 //     stage while tile i is computed (each thread copies and later reads only its own record, so
 //     cp.async.wait_group is the only synchronisation the inputs need);
-//   * the dedicated prologue warp runs one tile ahead, writing a double-buffered EnvScratch;
+//   * the dedicated prologue warp runs `pro_batch` tiles per pass and up to 2*pro_batch tiles ahead,
+//     handing a 64-byte PipeEnv record per env over through an mbarrier ring, and writes the
+//     per-env outputs (clock, outdoor temperature, signal) itself;
 //   * the bulk (TMA) observation store of tile i drains while tile i+1 is loaded and updated.
-// Barrier 1 = house warps only (power partial sums), barrier 0 = all warps (prologue hand-over).
+// Barrier 1 = house warps only (message window + power partial sums); everything that is constant
+// over the tile loop (shared-memory addresses, neighbour window, partial-sum slots) is computed
+// once per thread before the loop.
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async_16(void* s, const void* g) {
@@ -758,7 +808,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-// mbarrier hand-over between the prologue warp (producer of EnvScratch) and the house warps
+// mbarrier hand-over between the prologue warp (producer of PipeEnv records) and the house warps
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -779,62 +829,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
       : "memory");
 }
 
-// shared-memory control block of the pipelined kernel (at off_ctl).  The EnvScratch ring has
-// kRing = 2 * kBatch slots; slot = it % kRing for the it-th tile of this CTA.
-template <int kRing>
+// shared-memory control block of the pipelined kernel (at off_ctl).  The PipeEnv ring has
+// ring = 2 * pro_batch <= kMaxRing slots; slot = it % ring for the it-th tile of this CTA.
+constexpr int kMaxRing = 16;
 struct PipeCtl {
-  uint64_t full[kRing];   // prologue -> house warps: slot is ready            (count 1)
-  uint64_t empty[kRing];  // house warps -> prologue: slot may be overwritten   (count house_warps)
-  int tile_due[kRing];    // any env of the tile has an interpolation refresh due
+  uint64_t full[kMaxRing];   // prologue -> house warps: slot is ready            (count 1)
+  uint64_t empty[kMaxRing];  // house warps -> prologue: slot may be overwritten   (count house_warps)
+  int tile_due[kMaxRing];    // any env of the tile has an interpolation refresh due
 };
-inline size_t pipe_ctl_bytes(int ring) { return (size_t)ring * 20; }
 
 // The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
-// groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  When the house
-// work of a tile is short (no observation written) a deeper batch keeps the prologue's dependent
-// fp64 / Philox chains off the critical path by sheer lookahead.
-template <int kBatch>
+// groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  The deeper the
+// batch, the further the prologue's dependent fp64 / Philox / global-load chains are from the
+// house warps' critical path.
 __device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
-  constexpr int B = kBatch, ring = 2 * B;
-  PipeCtl<ring>& ctl = *reinterpret_cast<PipeCtl<ring>*>(smem_raw + p.off_ctl);
+  PipeEnv* s_env = reinterpret_cast<PipeEnv*>(smem_raw + p.off_env);
+  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  const int B = p.pro_batch, ring = 2 * B;
   const int lane = threadIdx.x & 31;
-  if (kBatch == 1) {
-    // one tile per pass: the whole warp works on the tile's G envs, pro_lanes lanes per env
-    const int L = p.pro_lanes, groups = 32 / L;
-    const int sub = lane & (L - 1), grp = lane / L;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-      const int b = it & 1;
-      if (it >= 2) mbar_wait(&ctl.empty[b], ((it >> 1) & 1) ^ 1);  // house warps are done with tile it-2
-      const int env0 = tile * p.G;
-      const int genvs = min(p.G, p.E - env0);
-      EnvScratch* buf = s_env + b * p.G;
-      int my_due = 0;
-      for (int first = 0; first < genvs; first += groups) {
-        const int le2 = first + grp;
-        const bool valid = le2 < genvs;
-        const int lec = valid ? le2 : genvs - 1;
-        my_due |= env_prologue(p, buf[lec], env0 + lec, sub, L, valid, false, false);
-      }
-      my_due = __any_sync(0xffffffffu, my_due);
-      if (lane == 0) ctl.tile_due[b] = my_due;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl.full[b]);
-    }
-    return;
-  }
-  // kBatch tiles per pass: the 32 lanes are split into kBatch groups (one per tile), each group into
-  // lane sets of pro_lanes lanes per env.  When the house work of a tile is short (no observation
-  // written) the deeper lookahead keeps the prologue's dependent fp64 / Philox chains off the
-  // critical path.
-  constexpr int lanes_per_tile = 32 / B;
+  const int lanes_per_tile = 32 / B;
   const int L = p.pro_lanes, groups = lanes_per_tile / L;  // env groups processed at once per tile
   const int tlane = lane & (lanes_per_tile - 1);
   const int sub = tlane & (L - 1), grp = tlane / L;
   const int my_k = lane / lanes_per_tile;  // which tile of the pass this lane works for
   const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
+  EnvScratch unused;
   for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) {  // warp-uniform
     const int it = it0 + my_k;
     const int tile = blockIdx.x + it * gridDim.x;
@@ -846,13 +866,13 @@ __device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
     const int tile_c = tile_valid ? tile : blockIdx.x;  // lanes of an absent tile compute but never write
     const int env0 = tile_c * p.G;
     const int genvs = min(p.G, p.E - env0);
-    EnvScratch* buf = s_env + slot * p.G;
+    PipeEnv* buf = s_env + slot * p.G;
     int my_due = 0;
     for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count (G, not genvs)
       const int le2 = first + grp;
       const bool valid = tile_valid && le2 < genvs;
       const int lec = le2 < genvs ? le2 : genvs - 1;
-      my_due |= env_prologue(p, buf[lec], env0 + lec, sub, L, valid, false, false);
+      my_due |= env_prologue<true>(p, unused, buf[lec], env0 + lec, sub, L, valid, false, false);
     }
     const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
     if (tile_valid && tlane == 0) ctl.tile_due[slot] = (due_ballot & group_mask) != 0;
@@ -861,18 +881,83 @@ __device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
   }
 }
 
-template <int kC, int kAct, int kBatch>
+// Deferred interpolation refresh (every interp_update_period seconds; PowerGrid.step :1250-1255,
+// interpolatePower :1195-1234).  It runs on 1 step in 75, needs fp64 and a 32-corner table walk per
+// house, and would cost the tile loop registers if it sat inside it.  So the tile loop treats a due
+// env like any other (the prologue parks its perlin value and marks it), and this pass -- after the
+// loop, same launch, same CTA, same tile order -- evaluates the table on the houses' NEW state,
+// re-evaluates the signal and patches observation feature 9 (the only output that depends on it).
+__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
+  float* s_fsig = reinterpret_cast<float*>(smem_raw + p.off_pw);  // [G], the power partials are dead by now
+  const int tid = threadIdx.x;
+  const int N = p.N, G = p.G, GN = G * N;
+  const int nb = p.interp_nb_agents;
+  const int nsamp = N <= nb ? N : nb;
+  const int T = p.hmax;
+  // the bulk stores of this warp's rows must have landed before feature 9 is patched
+  if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int H = min(GN, (p.E - tile * G) * N);
+    const bool active = tid < H;
+    const int e = tile * G + le;
+    const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+    const bool due = active && p.time_since_interp[e] < 0;
+    int any;
+    asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.or.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
+                 : "=r"(any)
+                 : "r"((int)due), "r"(T)
+                 : "memory");
+    if (!any) continue;
+    double od_new = 0.0;
+    if (due) od_new = p.od_temp[e];
+    if (due && li < nsamp) {
+      int src = li;
+      if (N > nb) {
+        if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
+        else {
+          const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                                     STREAM_IDS + 16 * (uint32_t)li, p.seed);
+          src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
+        }
+      }
+      const size_t hs = (size_t)e * N + src;
+      const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
+      const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
+      s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, 0.0, 0.0);
+    }
+    house_sync(T);
+    if (due && li == 0) {
+      double base = 0.0;
+      for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);  // id order, :1218-1232
+      if (N > nb) base = mul_rn(base, (double)N / (double)nb);
+      const Calendar cal = calendar_time((uint32_t)p.t_epoch[e]);
+      const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
+      const double sig_noise = p.base_power[e];  // parked by the prologue
+      const double sig = grid_signal(p, base, time_sec, sig_noise, p.artificial_ratio[e], p.max_power[e]);
+      p.base_power[e] = base;
+      p.time_since_interp[e] = 0;
+      p.signal[e] = sig;
+      s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
+    }
+    house_sync(T);
+    if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
+    house_sync(T);  // s_val / s_fsig are reused by the next due tile
+  }
+}
+
+template <int kC, int kAct, bool kObs>
 __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
-  using R = float;
-  using T2 = float2;
-  using T4 = float4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  constexpr int kRing = 2 * kBatch;
-  PipeCtl<kRing>& ctl = *reinterpret_cast<PipeCtl<kRing>*>(smem_raw + p.off_ctl);
+  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  const int ring_mask = 2 * p.pro_batch - 1;
+  const int ring_shift = 31 - __clz(ring_mask + 1);
   if (tid == 0) {
-    for (int i = 0; i < kRing; ++i) {
+    for (int i = 0; i <= ring_mask; ++i) {
       mbar_init(&ctl.full[i], 1);
       mbar_init(&ctl.empty[i], p.house_warps);
     }
@@ -880,107 +965,110 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   }
   __syncthreads();
   if (warp >= p.house_warps) {
-    prologue_pipe_main<kBatch>(p);
+    prologue_pipe_main(p);
     return;
   }
-  // loop invariants are read from the parameter (constant) bank where they are used instead of
-  // being kept in registers across the tile loop
-#define N (p.N)
-#define G (p.G)
-#define T (p.hmax) /* house threads per CTA */
-#define house_threads (p.house_threads)
-#define ns (p.ns)
+
+  // ---------------- per-thread constants of the tile loop ------------------------------------
+  const int N = p.N, G = p.G;
   const int C = kC > 0 ? kC : p.C;
   const int half = C >> 1;
-  const int le = tid < G * N ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;
+  const int ns = N + C;
+  const int GN = G * N;                 // houses of a full tile
+  const int T = p.hmax;                 // house threads of the CTA (multiple of 32)
+  const int le = tid < GN ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
   const int li = tid - le * N;
+  // own slot in message window 0 ([half halo | N houses | halo] per env); window 1 follows
+  float4* const msg0 = reinterpret_cast<float4*>(smem_raw + p.off_msg) + (le * ns + half + li);
+  const int msg_buf = G * ns;
+  const bool halo_hi = li < C - half;   // my message is also the wrap-around halo after the last house
+  const bool halo_lo = li >= N - half;  // ... and before the first one
+  // warp-partial power sums: [2][G][part_stride]
+  float* const part0 = reinterpret_cast<float*>(smem_raw + p.off_pw) + le * p.part_stride;
+  const int part_buf = G * p.part_stride;
+  const int first_warp = (le * N) >> 5;
+  const int my_part = warp - first_warp;
+  const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
+  float* const row = reinterpret_cast<float*>(smem_raw + p.off_stage) + tid * p.F;  // rows contiguous like in HBM
+  PipeEnv* const s_env = reinterpret_cast<PipeEnv*>(smem_raw + p.off_env);
+  // cp.async input stage s (in_stride bytes each): [coef_a T x 16][coef_b T x 16][temps T x 8][coef_c T x 8][hvac T x 4]
+  unsigned char* const in_a = smem_raw + p.off_in + tid * 16;
+  unsigned char* const in_t = smem_raw + p.off_in + T * 32 + tid * 8;
+  unsigned char* const in_h = smem_raw + p.off_in + T * 48 + tid * 4;
+  const int in_stride = p.in_stride;
   const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
+  const int n_tiles = p.n_tiles;
+  const int tile_stride = gridDim.x;
+  const float inv_norm = p.f_inv_norm_reg_sig;
 
-  T4* s_msg_all = reinterpret_cast<T4*>(smem_raw + p.off_msg);        // two windows [G*(N+C)]
-  R* s_part_all = reinterpret_cast<R*>(smem_raw + p.off_pw);  // two [G][part_stride]
-  double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
-  EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
-  R* s_stage = reinterpret_cast<R*>(smem_raw + p.off_stage);
-  // input stage s: [coef_a T x 16][coef_b T x 16][temps T x 8][coef_c T x 8][hvac T x 4]
-  unsigned char* s_in = smem_raw + p.off_in;
-#define in_stride (p.in_stride)
-  auto in_ptr = [&](int s, int off, int elem) { return s_in + s * in_stride + T * off + tid * elem; };
+  auto tile_houses = [&](int tile) { return min(GN, (p.E - tile * G) * N); };
   auto issue_tile = [&](int tile, int s) {
-    const int env0 = tile * G;
-    const int H = min(G, p.E - env0) * N;
-    if (tid < H) {
-      const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
-      cp_async_16(in_ptr(s, 0, 16), reinterpret_cast<const T4*>(p.coef_a) + h);
-      cp_async_16(in_ptr(s, 16, 16), reinterpret_cast<const T4*>(p.coef_b) + h);
-      cp_async_8(in_ptr(s, 32, 8), reinterpret_cast<const T2*>(p.temps) + h);
-      cp_async_8(in_ptr(s, 40, 8), reinterpret_cast<const T2*>(p.coef_c) + h);
-      cp_async_4(in_ptr(s, 48, 4), p.hvac + h);
+    if (tid < tile_houses(tile)) {
+      const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+      const int so = s * in_stride;
+      cp_async_16(in_a + so, reinterpret_cast<const float4*>(p.coef_a) + h);
+      cp_async_16(in_a + so + T * 16, reinterpret_cast<const float4*>(p.coef_b) + h);
+      cp_async_8(in_t + so, reinterpret_cast<const float2*>(p.temps) + h);
+      cp_async_8(in_t + so + T * 8, reinterpret_cast<const float2*>(p.coef_c) + h);
+      cp_async_4(in_h + so, p.hvac + h);
     }
   };
-  // action byte and outdoor temperature of the next tile travel in registers
-  // (kept as loaded -- converting here would stall on the load instead of letting it fly)
-  auto fetch_scalars = [&](int tile, int& cmd, double& od) {
-    const int env0 = tile * G;
-    const int H = min(G, p.E - env0) * N;
-    cmd = 0;
-    od = 0;
-    if (tid < H) {
-      const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
-      if (kAct == MDR_ACT_ARRAY) cmd = p.actions[h];
-      od = p.od_temp[env0 + le];
-    }
+  // the action byte of the next tile travels in a register (kept as loaded: converting here would
+  // stall on the load instead of letting it fly)
+  auto fetch_action = [&](int tile) -> int {
+    if (kAct == MDR_ACT_ARRAY && tid < tile_houses(tile)) return p.actions[(unsigned)tile * (unsigned)GN + (unsigned)tid];
+    return 0;
   };
 
   int tile = blockIdx.x;
   int cmd_next = 0;
-  double od_next = 0;
-  if (tile < p.n_tiles) {
+  int any_due = 0;
+  if (tile < n_tiles) {
     issue_tile(tile, 0);
-    fetch_scalars(tile, cmd_next, od_next);
+    cmd_next = fetch_action(tile);
   }
   cp_async_commit();
-  const int F = p.F;
-  const int wrow0 = warp * 32;
-  R* stage = s_stage + wrow0 * F;  // the tile's rows are contiguous in shared memory, like in HBM
 
-  for (int it = 0; tile < p.n_tiles; ++it, tile += gridDim.x) {
+  for (int it = 0; tile < n_tiles; ++it, tile += tile_stride) {
     const int sbuf = it & 1;
-    const int env0 = tile * G;
-    const int genvs = min(G, p.E - env0);
-    const int H = genvs * N;
+    const int H = tile_houses(tile);
     const bool active = tid < H;
-    const int e = env0 + le;
-    const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
-    T4* s_msg = s_msg_all + sbuf * (G * ns);
-    R* s_part = s_part_all + sbuf * (G * p.part_stride);
+    const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+    const int e = tile * G + le;
     int cmd = cmd_next;
-    const R od_old = (R)od_next;
-    const int next = tile + gridDim.x;
-    if (next < p.n_tiles) {
+    const int next = tile + tile_stride;
+    if (next < n_tiles) {
       issue_tile(next, sbuf ^ 1);
-      fetch_scalars(next, cmd_next, od_next);
+      cmd_next = fetch_action(next);
     }
     cp_async_commit();
+    // hand-over from the prologue warp: it produced this tile's records at least one tile ago
+    const int slot = it & ring_mask;
+    mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);
+    PipeEnv* const env_buf = s_env + slot * G;
     cp_async_wait<1>();  // this thread's copies of the current tile have landed
 
     // ---------------- phase A: per house ---------------------------------------------------
-    T2 tt = make2(0.f, 0.f);
-    R target = 0, p_on = 0, deadband = 0, lockdur_r = 1, pen = 0, pw = 0;
+    float t_air = 0, t_mass = 0, target = 0, p_on = 0, deadband = 0, inv_lock = 1, pen = 0, pw = 0;
     int on = 0, lock = 0, sso = 0;
+    float4* const msg = msg0 + sbuf * msg_buf;
     if (active) {
-      const T4 ca4 = *reinterpret_cast<const T4*>(in_ptr(sbuf, 0, 16));
-      const T4 cb = *reinterpret_cast<const T4*>(in_ptr(sbuf, 16, 16));
-      tt = *reinterpret_cast<const T2*>(in_ptr(sbuf, 32, 8));
-      const T2 cc = *reinterpret_cast<const T2*>(in_ptr(sbuf, 40, 8));
-      const int hv = *reinterpret_cast<const int*>(in_ptr(sbuf, 48, 4));
-      target = cb.w; p_on = cb.z; deadband = cc.x; lockdur_r = cc.y;
-      on = hv & 1; lock = (hv >> 1) & 1; sso = hv >> 2;
+      const int so = sbuf * in_stride;
+      const float4 ca4 = *reinterpret_cast<const float4*>(in_a + so);
+      const float4 cb = *reinterpret_cast<const float4*>(in_a + so + T * 16);
+      const float2 tt = *reinterpret_cast<const float2*>(in_t + so);
+      const float2 cc = *reinterpret_cast<const float2*>(in_t + so + T * 8);
+      const int hv = *reinterpret_cast<const int*>(in_h + so);
+      const float od_old = env_buf[le].od_old;
+      target = cb.w; p_on = cb.z; deadband = cc.x;
+      inv_lock = __fdividef(1.0f, cc.y);
+      on = hv & 1; sso = hv >> 2;
       if (kAct == MDR_ACT_ARRAY) cmd = cmd != 0;
       else if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
       else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
-      const int lockdur = (int)lockdur_r;
+      const int lockdur = (int)cc.y;
       if (!on) sso += dt;
       lock = !(on || sso >= lockdur);
       const int new_on = lock ? 0 : cmd;
@@ -988,153 +1076,106 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       if (!lock && !new_on && sso + dt < lockdur) lock = 1;
       on = new_on;
       // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature
-      const R qa = on ? cb.y : (R)0;
-      const R tss = od_old + qa * cb.x;
-      const R x = tt.x - tss, y = tt.y - tss;
-      tt.x = tt.x + (ca4.x * x + ca4.y * y);
-      tt.y = tt.y + (ca4.z * x + ca4.w * y);
-      reinterpret_cast<T2*>(p.temps)[h] = tt;
+      const float qa = on ? cb.y : 0.0f;
+      const float tss = od_old + qa * cb.x;
+      const float x = tt.x - tss, y = tt.y - tss;
+      t_air = tt.x + (ca4.x * x + ca4.y * y);
+      t_mass = tt.y + (ca4.z * x + ca4.w * y);
+      reinterpret_cast<float2*>(p.temps)[h] = make_float2(t_air, t_mass);
       p.hvac[h] = (sso << 2) | (lock << 1) | on;
-      pw = on ? p_on : (R)0;
-      const R inv_norm = (R)p.inv_norm_reg_sig;
-      const T4 m = make4((tt.x - target) * 0.2f, (R)sso, pw * inv_norm, p_on * inv_norm);
-      T4* win = s_msg + le * ns;
-      win[half + li] = m;
-      if (li < C - half) win[half + N + li] = m;
-      if (li >= N - half) win[li - (N - half)] = m;
-      const R hi = target + deadband / 2, lo = target - deadband / 2;
-      if (hi < tt.x) pen = (tt.x - hi) * (tt.x - hi);
-      else if (lo > tt.x) pen = (lo - tt.x) * (lo - tt.x);
+      pw = on ? p_on : 0.0f;
+      // SingleHouse.message :624-662 normalised as utils.py:842-868 (sso is scaled by the receiver)
+      const float4 m = make_float4((t_air - target) * 0.2f, (float)sso, pw * inv_norm, p_on * inv_norm);
+      msg[0] = m;
+      if (halo_hi) msg[N] = m;
+      if (halo_lo) msg[-N] = m;
+      // utils.deadbandL2, utils.py:1266-1274
+      const float hi = target + deadband * 0.5f, lo = target - deadband * 0.5f;
+      if (hi < t_air) pen = (t_air - hi) * (t_air - hi);
+      else if (lo > t_air) pen = (lo - t_air) * (lo - t_air);
     }
+    float* const part = part0 + sbuf * part_buf;
     {
       const int key = active ? le : -1;
       // fp32 partial sums are exact here: integer-valued watts, at most 224 houses (< 2^24 W)
-      const R part = segmented_sum<R>(pw, key, lane);
+      const float psum = segmented_sum<float>(pw, key, lane);
       const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-      if (active && (lane == 0 || prev_key != key)) s_part[le * p.part_stride + (warp - ((le * N) >> 5))] = part;
+      if (active && (lane == 0 || prev_key != key)) part[my_part] = psum;
     }
-    // the staging tile of this warp may still be read by the previous tile's bulk store
-    if (it > 0 && p.obs != nullptr) {
+    // the staging rows of this warp may still be read by the previous tile's bulk store
+    if (kObs && it > 0) {
       if (lane == 0) bulk_wait_read_all();
       __syncwarp();
     }
     // the only CTA-wide rendezvous of a tile: message window + power partials are complete.
     // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
-    house_sync(house_threads);
+    house_sync(T);
 
-    R P = 0;
+    float P = 0;
     if (active) {
-      const int first_warp = (le * N) >> 5, last_warp = (le * N + N - 1) >> 5;
-      for (int w = 0; w <= last_warp - first_warp; ++w) P += s_part[le * p.part_stride + w];
+      // an env of <= 224 houses spans at most 8 warps; same summation order as a counted loop
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if (w < nparts) P += part[w];
+      if (li == 0) p.cluster_power[e] = (double)P;
     }
-    const int nrows_w = max(0, min(32, H - wrow0));
-    const R inv_lock = (R)1 / lockdur_r;
-    if (p.obs != nullptr && lane < nrows_w) {
-      R* row = stage + lane * F;
-      row[0] = (tt.x - 20) * 0.2f;
-      row[1] = (tt.y - 20) * 0.2f;
-      row[2] = (target - 20) * 0.2f;
+    if (kObs && active) {
+      // fast-path row: [T_air, T_mass, target, deadband, cap, on, lockout, sso, 1, signal, power | C x 4 messages]
+      row[0] = (t_air - 20.0f) * 0.2f;
+      row[1] = (t_mass - 20.0f) * 0.2f;
+      row[2] = (target - 20.0f) * 0.2f;
       row[3] = deadband;
-      row[4] = p_on * (R)p.cop_over_def_cap;
-      row[5] = (R)on;
-      row[6] = (R)lock;
-      row[7] = (R)sso * inv_lock;
-      row[8] = 1.f;
-      row[10] = P * (R)p.inv_norm_sig_agents;
-      const T4* win = s_msg + le * ns + li;
-      R* mrow = row + 11;
+      row[4] = p_on * p.f_cop_over_def_cap;
+      row[5] = (float)on;
+      row[6] = (float)lock;
+      row[7] = (float)sso * inv_lock;
+      row[8] = 1.0f;
+      row[10] = P * p.f_inv_norm_sig_agents;
+      // neighbours (:816-828) = the C window entries around this house, skipping itself
+      const float4* win = msg - half;
+      float* mrow = row + 11;
 #pragma unroll
       for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
-        const T4 m = win[k + (k >= half ? 1 : 0)];
+        const float4 m = win[k + (k >= half ? 1 : 0)];
         mrow[4 * k + 0] = m.x;
         mrow[4 * k + 1] = m.y * inv_lock;
         mrow[4 * k + 2] = m.z;
         mrow[4 * k + 3] = m.w;
       }
     }
-    // hand-over from the prologue warp: it produced this tile's EnvScratch one tile ago
-    const int slot = it & (kRing - 1);
-    mbar_wait(&ctl.full[slot], (it / kRing) & 1);
-    EnvScratch* env_buf = s_env + slot * G;
-    const int any_due = interp_mode ? ctl.tile_due[slot] : 0;
-
-    if (active && li == 0) {
-      const EnvScratch& es = env_buf[le];
-      p.cluster_power[e] = (double)P;
-      p.od_temp[e] = es.od_new;
-      p.t_epoch[e] = (int64_t)es.t_new;
-      if (!es.due) {
-        p.base_power[e] = es.base;
-        p.signal[e] = es.sig_new;
-        if (interp_mode) p.time_since_interp[e] = es.tsi;
-      }
+    any_due |= ctl.tile_due[slot];
+    if (active) {
+      // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
+      const float dn = (float)((double)P - env_buf[le].s_old) * p.f_inv_n;
+      if (p.reward != nullptr) reinterpret_cast<float*>(p.reward)[h] = -(pen * p.f_k_temp + dn * dn * p.f_k_sig);
+      if (kObs) row[9] = env_buf[le].f_sig;
     }
-    if (any_due) {
-      const int nb = p.interp_nb_agents;
-      const int nsamp = N <= nb ? N : nb;
-      if (active && env_buf[le].due && li < nsamp) {
-        int src = li;
-        if (N > nb) {
-          if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
-          else {
-            const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
-                                       STREAM_IDS + 16 * (uint32_t)li, p.seed);
-            src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
-          }
+    if (kObs) {
+      const int wrow0 = warp * 32;
+      const int nrows_w = min(32, H - wrow0);
+      if (nrows_w > 0) {
+        const int F = p.F;
+        float* dst = reinterpret_cast<float*>(p.obs) + (size_t)((unsigned)tile * (unsigned)GN + (unsigned)wrow0) * F;
+        const float* src = reinterpret_cast<const float*>(smem_raw + p.off_stage) + wrow0 * F;
+        const uint32_t bytes = (uint32_t)(nrows_w * F * sizeof(float));
+        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
+        if (bulk_ok) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) bulk_store_s2g(dst, src, bytes);
+        } else {
+          __syncwarp();
+          for (int i = lane; i < nrows_w * F; i += 32) dst[i] = src[i];
         }
-        const size_t hs = (size_t)e * N + src;
-        const T2 t2 = reinterpret_cast<const T2*>(p.temps)[hs];
-        const double tg = (double)reinterpret_cast<const T4*>(p.coef_b)[hs].w;
-        const EnvScratch& es = env_buf[le];
-        s_val[tid] = interp_eval<R>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, es.od_new - tg, es.hour_s,
-                                    es.date);
-      }
-      house_sync(house_threads);
-      if (active && li == 0 && env_buf[le].due) {
-        EnvScratch& es = env_buf[le];
-        double base = 0.0;
-        for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);
-        if (N > nb) base = mul_rn(base, (double)N / (double)nb);
-        const double sig = grid_signal(p, base, es.time_sec, es.sig_noise, p.artificial_ratio[e], p.max_power[e]);
-        p.base_power[e] = base;
-        p.time_since_interp[e] = 0;
-        p.signal[e] = sig;
-        es.f_sig = sig * p.inv_norm_sig_agents;
-      }
-      house_sync(house_threads);
-    }
-    if (active && p.reward != nullptr) {
-      const EnvScratch& es = env_buf[le];
-      const R dn = (R)((double)P - es.s_old) * (R)p.inv_n;
-      reinterpret_cast<R*>(p.reward)[h] = -(pen * (R)p.k_temp + dn * dn * (R)p.k_sig);
-    }
-    if (p.obs != nullptr && nrows_w > 0) {
-      if (lane < nrows_w) stage[lane * F + 9] = (R)env_buf[le].f_sig;
-      R* dst = reinterpret_cast<R*>(p.obs) + (size_t)((unsigned)env0 * (unsigned)N + (unsigned)wrow0) * F;
-      const uint32_t bytes = (uint32_t)(nrows_w * F * sizeof(R));
-      const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
-      if (bulk_ok) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) bulk_store_s2g(dst, stage, bytes);
-      } else {
-        __syncwarp();
-        for (int i = lane; i < nrows_w * F; i += 32) dst[i] = stage[i];
-        __syncwarp();
       }
     }
-    // this warp is done with EnvScratch slot `slot`: let the prologue warp reuse it for tile it+ring
+    // this warp is done with ring slot `slot`: let the prologue warp reuse it for tile it+ring
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctl.empty[slot]);
   }
   cp_async_wait<0>();
-  if (lane == 0) bulk_wait_read_all();
-#undef N
-#undef G
-#undef T
-#undef house_threads
-#undef ns
-#undef in_stride
+  if (kObs && lane == 0) bulk_wait_read_all();
+  if (interp_mode && any_due) pipe_refresh_pass(p, le, li);  // CTA-uniform: every house thread read the same flags
 }
 
 // ----------------------------------------------------------------------------------------
@@ -1181,7 +1222,7 @@ static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cuda
   return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
 
-template <int kC, int kAct, int kBatch>
+template <int kC, int kAct, bool kObs>
 static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, cudaStream_t stream) {
   static int ctas_per_sm[64] = {};
   static int sm_count[64] = {};
@@ -1191,14 +1232,14 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   cudaGetDevice(&dev);
   if (dev >= 64) return cudaErrorInvalidDevice;
   if (sm_count[dev] == 0) {
-    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC, kAct, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
+    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC, kAct, kObs>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
     if (err != cudaSuccess) return err;
     err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
     if (err != cudaSuccess) return err;
   }
   if (cached_threads[dev] != g.threads || cached_smem[dev] != g.pipe_smem_bytes) {
     int n = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC, kAct, kBatch>, g.threads, g.pipe_smem_bytes);
+    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC, kAct, kObs>, g.threads, g.pipe_smem_bytes);
     if (err != cudaSuccess) return err;
     if (n < 1) return cudaErrorLaunchOutOfResources;
     ctas_per_sm[dev] = n;
@@ -1209,29 +1250,35 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   kp.n_tiles = g.ctas;
   int grid = sm_count[dev] * ctas_per_sm[dev];
   if (grid > g.ctas) grid = g.ctas;
-  step_pipe_kernel<kC, kAct, kBatch><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
+  step_pipe_kernel<kC, kAct, kObs><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
   return cudaGetLastError();
 }
 
-template <int kC>
+template <int kC, bool kObs>
 static cudaError_t launch_pipe_c(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  if (g.pro_batch == 1) {
-    if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, 1>(kp, g, stream);
-    if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, 1>(kp, g, stream);
-    return launch_pipe_t<kC, MDR_ACT_RANDOM, 1>(kp, g, stream);
-  }
-  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, 8>(kp, g, stream);
-  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, 8>(kp, g, stream);
-  return launch_pipe_t<kC, MDR_ACT_RANDOM, 8>(kp, g, stream);
+  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, kObs>(kp, g, stream);
+  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, kObs>(kp, g, stream);
+  return launch_pipe_t<kC, MDR_ACT_RANDOM, kObs>(kp, g, stream);
 }
 
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  return kp.C == 10 ? launch_pipe_c<10>(kp, g, stream) : launch_pipe_c<0>(kp, g, stream);
+  if (kp.obs != nullptr) return kp.C == 10 ? launch_pipe_c<10, true>(kp, g, stream) : launch_pipe_c<0, true>(kp, g, stream);
+  return kp.C == 10 ? launch_pipe_c<10, false>(kp, g, stream) : launch_pipe_c<0, false>(kp, g, stream);
 }
 
-// tiles per prologue pass: 1 when the observation is written (house work per tile covers the prologue and
-// shared memory is tight), up to 8 otherwise, keeping at least one lane per env
-int pipe_pro_batch(int envs_per_cta, bool has_obs) { return (!has_obs && 8 * envs_per_cta <= 32) ? 8 : 1; }
+// tiles per prologue pass (power of two): as deep as the lanes (one per env at least), the ring
+// (kMaxRing slots) and the shared-memory budget (the observation staging tile is the big consumer)
+// allow.  MDR_PRO_BATCH overrides the cap for tuning.
+int pipe_pro_batch(int envs_per_cta, bool has_obs) {
+  int cap = has_obs ? 4 : 8;
+  if (const char* s = getenv("MDR_PRO_BATCH")) {
+    const int v = atoi(s);
+    if (v == 1 || v == 2 || v == 4 || v == 8) cap = v;
+  }
+  int b = 1;
+  while (2 * b <= cap && 2 * b * envs_per_cta <= 32) b *= 2;
+  return b;
+}
 
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision) {
   return precision == MDR_F32 && kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 &&
@@ -1248,7 +1295,7 @@ cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int preci
   return precision == MDR_F32 ? launch_step_r<float>(kp, g, stream) : launch_step_r<double>(kp, g, stream);
 }
 
-// layout of the pipelined kernel: message window, power partials and EnvScratch double buffered, one
+// layout of the pipelined kernel: message window and power partials double buffered, a ring of PipeEnv records, one
 // contiguous staging tile for the tile's G*N observation rows, two cp.async input stages
 size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int n_features, bool need_val, bool has_obs,
                         int n_comm, int part_stride, int pro_batch) {
@@ -1256,8 +1303,8 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   const size_t off_msg = o;   o += align16((size_t)2 * genvs * (n_houses + n_comm) * 4 * sizeof(float));
   const size_t off_pw = o;    o += align16((size_t)2 * genvs * part_stride * sizeof(double));
   const size_t off_val = o;   o += need_val ? align16((size_t)hmax * sizeof(double)) : 0;
-  const size_t off_env = o;   o += align16((size_t)2 * pro_batch * genvs * sizeof(EnvScratch));
-  const size_t off_ctl = o;   o += align16(pipe_ctl_bytes(2 * pro_batch));
+  const size_t off_env = o;   o += align16((size_t)2 * pro_batch * genvs * sizeof(PipeEnv));
+  const size_t off_ctl = o;   o += align16(sizeof(PipeCtl));
   const size_t off_stage = o; o += has_obs ? align16((size_t)genvs * n_houses * n_features * sizeof(float)) : 0;
   const size_t off_in = o;    o += align16((size_t)2 * hmax * 52);
   if (kp) {

@@ -50,6 +50,7 @@ struct KernelParams {
   // scalars
   double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
   double inv_norm_reg_sig, inv_norm_sig_agents, cop_over_def_cap, inv_perlin_period, inv_n, k_temp, k_sig, od_amplitude, od_bias, two_pi_over_24;
+  float f_inv_norm_reg_sig, f_inv_norm_sig_agents, f_cop_over_def_cap, f_inv_n, f_k_temp, f_k_sig;  // fp32 copies (pipelined kernel)
   double def_ua, def_cm, def_ca, def_hm, def_cop, def_latent, def_cap, hvac_cop, hvac_latent;
   double day_temp, night_temp, temp_std, window_area, shading_coeff, avg_power_per_hvac;
   double sin_periods[MDR_MAX_SINUSOIDS], sin_ratios[MDR_MAX_SINUSOIDS];
