@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDR_ABI_VERSION 5
+#define MDR_ABI_VERSION 6
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
@@ -119,6 +119,13 @@ typedef struct MdrConfig {
   int32_t interp_dims[MDR_INTERP_DIMS];
   double interp_axes[MDR_INTERP_DIMS][MDR_INTERP_MAX_AXIS];
   uint64_t seed; /* Philox key for draws that are not replayed */
+  /* Optional L2 residency window for the step launches (0 bytes = none): the address range that holds the
+     per-house state and coefficients re-read by every step.  Accesses inside it are launched with
+     cudaAccessPropertyPersisting (hit ratio l2_hit_ratio), so the once-written observation stream does not
+     evict them.  Needs a persisting-L2 carve-out on the device: see mdr_l2_persist_limit. */
+  const void *l2_window_base;
+  uint64_t l2_window_bytes;
+  double l2_hit_ratio;
 } MdrConfig;
 
 /* Per-house struct-of-arrays.  Packed vectors keep every access a coalesced 8/16-byte load. */
@@ -212,6 +219,11 @@ int mdr_observe(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *en
    requires on-device action/noise sources).  One kernel launch per step. */
 int mdr_step(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
              const MdrStepInputs *in, const MdrOutputs *out, int32_t n_steps, void *stream);
+
+/* Sets the device's persisting-L2 carve-out (cudaLimitPersistingL2CacheSize) to min(bytes, device maximum);
+   bytes = 0 resets it and drops persisting lines.  Reports the granted carve-out and the largest access
+   policy window of the device.  Device-global setting: call once per process and device. */
+int mdr_l2_persist_limit(int device, size_t bytes, size_t *granted_bytes, size_t *max_window_bytes);
 
 /* Same step with HOST buffers: copies `host_actions` to `in->actions` (device staging), runs
    the step, copies obs / reward / per-env (power, signal) back into the host pointers and

@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-MDR_ABI_VERSION = 5
+MDR_ABI_VERSION = 6
 MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
@@ -35,7 +35,7 @@ class MdrConfig(C.Structure):
         + [(n, _f64) for n in ("steps_amplitude_per_hvac", "steps_period", "perlin_amplitude", "perlin_period",
                                "comm_defect_prob")]
         + [("interp_dims", _i32 * INTERP_DIMS), ("interp_axes", (_f64 * INTERP_MAX_AXIS) * INTERP_DIMS),
-           ("seed", C.c_uint64)]
+           ("seed", C.c_uint64), ("l2_window_base", _vp), ("l2_window_bytes", C.c_uint64), ("l2_hit_ratio", _f64)]
     )
 
 
@@ -60,7 +60,8 @@ class MdrOutputs(C.Structure):
 
 
 EXPORTS = ("mdr_version", "mdr_strerror", "mdr_last_cuda_error", "mdr_obs_width", "mdr_validate",
-           "mdr_launch_geometry", "mdr_precompute", "mdr_reset", "mdr_observe", "mdr_step", "mdr_step_host")
+           "mdr_launch_geometry", "mdr_precompute", "mdr_reset", "mdr_observe", "mdr_step", "mdr_step_host",
+           "mdr_l2_persist_limit")
 
 _lib = None
 
@@ -102,6 +103,7 @@ def load(build_if_missing: bool = True):
     lib.mdr_observe.argtypes = step_args + [_vp]
     lib.mdr_step.argtypes = step_args + [_i32, _vp]
     lib.mdr_step_host.argtypes = step_args + [_vp, _vp, _vp, _vp, _vp, _vp]
+    lib.mdr_l2_persist_limit.argtypes = [C.c_int, C.c_size_t, P(C.c_size_t), P(C.c_size_t)]
     if lib.mdr_version() != MDR_ABI_VERSION:
         raise MdrError("libmdr_b200.so ABI %d != binding ABI %d (rebuild)" % (lib.mdr_version(), MDR_ABI_VERSION))
     _lib = lib

@@ -129,6 +129,9 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   g->smem_bytes = smem;
   g->pipe_smem_bytes = 0;
   g->pro_batch = 1;
+  g->l2_window_base = c->l2_window_base;
+  g->l2_window_bytes = c->l2_window_base ? (size_t)c->l2_window_bytes : 0;
+  g->l2_hit_ratio = (float)(c->l2_hit_ratio > 0.0 && c->l2_hit_ratio <= 1.0 ? c->l2_hit_ratio : 1.0);
   if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32) {
     g->pro_batch = mdr::pipe_pro_batch(G, has_obs);
     const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride, g->pro_batch);
@@ -245,6 +248,29 @@ static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, cons
   k.interp_table = in->interp_table; k.step_index = in->step_index;
   k.obs = out->obs; k.reward = out->reward;
   k.is_reset = is_reset;
+  return MDR_OK;
+}
+
+extern "C" int mdr_l2_persist_limit(int device, size_t bytes, size_t* granted_bytes, size_t* max_window_bytes) {
+  cudaError_t err = cudaSetDevice(device);
+  if (err != cudaSuccess) return cuda_fail(err);
+  int max_persist = 0, max_window = 0;
+  err = cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+  if (err != cudaSuccess) return cuda_fail(err);
+  err = cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+  if (err != cudaSuccess) return cuda_fail(err);
+  const size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+  err = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  if (err != cudaSuccess) return cuda_fail(err);
+  if (bytes == 0) {
+    err = cudaCtxResetPersistingL2Cache();
+    if (err != cudaSuccess) return cuda_fail(err);
+  }
+  size_t got = 0;
+  err = cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+  if (err != cudaSuccess) return cuda_fail(err);
+  if (granted_bytes) *granted_bytes = got;
+  if (max_window_bytes) *max_window_bytes = (size_t)max_window;
   return MDR_OK;
 }
 

@@ -1160,12 +1160,15 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         const uint32_t bytes = (uint32_t)(nrows_w * F * sizeof(float));
         const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
         if (bulk_ok) {
+          // measured alternatives (tools/microbench): a coalesced st.global.v4 copy loop is ~4% slower,
+          // an L2 evict_first hint on this store changes nothing
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) bulk_store_s2g(dst, src, bytes);
         } else {
           __syncwarp();
           for (int i = lane; i < nrows_w * F; i += 32) dst[i] = src[i];
+          __syncwarp();
         }
       }
     }
@@ -1250,8 +1253,27 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   kp.n_tiles = g.ctas;
   int grid = sm_count[dev] * ctas_per_sm[dev];
   if (grid > g.ctas) grid = g.ctas;
-  step_pipe_kernel<kC, kAct, kObs><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
-  return cudaGetLastError();
+  if (g.l2_window_bytes == 0) {
+    step_pipe_kernel<kC, kAct, kObs><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
+    return cudaGetLastError();
+  }
+  // keep the per-house state/coefficients L2-resident across steps (they are re-read every step,
+  // the observation rows only stream through)
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeAccessPolicyWindow;
+  attr.val.accessPolicyWindow.base_ptr = const_cast<void*>(g.l2_window_base);
+  attr.val.accessPolicyWindow.num_bytes = g.l2_window_bytes;
+  attr.val.accessPolicyWindow.hitRatio = g.l2_hit_ratio;
+  attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(g.threads);
+  lc.dynamicSmemBytes = g.pipe_smem_bytes;
+  lc.stream = stream;
+  lc.attrs = &attr;
+  lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, step_pipe_kernel<kC, kAct, kObs>, kp);
 }
 
 template <int kC, bool kObs>

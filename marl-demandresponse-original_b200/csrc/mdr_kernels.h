@@ -62,6 +62,9 @@ struct KernelParams {
 struct Geometry {
   int envs_per_cta, threads, ctas, rows_per_pass, hmax, house_warps, pro_warp, part_stride, pro_batch;
   size_t smem_bytes, pipe_smem_bytes;
+  const void* l2_window_base;  // optional persisting-L2 access policy window of the launch
+  size_t l2_window_bytes;
+  float l2_hit_ratio;
 };
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,

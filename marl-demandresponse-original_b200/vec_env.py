@@ -40,7 +40,7 @@ def load_interp_table(flat: FlatConfig):
 
 class VecDemandResponseEnv:
     def __init__(self, config, population, *, precision="fp32", device=None, interp_table=None, seed=0,
-                 action_source="array", comm_table=None, test=False, with_obs=True):
+                 action_source="array", comm_table=None, test=False, with_obs=True, l2_persist=None):
         if not torch.cuda.is_available():
             raise _lib.MdrError("a CUDA device is required: this environment has no CPU fallback")
         self.lib = _lib.load()
@@ -51,6 +51,9 @@ class VecDemandResponseEnv:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.seed, self.action_source, self.with_obs = int(seed), action_source, bool(with_obs)
+        # L2 residency of the per-house state (None = MDR_L2_PERSIST env var; default OFF: measured 2x slower on c4)
+        self.l2_persist = (os.environ.get("MDR_L2_PERSIST", "0") == "1") if l2_persist is None else bool(l2_persist)
+        self._l2_window = (0, 0, 1.0)
         self.n_envs = int(len(np.atleast_1d(population["t_epoch"])))
         self.n_houses = self.flat.n_houses
         self.n_comm = self.flat.n_comm
@@ -79,15 +82,29 @@ class VecDemandResponseEnv:
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
         self.raw = {k: z(e, n, dtype=f64) for k in ("ua", "cm", "ca", "hm", "cap", "target", "deadband")}
         self.lockout_dur = z(e, n, dtype=i32)
-        self.coef_a, self.coef_b, self.coef_c = z(e, n, 4, dtype=r), z(e, n, 4, dtype=r), z(e, n, 2, dtype=r)
+        # everything the step kernel re-reads per house lives in ONE arena (coefficients, state,
+        # action staging), so a single access-policy window can keep it L2-resident across steps
+        rb = 4 if r == torch.float32 else 8
+        sizes = [("coef_a", 4 * rb), ("coef_b", 4 * rb), ("coef_c", 2 * rb), ("temps", 2 * rb), ("hvac", 4), ("actions", 1)]
+        offs, o = {}, 0
+        for name, per_house in sizes:
+            offs[name] = o
+            o += (e * n * per_house + 255) // 256 * 256
+        self._arena = torch.zeros(o, dtype=torch.uint8, device=dev)
+
+        def carve(name, shape, dtype):
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            return self._arena[offs[name]:offs[name] + nbytes].view(dtype).view(*shape)
+
+        self.coef_a, self.coef_b = carve("coef_a", (e, n, 4), r), carve("coef_b", (e, n, 4), r)
+        self.coef_c, self.temps = carve("coef_c", (e, n, 2), r), carve("temps", (e, n, 2), r)
+        self.hvac = carve("hvac", (e, n), i32)
         self.interp_key = z(e, n, dtype=i32)
-        self.temps = z(e, n, 2, dtype=r)
-        self.hvac = z(e, n, dtype=i32)
         self.env = {k: z(e, dtype=f64) for k in ("phase", "od_temp", "solar_gain", "artificial_ratio",
                                                 "max_power", "base_power", "signal", "cluster_power", "perlin_seed")}
         self.t_epoch = z(e, dtype=torch.int64)
         self.time_since_interp = z(e, dtype=i32)
-        self.actions = z(e, n, dtype=torch.uint8)
+        self.actions = carve("actions", (e, n), torch.uint8)
         self.obs = z(e, n, self.n_features, dtype=r) if self.with_obs else None
         self.reward = z(e, n, dtype=r)
         self._pinned = None
@@ -145,6 +162,10 @@ class VecDemandResponseEnv:
     def _build_structs(self):
         self.cfg = self.flat.to_struct(self.n_envs, self.precision, self.device.index, self.seed, self.action_source,
                                        per_env_table=self._per_env_table)
+        if self.l2_persist:
+            self._setup_l2_window()
+        self.cfg.l2_window_base = C.c_void_p(self._l2_window[0]) if self._l2_window[1] else None
+        self.cfg.l2_window_bytes, self.cfg.l2_hit_ratio = self._l2_window[1], self._l2_window[2]
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         h = _lib.MdrHouses()
         for k in ("ua", "cm", "ca", "hm", "cap", "target", "deadband"):
@@ -163,6 +184,19 @@ class VecDemandResponseEnv:
         self.out_s.obs, self.out_s.reward = p(self.obs), p(self.reward)
         self._refs = (C.byref(self.cfg), C.byref(self.houses_s), C.byref(self.envs_s), C.byref(self.in_s),
                       C.byref(self.out_s))
+
+    def _setup_l2_window(self):
+        """Persisting-L2 carve-out + access policy window over the state arena (B200: 126 MB L2)."""
+        granted, max_window = C.c_size_t(), C.c_size_t()
+        nbytes = self._arena.numel()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mdr_l2_persist_limit(self.device.index, nbytes, C.byref(granted), C.byref(max_window)),
+                       "mdr_l2_persist_limit")
+        window = min(nbytes, max_window.value)
+        if granted.value == 0 or window == 0:
+            self._l2_window = (0, 0, 1.0)
+            return
+        self._l2_window = (self._arena.data_ptr(), window, min(1.0, granted.value / window))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -349,7 +383,8 @@ class VecDemandResponseEnv:
     def __deepcopy__(self, memo):
         new = object.__new__(type(self))
         memo[id(self)] = new
-        skip = {"lib", "cfg", "houses_s", "envs_s", "in_s", "out_s", "_refs", "_keep", "_pinned"}
+        skip = {"lib", "cfg", "houses_s", "envs_s", "in_s", "out_s", "_refs", "_keep", "_pinned", "_arena", "coef_a",
+                "coef_b", "coef_c", "temps", "hvac", "actions"}
         for k, v in self.__dict__.items():
             if k in skip:
                 continue
@@ -362,5 +397,13 @@ class VecDemandResponseEnv:
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
         new.lib, new._keep, new._pinned = self.lib, [], None
+        # the arena-backed tensors are views: clone the arena and carve the same views out of the copy
+        new._arena = self._arena.clone()
+        base = self._arena.data_ptr()
+        for k in ("coef_a", "coef_b", "coef_c", "temps", "hvac", "actions"):
+            t = getattr(self, k)
+            off = t.data_ptr() - base
+            nbytes = t.numel() * t.element_size()
+            new.__dict__[k] = new._arena[off:off + nbytes].view(t.dtype).view(*t.shape)
         new._build_structs()
         return new

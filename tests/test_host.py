@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "mdr_b200.h")).read()
-    declared = set(re.findall(r"\b(mdr_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mdr_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     lib = mdr_b200.load_library()
     for name in declared:
