@@ -27,6 +27,7 @@
 
 namespace mdr {
 
+
 // ----------------------------------------------------------------------------------------
 struct EnvScratch {
   double P, od_new, rew_sig, pen_mean, pen_max, hour_s, date, s_old, sig_new, sig_noise, base;
@@ -288,7 +289,10 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
   if (!reset) {
     // ClusterHouses.compute_OD_temp, :1070-1081 (amplitude, bias and 2*pi/24 folded on the host)
     const double time_day = cal.hour + cal.minute * (1.0 / 60.0);
-    od_new = p.od_amplitude * sin(p.two_pi_over_24 * (time_day + (-6 + phase))) + p.od_bias;
+    // (the fp32 pipelined kernel takes sinpi: no Payne-Hanek slow path in its instruction stream, and
+    //  the 1e-16 relative difference to sin(2*pi/24 * u) is far below fp32 resolution)
+    od_new = kPipe ? p.od_amplitude * sinpi((time_day + (-6 + phase)) * (1.0 / 12.0)) + p.od_bias
+                   : p.od_amplitude * sin(p.two_pi_over_24 * (time_day + (-6 + phase))) + p.od_bias;
     od_new += od_noise;
   }
   // SingleHouse.update_temperature evaluates house_solar_gain at the NEW datetime (:694)
@@ -305,9 +309,8 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
   double sig = s_old;
   if (!observe_only && !due) sig = grid_signal(p, base, time_sec, sig_noise, ratio, max_power);
   if (kPipe) {
-    // pipelined kernel: the prologue warp owns the per-env outputs that do not depend on the houses
-    // (each env belongs to exactly one tile per launch, and the house threads take the old values
-    // from the record, so running ahead of them is safe)
+    // pipelined kernel: the prologue warp owns the per-env outputs that neither depend on the houses
+    // nor are read by them (each env belongs to exactly one tile per launch, so running ahead is safe)
     if (sub == 0 && valid) {
       pe.s_old = s_old;
       pe.od_new = od_new;
@@ -317,7 +320,7 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
       pe.due = due;
       pe.time_sec = time_sec;
       p.t_epoch[e2] = (int64_t)t;
-      p.od_temp[e2] = od_new;
+      p.od_temp[e2] = od_new;  // the house threads take the OLD value from the record
       if (!due) {
         p.base_power[e2] = base;
         p.signal[e2] = sig;
@@ -794,6 +797,44 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
 // over the tile loop (shared-memory addresses, neighbour window, partial-sum slots) is computed
 // once per thread before the loop.
 // ----------------------------------------------------------------------------------------
+// Trace build (-DMDR_TRACE): lane 0 of every warp of CTA MDR_TRACE_CTA stamps globaltimer at fixed
+// points of its first MDR_TRACE_TILES tiles; tools/trace_tile.py reads the buffer back.
+#ifdef MDR_TRACE
+#ifndef MDR_TRACE_CTA
+#define MDR_TRACE_CTA 200
+#endif
+#define MDR_TRACE_TILES 24
+#define MDR_TRACE_POINTS 10
+__device__ unsigned long long g_trace[8 * MDR_TRACE_TILES * MDR_TRACE_POINTS];
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define MDR_STAMP_AT(w, t, k)                                                                        \
+  do {                                                                                                \
+    if (blockIdx.x == MDR_TRACE_CTA && (threadIdx.x & 31) == 0 && (t) < MDR_TRACE_TILES)              \
+      g_trace[((w) * MDR_TRACE_TILES + (t)) * MDR_TRACE_POINTS + (k)] = global_ns();                  \
+  } while (0)
+#define MDR_STAMP(k) MDR_STAMP_AT(warp, it, k)
+}  // namespace mdr
+// trace builds only (tools/trace_tile.py): copies the globaltimer stamps of the traced CTA to the host
+extern "C" int mdr_debug_trace(unsigned long long* host, size_t n, int clear) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -5;
+  if (cudaMemcpyFromSymbol(host, mdr::g_trace, n * sizeof(unsigned long long)) != cudaSuccess) return -5;
+  if (clear) {
+    void* ptr = nullptr;
+    cudaGetSymbolAddress(&ptr, mdr::g_trace);
+    cudaMemset(ptr, 0, n * sizeof(unsigned long long));
+  }
+  return 0;
+}
+namespace mdr {
+#else
+#define MDR_STAMP_AT(w, t, k) do { } while (0)
+#define MDR_STAMP(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async_16(void* s, const void* g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
@@ -842,43 +883,53 @@ struct PipeCtl {
 // groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  The deeper the
 // batch, the further the prologue's dependent fp64 / Philox / global-load chains are from the
 // house warps' critical path.
-__device__ __noinline__ void prologue_pipe_main(const KernelParams& p) {
+// One pass: tiles it0 .. it0+B-1 of this CTA (B a power of two <= pro_batch).
+__device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PipeEnv* s_env = reinterpret_cast<PipeEnv*>(smem_raw + p.off_env);
   PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
-  const int B = p.pro_batch, ring = 2 * B;
+  const int ring = 2 * p.pro_batch;
+  const int ring_shift = 31 - __clz(ring);
   const int lane = threadIdx.x & 31;
   const int lanes_per_tile = 32 / B;
-  const int L = p.pro_lanes, groups = lanes_per_tile / L;  // env groups processed at once per tile
+  int L = 16;  // lanes cooperating on one env (2 * nb_octaves + 1 = 11 Philox draws per env)
+  while (L > 1 && L * p.G > lanes_per_tile) L >>= 1;
+  const int groups = lanes_per_tile / L;  // envs of a tile processed at once (>= 1: G * pro_batch <= 32)
   const int tlane = lane & (lanes_per_tile - 1);
   const int sub = tlane & (L - 1), grp = tlane / L;
   const int my_k = lane / lanes_per_tile;  // which tile of the pass this lane works for
   const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
-  EnvScratch unused;
-  for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) {  // warp-uniform
-    const int it = it0 + my_k;
-    const int tile = blockIdx.x + it * gridDim.x;
-    const bool tile_valid = tile < p.n_tiles;
-    const int slot = it & (ring - 1);
-    const int use = it / ring;
-    if (tile_valid && use >= 1) mbar_wait(&ctl.empty[slot], (use & 1) ^ 1);  // house warps released the slot
-    __syncwarp();
-    const int tile_c = tile_valid ? tile : blockIdx.x;  // lanes of an absent tile compute but never write
-    const int env0 = tile_c * p.G;
-    const int genvs = min(p.G, p.E - env0);
-    PipeEnv* buf = s_env + slot * p.G;
-    int my_due = 0;
-    for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count (G, not genvs)
-      const int le2 = first + grp;
-      const bool valid = tile_valid && le2 < genvs;
-      const int lec = le2 < genvs ? le2 : genvs - 1;
-      my_due |= env_prologue<true>(p, unused, buf[lec], env0 + lec, sub, L, valid, false, false);
-    }
-    const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
-    if (tile_valid && tlane == 0) ctl.tile_due[slot] = (due_ballot & group_mask) != 0;
-    __syncwarp();
-    if (tile_valid && tlane == 0) mbar_arrive(&ctl.full[slot]);
+  const int it = it0 + my_k;
+  const int tile = blockIdx.x + it * gridDim.x;
+  const bool tile_valid = tile < p.n_tiles;
+  const int slot = it & (ring - 1);
+  MDR_STAMP_AT(7, it0, 8);
+  // the house warps must have released the pass's ring slots.  Warp-uniform loop over the B barriers:
+  // per-lane-group waits on different mbarriers (a divergent try_wait spin) were measured to return
+  // up to 8 us late (tools/trace_tile.py)
+  for (int k = 0; k < B; ++k) {
+    const int itk = it0 + k;
+    if (blockIdx.x + itk * gridDim.x < p.n_tiles && (itk >> ring_shift) >= 1)
+      mbar_wait(&ctl.empty[itk & (ring - 1)], (((itk >> ring_shift) & 1) ^ 1));
   }
+  MDR_STAMP_AT(7, it0, 0);
+  const int tile_c = tile_valid ? tile : blockIdx.x;  // lanes of an absent tile compute but never write
+  const int env0 = tile_c * p.G;
+  const int genvs = min(p.G, p.E - env0);
+  PipeEnv* buf = s_env + slot * p.G;
+  EnvScratch unused;
+  int my_due = 0;
+  for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count (G, not genvs)
+    const int le2 = first + grp;
+    const bool valid = tile_valid && le2 < genvs;
+    const int lec = le2 < genvs ? le2 : genvs - 1;
+    my_due |= env_prologue<true>(p, unused, buf[lec], env0 + lec, sub, L, valid, false, false);
+  }
+  const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
+  if (tile_valid && tlane == 0) ctl.tile_due[slot] = (due_ballot & group_mask) != 0;
+  __syncwarp();
+  if (tile_valid && tlane == 0) mbar_arrive(&ctl.full[slot]);
+  MDR_STAMP_AT(7, it0, 7);
 }
 
 // Deferred interpolation refresh (every interp_update_period seconds; PowerGrid.step :1250-1255,
@@ -965,7 +1016,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   }
   __syncthreads();
   if (warp >= p.house_warps) {
-    prologue_pipe_main(p);
+    const int B = p.pro_batch;
+    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
     return;
   }
 
@@ -1035,6 +1087,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const bool active = tid < H;
     const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
     const int e = tile * G + le;
+    MDR_STAMP(0);
     int cmd = cmd_next;
     const int next = tile + tile_stride;
     if (next < n_tiles) {
@@ -1042,11 +1095,15 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       cmd_next = fetch_action(next);
     }
     cp_async_commit();
-    // hand-over from the prologue warp: it produced this tile's records at least one tile ago
+    // hand-over from the prologue warp (normally produced more than a tile ago).  Waiting here rather than
+    // at the end of the tile (with the house threads prefetching od_temp themselves) measured the same.
     const int slot = it & ring_mask;
+    const PipeEnv* const env_buf = s_env + slot * G;
     mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);
-    PipeEnv* const env_buf = s_env + slot * G;
+    const float od_old = env_buf[le].od_old;
+    MDR_STAMP(1);
     cp_async_wait<1>();  // this thread's copies of the current tile have landed
+    MDR_STAMP(2);
 
     // ---------------- phase A: per house ---------------------------------------------------
     float t_air = 0, t_mass = 0, target = 0, p_on = 0, deadband = 0, inv_lock = 1, pen = 0, pw = 0;
@@ -1059,7 +1116,6 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       const float2 tt = *reinterpret_cast<const float2*>(in_t + so);
       const float2 cc = *reinterpret_cast<const float2*>(in_t + so + T * 8);
       const int hv = *reinterpret_cast<const int*>(in_h + so);
-      const float od_old = env_buf[le].od_old;
       target = cb.w; p_on = cb.z; deadband = cc.x;
       inv_lock = __fdividef(1.0f, cc.y);
       on = hv & 1; sso = hv >> 2;
@@ -1102,14 +1158,18 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
       if (active && (lane == 0 || prev_key != key)) part[my_part] = psum;
     }
-    // the staging rows of this warp may still be read by the previous tile's bulk store
+    MDR_STAMP(3);
+    // the staging rows of this warp may still be read by the previous tile's bulk store (waited for
+    // BEFORE the barrier: the two waits then overlap; after it they add up -- measured +5% on c4)
     if (kObs && it > 0) {
       if (lane == 0) bulk_wait_read_all();
       __syncwarp();
     }
+    MDR_STAMP(4);
     // the only CTA-wide rendezvous of a tile: message window + power partials are complete.
     // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
     house_sync(T);
+    MDR_STAMP(5);
 
     float P = 0;
     if (active) {
@@ -1143,6 +1203,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         mrow[4 * k + 3] = m.w;
       }
     }
+    MDR_STAMP(6);
     any_due |= ctl.tile_due[slot];
     if (active) {
       // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
@@ -1175,6 +1236,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     // this warp is done with ring slot `slot`: let the prologue warp reuse it for tile it+ring
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctl.empty[slot]);
+    MDR_STAMP(7);
   }
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();

@@ -1,0 +1,46 @@
+"""Per-tile timeline of one CTA of the pipelined step kernel (trace build of the library:
+nvcc ... -rdc=true -DMDR_TRACE -o variants/lib_trace.so; run with MDR_LIB_PATH pointing at it)."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+import mdr_b200
+
+name = sys.argv[1] if len(sys.argv) > 1 else "c4"
+w = bench.WORKLOADS[name]
+cfg = bench.workload_config(w)
+flat = mdr_b200.FlatConfig(cfg)
+E, N = w["envs"], w["houses"]
+pop = mdr_b200.synthetic_population(flat, E, seed=1234)
+table = mdr_b200.synthetic_interp_table() if w["interp"] else None
+env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", device="cuda:0", seed=1234, interp_table=table,
+                                    action_source=w["action_source"], with_obs=w["obs"])
+env.reset_tensor()
+act = (torch.rand(E, N, device="cuda:0") < 0.5).to(torch.uint8)
+a = act if w["action_source"] == "array" else None
+for _ in range(20):
+    env.step_tensor(a)
+TILES, POINTS = 24, 10
+n = 8 * TILES * POINTS
+buf = (C.c_ulonglong * n)()
+lib = env.lib
+lib.mdr_debug_trace.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+lib.mdr_debug_trace(buf, n, 1)
+env.step_tensor(a)
+lib.mdr_debug_trace(buf, n, 0)
+t = np.frombuffer(buf, dtype=np.uint64).reshape(8, TILES, POINTS).astype(np.int64)
+t0 = t[t > 0].min()
+rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
+names = ["tile start", "issued next+record", "inputs landed", "phase A done", "drain done", "after barrier", "rows done",
+         "tile end"]
+np.set_printoptions(precision=1, suppress=True, linewidth=200)
+for wi in (0, 3, 6):
+    print("house warp %d (us since first stamp): columns = %s" % (wi, ", ".join(names)))
+    print(rel[wi, :, :8])
+print("prologue warp: per pass starting at tile it0: [wait for slot, start, end]")
+print(rel[7][:, [8, 0, 7]])
