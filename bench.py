@@ -39,6 +39,10 @@ WORKLOADS = {
     "c3": dict(envs=10000, houses=100, interp=False, action_source="bangbang", obs=False,
                desc="BASELINE config 3: 1M houses (10000 clusters x 100), heterogeneous parameters + lockout, on-device "
                     "bang-bang, no per-step observation"),
+    "c3fused": dict(envs=10000, houses=100, interp=False, action_source="bangbang", obs=False, fused=75,
+                    desc="BASELINE config 3 through the fused multi-step kernel: 1M houses (10000 clusters x 100), 75 env "
+                         "steps (5 simulated minutes) per launch with the house state in registers, on-device bang-bang + "
+                         "deploy metrics; scored with the per-step 67 B/house-step, flagged fused-K"),
     "c3big": dict(envs=1000, houses=1000, interp=False, action_source="bangbang", obs=False,
                   desc="BASELINE config 3 as 1000 clusters x 1000 houses (one cluster per CTA, generic kernel)"),
 }
@@ -183,8 +187,18 @@ def gpu_arm(args):
     ring = [(torch.rand(E, N, device=dev, generator=gen) < 0.5).to(torch.uint8) for _ in range(8)]
     use_array = w["action_source"] == "array"
 
+    fused = int(w.get("fused", 1))  # env steps per launch (fused multi-step kernel) -- a bench "step" stays ONE env step
+    if fused > 1:
+        env.enable_metrics()
+        args.steps = max(fused, (args.steps // fused) * fused)
+        args.warmup = max(fused, (args.warmup // fused) * fused)
+
     def one_step(i):
-        env.step_tensor(ring[i & 7] if use_array else None)
+        if fused > 1:
+            if i % fused == 0:
+                env.run(fused)
+        else:
+            env.step_tensor(ring[i & 7] if use_array else None)
 
     for i in range(args.warmup):
         one_step(i)
@@ -255,6 +269,8 @@ def gpu_arm(args):
         if os.path.isfile(tpath):
             traffic = json.load(open(tpath)).get("%s_%s" % (args.workload, args.precision))
         geom = env.launch_geometry()
+        if fused > 1:
+            geom["kernel"] = "mdr::run_fused_kernel (%d env steps per launch, state in registers)" % fused
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             procs = os.cpu_count() or 1
@@ -273,8 +289,8 @@ def gpu_arm(args):
                        "l2": "per-step working set %.0f MB > 126 MB L2 (no flush needed)" % (algo * E * N / 1e6)
                              if algo * E * N > 126e6 else "working set fits L2: state/params are re-read from L2 every step, "
                              "as in a real rollout; obs writes stream to HBM",
-                       "launch": geom, "parallelism": "env-sharded x%d, no collective on the step path" % world},
-            "clocks": clocks, "gpu_launches": args.steps,
+                       "launch": geom, "env_steps_per_launch": fused, "parallelism": "env-sharded x%d, no collective on the step path" % world},
+            "clocks": clocks, "gpu_launches": args.steps // fused,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "api": "VecDemandResponseEnv.step_host -> mdr_step_host (pinned host buffers)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDR_ABI_VERSION 6
+#define MDR_ABI_VERSION 7
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
@@ -159,10 +159,29 @@ typedef struct MdrEnvs {
   double *cluster_power;     /* ClusterHouses.cluster_hvac_power */
   int32_t *time_since_interp;/* PowerGrid.time_since_last_interp */
   const double *perlin_seed; /* seed of the device perlin (production mode only) */
-  double *metrics;           /* optional [n_envs, MDR_N_METRICS] running sums, or NULL */
+  double *metrics;           /* optional [n_envs, MDR_N_METRICS] running accumulators (see MDR_M_*), or NULL */
 } MdrEnvs;
 
-#define MDR_N_METRICS 6 /* steps, sum reward/N, sum |T-target|/N, sum (S-P)^2, max |T-target|, sum |S-P|/N^2 */
+/* Per-env running accumulators of MdrEnvs.metrics ([n_envs, MDR_N_METRICS] doubles, += by every mdr_step call
+   that takes the fused multi-step path).  They are the quantities main-deploy.py:124-209 and
+   metrics.py:22-47 accumulate, before their final divisions; T = new air temperature, S = new signal,
+   P = cluster power of the step, r = reward, N = houses per env. */
+enum {
+  MDR_M_STEPS = 0,                /* steps accumulated */
+  MDR_M_SUM_MEAN_REWARD = 1,      /* sum_t sum_k r_k / N              (metrics.py:25) */
+  MDR_M_SUM_MEAN_TEMP_OFFSET = 2, /* sum_t sum_k (T_k - target_k) / N (main-deploy.py:128) */
+  MDR_M_SUM_MEAN_TEMP_ERROR = 3,  /* sum_t sum_k |T_k - target_k| / N (:129) */
+  MDR_M_SUM_SQ_TEMP_ERROR = 4,    /* sum_t sum_k (T_k - target_k)^2   (:136) */
+  MDR_M_SUM_SQ_MAX_TEMP_ERROR = 5,/* sum_t (max_k |T_k - target_k|)^2 (:139) */
+  MDR_M_MAX_TEMP_ERROR = 6,       /* max_t max_k |T_k - target_k|     (:130-131), a running max, not a sum */
+  MDR_M_SUM_OD_TEMP = 7,          /* sum_t OD_temp                    (:140) */
+  MDR_M_SUM_SIGNAL = 8,           /* sum_t S                          (:141) */
+  MDR_M_SUM_CONSUMPTION = 9,      /* sum_t P                          (:142) */
+  MDR_M_SUM_SIGNAL_OFFSET = 10,   /* sum_t (S - P)                    (:144-145) */
+  MDR_M_SUM_SIGNAL_ERROR = 11,    /* sum_t |S - P|                    (:146) */
+  MDR_M_SUM_SQ_SIGNAL_ERROR = 12, /* sum_t (S - P)^2                  (:149) */
+  MDR_N_METRICS = 13
+};
 
 /* Inputs of one step.  NULL replay pointers select on-device generation. */
 typedef struct MdrStepInputs {
@@ -216,7 +235,11 @@ int mdr_observe(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *en
                 const MdrStepInputs *in, const MdrOutputs *out, void *stream);
 
 /* MADemandResponseEnv.step (:174-210) for every env of the shard, `n_steps` times (n_steps > 1
-   requires on-device action/noise sources).  One kernel launch per step. */
+   requires on-device action/noise sources).  One kernel launch per step -- except that steps which need
+   nothing from the host between them (on-device action source, no replayed noise, constant base power,
+   individual_L2 penalty, out->obs == NULL) run as ONE fused launch with the house state in registers
+   (the main-deploy.py:102-209 loop); only that path accumulates envs->metrics, any other
+   configuration with metrics != NULL returns MDR_ERR_UNSUPPORTED. */
 int mdr_step(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
              const MdrStepInputs *in, const MdrOutputs *out, int32_t n_steps, void *stream);
 

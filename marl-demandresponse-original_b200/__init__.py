@@ -29,7 +29,7 @@ def __getattr__(name):
     if name in ("regenerate_table", "regenerate_entries"):
         from . import montecarlo
         return getattr(montecarlo, name)
-    if name in ("RolloutMetrics", "shard_range", "reduce_metrics"):
+    if name in ("RolloutMetrics", "shard_range", "reduce_metrics", "reduce_device_metrics"):
         from . import sharding
         return getattr(sharding, name)
     raise AttributeError(name)

@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-MDR_ABI_VERSION = 6
+MDR_ABI_VERSION = 7
 MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
@@ -15,6 +15,10 @@ PEN = {"individual_L2": 0, "common_L2": 1, "common_max": 2, "mixture": 3}
 BASE = {"constant": 0, "interpolation": 1}
 SIG_FLAT, SIG_SINUSOIDALS, SIG_REGULAR_STEPS, SIG_PERLIN = 0, 1, 2, 3
 ACT = {"array": 0, "bangbang": 1, "random": 2}
+METRIC_NAMES = ("steps", "sum_mean_reward", "sum_mean_temp_offset", "sum_mean_temp_error", "sum_sq_temp_error",
+                "sum_sq_max_temp_error", "max_temp_error", "sum_od_temp", "sum_signal", "sum_consumption",
+                "sum_signal_offset", "sum_signal_error", "sum_sq_signal_error")
+N_METRICS = len(METRIC_NAMES)
 
 _i32, _f64, _vp = C.c_int32, C.c_double, C.c_void_p
 

@@ -238,7 +238,7 @@ static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, cons
       out->obs)
     return MDR_ERR_NULL;
   if (out->obs && !aligned16(out->obs)) return MDR_ERR_ALIGN;
-  if (e->metrics) return MDR_ERR_UNSUPPORTED;  // reserved
+  k.metrics = e->metrics;
   k.t_epoch = e->t_epoch; k.phase = e->phase; k.od_temp = e->od_temp; k.solar_gain = e->solar_gain;
   k.artificial_ratio = e->artificial_ratio; k.max_power = e->max_power;
   k.base_power = e->base_power; k.signal = e->signal; k.cluster_power = e->cluster_power;
@@ -333,6 +333,13 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
                           cfg->base_power_mode == MDR_BASE_INTERPOLATION, out->obs != nullptr, cfg->n_comm, g.part_stride,
                           g.pro_batch);
   }
+  const char* no_fused = getenv("MDR_NO_FUSED");
+  if (!(no_fused && no_fused[0] == '1') && mdr::fused_eligible(k) && g.pro_warp >= g.house_warps &&
+      (n_steps > 1 || k.metrics != nullptr)) {
+    err = mdr::launch_fused(k, g, cfg->precision, n_steps, stream);
+    return err == cudaSuccess ? MDR_OK : cuda_fail(err);
+  }
+  if (k.metrics != nullptr) return MDR_ERR_UNSUPPORTED;
   for (int i = 0; i < n_steps; ++i) {
     err = pipe ? mdr::launch_pipe(k, g, stream) : mdr::launch_step_any(k, g, cfg->precision, stream);
     if (err != cudaSuccess) return cuda_fail(err);

@@ -18,6 +18,7 @@ struct KernelParams {
   int ns, house_threads, in_stride;                            // N + C, house_warps * 32, bytes of one cp.async input stage
   int pro_batch;                                              // pipelined kernel: tiles the prologue warp produces per pass
   int n_tiles;                                                // pipelined kernel: number of G-env tiles
+  int n_fused;                                                // fused multi-step kernel: steps of this launch
   int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
   unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)
@@ -46,6 +47,7 @@ struct KernelParams {
   const int32_t* comm_table;
   const void* interp_table;
   void *obs, *reward;
+  double* metrics;  // [E, MDR_N_METRICS] running accumulators (fused multi-step kernel), or nullptr
   uint64_t step_index, seed;
   // scalars
   double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
@@ -74,6 +76,8 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
 int pipe_pro_batch(int envs_per_cta, bool has_obs);
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision);
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream);
+bool fused_eligible(const KernelParams& kp);
+cudaError_t launch_fused(const KernelParams& kp, const Geometry& g, int precision, int n_steps, cudaStream_t stream);
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);
 cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream);
 

@@ -60,3 +60,21 @@ def reduce_metrics(metrics: RolloutMetrics, group=None):
     out["mean_abs_temp_error"] = out["sum_abs_temp_error"] / hs
     out["rmse_signal"] = (out["sum_sq_signal_error"] / hs) ** 0.5
     return out
+
+
+def reduce_device_metrics(metrics, group=None):
+    """End-of-rollout reduction of the ON-DEVICE accumulators (VecDemandResponseEnv.metrics, [E_shard, N_METRICS],
+    see MDR_M_* in include/mdr_b200.h) over the env axis and over the ranks: one all-reduce(sum) + one
+    all-reduce(max) of N_METRICS + 1 doubles.  Returns the totals as a dict (sums over all envs of all shards;
+    `max_temp_error` is a max; `envs` counts the envs), the only collective of a sharded rollout."""
+    from . import _lib
+    imax = _lib.METRIC_NAMES.index("max_temp_error")
+    sums = torch.cat([metrics.sum(dim=0), torch.tensor([float(metrics.shape[0])], dtype=metrics.dtype, device=metrics.device)])
+    mx = metrics[:, imax].max().reshape(1).clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    out = {k: float(v) for k, v in zip(_lib.METRIC_NAMES, sums[:-1].tolist())}
+    out["max_temp_error"] = float(mx.item())
+    out["envs"] = float(sums[-1].item())
+    return out

@@ -107,6 +107,7 @@ class VecDemandResponseEnv:
         self.actions = carve("actions", (e, n), torch.uint8)
         self.obs = z(e, n, self.n_features, dtype=r) if self.with_obs else None
         self.reward = z(e, n, dtype=r)
+        self.metrics = None  # [E, N_METRICS] fp64 accumulators, allocated by enable_metrics()
         self._pinned = None
 
     def load_population(self, pop):
@@ -177,7 +178,7 @@ class VecDemandResponseEnv:
         e.t_epoch, e.time_since_interp = p(self.t_epoch), p(self.time_since_interp)
         for k in self.env:
             setattr(e, k, p(self.env[k]))
-        e.metrics = None
+        e.metrics = p(self.metrics)
         self.envs_s = e
         self.in_s = _lib.MdrStepInputs()
         self.out_s = _lib.MdrOutputs()
@@ -294,10 +295,52 @@ class VecDemandResponseEnv:
         return t
 
     def run(self, n_steps):
-        """`n_steps` steps with the on-device action source (one launch per step, issued from C)."""
+        """`n_steps` steps with the on-device action source: the deploy loop of main-deploy.py:102-209.
+        Configurations that need nothing from the host between steps (constant base power, individual_L2
+        penalty, with_obs=False) run as ONE fused launch with the house state in registers; anything else
+        is one launch per step, issued from C.  Returns (obs, reward, power, signal) of the LAST step."""
         if self.action_source == "array":
             raise ValueError("run() needs action_source='bangbang' or 'random'")
         return self.step_tensor(None, n_steps=n_steps)
+
+    def enable_metrics(self, reset=True):
+        """Allocates (or clears) the per-env accumulators of main-deploy.py:124-209 / metrics.py:22-47; they are
+        updated on the device by run() / step_tensor() whenever the fused path applies (see mdr_step)."""
+        if self.metrics is None:
+            self.metrics = torch.zeros(self.n_envs, _lib.N_METRICS, dtype=torch.float64, device=self.device)
+            self._build_structs()
+        elif reset:
+            self.metrics.zero_()
+        return self.metrics
+
+    def disable_metrics(self):
+        self.metrics = None
+        self._build_structs()
+
+    def metrics_summary(self, metrics=None):
+        """The figures main-deploy.py:176-209 prints, per env, from the accumulators ([E, N_METRICS] tensor,
+        default: this env's own).  Returns a dict of [E] fp64 tensors."""
+        m = self.metrics if metrics is None else metrics
+        if m is None:
+            raise ValueError("metrics are not enabled")
+        col = {k: m[:, i] for i, k in enumerate(_lib.METRIC_NAMES)}
+        steps = col["steps"].clamp(min=1.0)
+        n = float(self.n_houses)
+        return {
+            "steps": col["steps"],
+            "mean_reward": col["sum_mean_reward"] / steps,
+            "mean_temp_offset": col["sum_mean_temp_offset"] / steps,
+            "mean_temp_error": col["sum_mean_temp_error"] / steps,
+            "max_temp_error": col["max_temp_error"],
+            "rmse_temp": torch.sqrt(col["sum_sq_temp_error"] / (steps * n)),
+            "rms_max_error_temp": torch.sqrt(col["sum_sq_max_temp_error"] / steps),
+            "mean_od_temp": col["sum_od_temp"] / steps,
+            "mean_signal": col["sum_signal"] / steps,
+            "mean_consumption": col["sum_consumption"] / steps,
+            "mean_signal_offset": col["sum_signal_offset"] / steps,
+            "mean_signal_error": col["sum_signal_error"] / steps,
+            "rmse_signal_per_agent": torch.sqrt(col["sum_sq_signal_error"] / steps) / n,
+        }
 
     def step_host(self, host_actions, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None, comm=None):
         """End-to-end step with HOST buffers (what the dict API and the e2e benchmark call):
@@ -363,6 +406,8 @@ class VecDemandResponseEnv:
             sd["obs"] = self.obs.clone()
         if self._comm is not None:
             sd["comm"] = self._comm.clone()
+        if self.metrics is not None:
+            sd["metrics"] = self.metrics.clone()
         sd["step_index"] = self.step_index
         return sd
 
@@ -377,6 +422,9 @@ class VecDemandResponseEnv:
             self.obs.copy_(sd["obs"])
         if "comm" in sd:
             self.set_comm_table(sd["comm"].cpu().numpy())
+        if "metrics" in sd:
+            self.enable_metrics()
+            self.metrics.copy_(sd["metrics"])
         self.step_index = int(sd["step_index"])
         self._precomputed = True
 

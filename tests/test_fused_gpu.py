@@ -1,0 +1,156 @@
+"""Fused multi-step ("deploy") kernel and the on-device metric accumulators, through the C ABI:
+  * K fused steps == K single-step launches (same Philox counters, same arithmetic);
+  * fp64 fused bang-bang rollout vs the numpy oracle stepped with the bang-bang rule (no random draws:
+    temp_std = 0, sinusoidal / flat / regular-step signals), bit-exact integers, 1e-9 on the reals;
+  * the accumulators vs the quantities main-deploy.py:124-209 sums, recomputed with torch from per-step outputs."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(n, signal="sinusoidals", temp_std=None, solar=False):
+    import mdr_b200
+    cfg = mdr_b200.make_default_config()
+    ep = cfg["default_env_prop"]
+    ep["cluster_prop"]["nb_agents"] = n
+    ep["power_grid_prop"]["base_power_mode"] = "constant"
+    ep["power_grid_prop"]["signal_mode"] = signal
+    if temp_std is not None:
+        ep["cluster_prop"]["temp_parameters"][ep["cluster_prop"]["temp_mode"]]["temp_std"] = temp_std
+    cfg["default_house_prop"]["solar_gain_bool"] = solar
+    return cfg
+
+
+def _env(cfg, n_envs, precision, action_source, seed=3):
+    import mdr_b200
+    flat = mdr_b200.FlatConfig(cfg)
+    pop = mdr_b200.synthetic_population(flat, n_envs, seed=seed)
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, seed=seed, action_source=action_source, with_obs=False)
+    env.reset_tensor()
+    return flat, pop, env
+
+
+def _per_step(env, k):
+    os.environ["MDR_NO_FUSED"] = "1"
+    try:
+        for _ in range(k):
+            out = env.step_tensor(None)
+    finally:
+        os.environ.pop("MDR_NO_FUSED", None)
+    return out
+
+
+@pytest.mark.parametrize("precision,n_envs,n,source,signal", [
+    ("fp64", 7, 50, "bangbang", "perlin"), ("fp64", 5, 37, "random", "sinusoidals"), ("fp32", 300, 100, "bangbang", "perlin"),
+    ("fp32", 9, 3, "random", "flat"), ("fp64", 3, 500, "bangbang", "regular_steps")])
+def test_fused_equals_single_steps(precision, n_envs, n, source, signal):
+    import torch
+    cfg = _cfg(n, signal)
+    _, _, a = _env(cfg, n_envs, precision, source)
+    _, _, b = _env(cfg, n_envs, precision, source)
+    k = 77
+    _, rew_a, p_a, s_a = a.run(k)
+    _, rew_b, p_b, s_b = _per_step(b, k)
+    torch.cuda.synchronize()
+    assert torch.equal(a.hvac, b.hvac)
+    assert torch.equal(a.t_epoch, b.t_epoch) and torch.equal(p_a, p_b)
+    tol = dict(rtol=0, atol=1e-9) if precision == "fp64" else dict(rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(a.temps, b.temps, **tol)
+    torch.testing.assert_close(rew_a, rew_b, **tol)
+    torch.testing.assert_close(a.env["od_temp"], b.env["od_temp"], rtol=0, atol=1e-9)
+    torch.testing.assert_close(s_a, s_b, rtol=1e-12, atol=1e-9)
+    # a second fused call continues from the first (step counter, clock)
+    a.run(5)
+    _per_step(b, 5)
+    assert torch.equal(a.hvac, b.hvac) and torch.equal(a.t_epoch, b.t_epoch)
+
+
+@pytest.mark.parametrize("signal,solar", [("sinusoidals", False), ("flat", True), ("regular_steps", False)])
+def test_fused_fp64_vs_oracle_bangbang(signal, solar):
+    import torch
+    from oracle import mdr_oracle as orc
+    n_envs, n, k = 4, 23, 150
+    cfg = _cfg(n, signal, temp_std=0.0, solar=solar)
+    flat, pop, env = _env(cfg, n_envs, "fp64", "bangbang")
+    oracle = orc.OracleEnv(cfg, {kk: v for kk, v in pop.items() if kk != "perlin_seed"})
+    for e in range(n_envs):
+        oracle.grid_step(e, orc.to_datetime(oracle.s["t_epoch"][e]), 0.0)
+    zeros = np.zeros(n_envs)
+    for _ in range(k):
+        act = (oracle.s["t_air"] > oracle.s["target"]).astype(np.uint8)  # agents/bangbang_controllers.py:50-61
+        _, o_rew, o_p, o_s = oracle.step(act, zeros, zeros)
+    _, rew, p, s = env.run(k)
+    torch.cuda.synchronize()
+    assert np.array_equal(env.hvac_on.cpu().numpy(), oracle.s["on"])
+    assert np.array_equal(env.hvac_lockout.cpu().numpy(), oracle.s["lockout"])
+    assert np.array_equal(env.seconds_since_off.cpu().numpy(), oracle.s["sso"])
+    assert np.array_equal(p.cpu().numpy(), o_p)
+    np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(env.t_mass.cpu().numpy(), oracle.s["t_mass"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(rew.cpu().numpy(), o_rew, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(s.cpu().numpy(), o_s, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_device_metrics_match_per_step_recomputation(precision):
+    import torch
+    from mdr_b200 import _lib
+    n_envs, n, k = 11, 60, 90
+    cfg = _cfg(n, "perlin")
+    _, _, a = _env(cfg, n_envs, precision, "bangbang")
+    _, _, b = _env(cfg, n_envs, precision, "bangbang")
+    a.enable_metrics()
+    a.run(40)
+    a.run(k - 40)  # accumulates across calls
+    ref = torch.zeros(n_envs, _lib.N_METRICS, dtype=torch.float64, device="cuda")
+    target = b.coef_b[..., 3].double()
+    for _ in range(k):
+        _, rew, p, s = _per_step(b, 1)
+        err = b.t_air.double() - target
+        d = s - p
+        ref[:, 0] += 1
+        ref[:, 1] += rew.double().sum(1) / n
+        ref[:, 2] += err.sum(1) / n
+        ref[:, 3] += err.abs().sum(1) / n
+        ref[:, 4] += (err * err).sum(1)
+        mx = err.abs().max(1).values
+        ref[:, 5] += mx * mx
+        ref[:, 6] = torch.maximum(ref[:, 6], mx)
+        ref[:, 7] += b.env["od_temp"]
+        ref[:, 8] += s
+        ref[:, 9] += p
+        ref[:, 10] += d
+        ref[:, 11] += d.abs()
+        ref[:, 12] += d * d
+    torch.cuda.synchronize()
+    rtol = 1e-9 if precision == "fp64" else 2e-4
+    torch.testing.assert_close(a.metrics, ref, rtol=rtol, atol=1e-6 if precision == "fp64" else 1e-2)
+    summ = a.metrics_summary()
+    assert torch.all(summ["steps"] == k) and torch.isfinite(summ["rmse_temp"]).all()
+    # metrics with a configuration that cannot take the fused path are refused, not silently dropped
+    import mdr_b200
+    cfg2 = _cfg(n, "perlin")
+    cfg2["default_env_prop"]["reward_prop"]["temp_penalty_mode"] = "common_L2"
+    flat2 = mdr_b200.FlatConfig(cfg2)
+    env2 = mdr_b200.VecDemandResponseEnv(cfg2, mdr_b200.synthetic_population(flat2, 4, seed=1), action_source="bangbang", with_obs=False)
+    env2.reset_tensor()
+    env2.enable_metrics()
+    with pytest.raises(mdr_b200.MdrError):
+        env2.run(3)
+
+
+def test_fused_full_size_day_slice_is_deterministic():
+    """c3 shape (10,000 clusters x 100 houses): 600 fused steps twice from the same state give identical bits."""
+    import torch
+    cfg = _cfg(100, "perlin")
+    _, _, a = _env(cfg, 10000, "fp32", "bangbang")
+    _, _, b = _env(cfg, 10000, "fp32", "bangbang")
+    a.run(600)
+    b.run(300)
+    b.run(300)
+    torch.cuda.synchronize()
+    assert torch.equal(a.temps, b.temps) and torch.equal(a.hvac, b.hvac) and torch.equal(a.env["signal"], b.env["signal"])
+    assert torch.isfinite(a.temps).all()

@@ -84,3 +84,50 @@ def test_two_rank_gloo_rollout_equals_single_process():
     for k in ("sum_reward", "sum_abs_temp_error", "sum_sq_signal_error", "mean_reward", "rmse_signal"):
         assert sharded[k] == pytest.approx(single[k], rel=1e-12), k
     assert sharded["max_abs_temp_error"] == single["max_abs_temp_error"]
+
+
+def _device_metrics_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = _fake_device_metrics()
+    lo, hi = sharding.shard_range(full.shape[0], rank, world)
+    red = sharding.reduce_device_metrics(full[lo:hi])
+    if rank == 0:
+        out.update(red)
+    dist.destroy_process_group()
+
+
+def _fake_device_metrics():
+    """Stand-in for VecDemandResponseEnv.metrics ([E, N_METRICS] fp64, layout MDR_M_* of include/mdr_b200.h)."""
+    from mdr_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    m = torch.rand(9, _lib.N_METRICS, dtype=torch.float64, generator=g)
+    m[:, 0] = 25.0
+    return m
+
+
+def test_device_metric_layout_matches_header():
+    from mdr_b200 import _lib
+    import re
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mdr_b200.h")).read()
+    names = re.findall(r"MDR_M_([A-Z_]+) = (\d+)", header)
+    assert [n.lower() for n, _ in names] == list(_lib.METRIC_NAMES)
+    assert [int(i) for _, i in names] == list(range(_lib.N_METRICS))
+    assert int(re.search(r"MDR_N_METRICS = (\d+)", header).group(1)) == _lib.N_METRICS
+
+
+def test_two_rank_gloo_device_metric_reduction():
+    from mdr_b200 import _lib
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_device_metrics_worker, args=(2, port, out), nprocs=2, join=True)
+        sharded = dict(out)
+    full = _fake_device_metrics()
+    single = sharding.reduce_device_metrics(full)
+    assert sharded["envs"] == single["envs"] == 9
+    for k in _lib.METRIC_NAMES:
+        assert sharded[k] == pytest.approx(single[k], rel=1e-12), k
+    assert sharded["max_temp_error"] == float(full[:, _lib.METRIC_NAMES.index("max_temp_error")].max())
