@@ -313,7 +313,8 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--cpu-steps", type=int, default=400)
+    ap.add_argument("--cpu-steps", type=int, default=4000,
+                    help="env steps per CPU-baseline process (default: ~3 s per core, ~45 core-seconds on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDR_ABI_VERSION 7
+#define MDR_ABI_VERSION 8
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
@@ -193,7 +193,26 @@ typedef struct MdrStepInputs {
   const int32_t *comm_table;  /* MDR_COMM_TABLE(_PER_ENV) neighbour ids */
   const void *interp_table;   /* real[prod(interp_dims)], C order (mergedGridSearchResultFinal.npy) */
   uint64_t step_index;        /* counter for the Philox streams */
+  const uint8_t *env_mask;    /* mdr_reset only: [E], nonzero = reset this env; NULL = all.  Needs out->obs == NULL
+                                 (follow with mdr_observe, which has no side effects) */
 } MdrStepInputs;
+
+/* Reset-time randomness of one population draw (mdr_populate): the parameters utils.applyPropertyNoise
+   (utils.py:573-709) reads from default_house_prop / noise_house_prop[noise_mode] / default_hvac_prop /
+   noise_hvac_prop[noise_mode] / default_env_prop, flattened. */
+typedef struct MdrPopulationSpec {
+  double init_air_temp, init_mass_temp, target_temp, deadband; /* default_house_prop, config.py:12-26 */
+  double ua, cm, ca, hm;
+  double std_start_temp, std_target_temp, factor_thermo_low, factor_thermo_high; /* noise_house_prop */
+  double cap_list[8];      /* noise_hvac_prop cooling_capacity_list[default capacity] (utils.py:669-676) */
+  int32_t n_cap;
+  int32_t lockout_duration, lockout_noise; /* default_hvac_prop, env/MA_DemandResponse.py:430 */
+  int32_t random_start;    /* start_datetime_mode == "random": + randrange(364) days + randrange(86400) s */
+  int64_t start_epoch;     /* naive seconds since 1970-01-01 of default_env_prop.start_datetime */
+  int32_t random_phase;    /* temp_parameters[temp_mode].random_phase_offset */
+  int32_t interp_update_period;
+  double artificial_ratio, artificial_ratio_range; /* power_grid_prop, :1116 */
+} MdrPopulationSpec;
 
 typedef struct MdrOutputs {
   void *obs;    /* real [E, N, F]: the normStateDict vector of every agent, or NULL to skip */
@@ -242,6 +261,15 @@ int mdr_observe(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *en
    configuration with metrics != NULL returns MDR_ERR_UNSUPPORTED. */
 int mdr_step(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
              const MdrStepInputs *in, const MdrOutputs *out, int32_t n_steps, void *stream);
+
+/* Device-side replacement of the host population builders: draws the raw house properties
+   (houses->ua..lockout_dur), the initial state (temps, hvac) and the per-env scalars (t_epoch, phase, od_temp,
+   artificial_ratio, max_power, perlin_seed; signal/base/cluster power zeroed) of every env selected by `env_mask`
+   ([E] bytes, NULL = all) from Philox streams keyed by (cfg->seed, draw_index, house or env).  Distribution-level
+   parity with utils.applyPropertyNoise / HVAC.__init__ / ClusterHouses.__init__ / PowerGrid.__init__; envs not
+   selected are not touched.  Follow with mdr_precompute and mdr_reset (same mask). */
+int mdr_populate(const MdrConfig *cfg, const MdrPopulationSpec *spec, const MdrHouses *houses, const MdrEnvs *envs,
+                 const uint8_t *env_mask, uint64_t draw_index, void *stream);
 
 /* Sets the device's persisting-L2 carve-out (cudaLimitPersistingL2CacheSize) to min(bytes, device maximum);
    bytes = 0 resets it and drops persisting lines.  Reports the granted carve-out and the largest access

@@ -11,8 +11,8 @@ from . import _lib, build, config_flatten, default_config, perlin, population  #
 from ._lib import MdrError, load as load_library  # noqa: F401
 from .config_flatten import FlatConfig, comm_table  # noqa: F401
 from .default_config import default_config as make_default_config  # noqa: F401
-from .population import (reference_order_population, shard_population, synthetic_interp_table,  # noqa: F401
-                         synthetic_population)
+from .population import (population_spec, reference_order_population, shard_population,  # noqa: F401
+                         synthetic_interp_table, synthetic_population)
 
 
 def __getattr__(name):

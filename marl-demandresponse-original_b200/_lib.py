@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-MDR_ABI_VERSION = 7
+MDR_ABI_VERSION = 8
 MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
@@ -56,7 +56,15 @@ class MdrEnvs(C.Structure):
 
 class MdrStepInputs(C.Structure):
     _fields_ = [(n, _vp) for n in ("actions", "od_noise", "signal_noise", "interp_ids", "msg_keep", "comm_table",
-                                   "interp_table")] + [("step_index", C.c_uint64)]
+                                   "interp_table")] + [("step_index", C.c_uint64), ("env_mask", _vp)]
+
+
+class MdrPopulationSpec(C.Structure):
+    _fields_ = ([(n, _f64) for n in ("init_air_temp", "init_mass_temp", "target_temp", "deadband", "ua", "cm", "ca", "hm",
+                                      "std_start_temp", "std_target_temp", "factor_thermo_low", "factor_thermo_high")]
+                + [("cap_list", _f64 * 8), ("n_cap", _i32), ("lockout_duration", _i32), ("lockout_noise", _i32),
+                   ("random_start", _i32), ("start_epoch", C.c_int64), ("random_phase", _i32),
+                   ("interp_update_period", _i32), ("artificial_ratio", _f64), ("artificial_ratio_range", _f64)])
 
 
 class MdrOutputs(C.Structure):
@@ -65,7 +73,7 @@ class MdrOutputs(C.Structure):
 
 EXPORTS = ("mdr_version", "mdr_strerror", "mdr_last_cuda_error", "mdr_obs_width", "mdr_validate",
            "mdr_launch_geometry", "mdr_precompute", "mdr_reset", "mdr_observe", "mdr_step", "mdr_step_host",
-           "mdr_l2_persist_limit")
+           "mdr_l2_persist_limit", "mdr_populate")
 
 _lib = None
 
@@ -108,6 +116,7 @@ def load(build_if_missing: bool = True):
     lib.mdr_step.argtypes = step_args + [_i32, _vp]
     lib.mdr_step_host.argtypes = step_args + [_vp, _vp, _vp, _vp, _vp, _vp]
     lib.mdr_l2_persist_limit.argtypes = [C.c_int, C.c_size_t, P(C.c_size_t), P(C.c_size_t)]
+    lib.mdr_populate.argtypes = [P(MdrConfig), P(MdrPopulationSpec), P(MdrHouses), P(MdrEnvs), _vp, C.c_uint64, _vp]
     if lib.mdr_version() != MDR_ABI_VERSION:
         raise MdrError("libmdr_b200.so ABI %d != binding ABI %d (rebuild)" % (lib.mdr_version(), MDR_ABI_VERSION))
     _lib = lib

@@ -245,6 +245,10 @@ static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, cons
   k.time_since_interp = e->time_since_interp; k.perlin_seed = e->perlin_seed;
   k.actions = in->actions; k.od_noise = in->od_noise; k.signal_noise = in->signal_noise;
   k.interp_ids = in->interp_ids; k.msg_keep = in->msg_keep; k.comm_table = in->comm_table;
+  if (in->env_mask) {
+    if (is_reset != 1 || out->obs) return MDR_ERR_UNSUPPORTED;  // masked reset only, observation via mdr_observe
+    k.env_mask = in->env_mask;
+  }
   k.interp_table = in->interp_table; k.step_index = in->step_index;
   k.obs = out->obs; k.reward = out->reward;
   k.is_reset = is_reset;
@@ -272,6 +276,34 @@ extern "C" int mdr_l2_persist_limit(int device, size_t bytes, size_t* granted_by
   if (granted_bytes) *granted_bytes = got;
   if (max_window_bytes) *max_window_bytes = (size_t)max_window;
   return MDR_OK;
+}
+
+extern "C" int mdr_populate(const MdrConfig* cfg, const MdrPopulationSpec* spec, const MdrHouses* h, const MdrEnvs* e,
+                            const uint8_t* env_mask, uint64_t draw_index, void* stream) {
+  int st = mdr_validate(cfg);
+  if (st != MDR_OK) return st;
+  if (!spec || !h || !e) return MDR_ERR_NULL;
+  if (!h->ua || !h->cm || !h->ca || !h->hm || !h->cap || !h->target || !h->deadband || !h->lockout_dur || !h->temps || !h->hvac)
+    return MDR_ERR_NULL;
+  if (!e->t_epoch || !e->phase || !e->od_temp || !e->artificial_ratio || !e->max_power || !e->base_power || !e->signal ||
+      !e->cluster_power)
+    return MDR_ERR_NULL;
+  if (spec->n_cap < 0 || spec->n_cap > 8 || spec->lockout_noise < 0 || spec->lockout_duration - spec->lockout_noise < 0)
+    return MDR_ERR_SHAPE;  // "Lockout duration must be positive", env/MA_DemandResponse.py:438-461
+  KernelParams k;
+  fill_config(k, cfg);
+  k.temps = h->temps; k.hvac = h->hvac;
+  k.t_epoch = e->t_epoch; k.phase = e->phase; k.od_temp = e->od_temp; k.solar_gain = e->solar_gain;
+  k.artificial_ratio = e->artificial_ratio; k.max_power = e->max_power; k.base_power = e->base_power;
+  k.signal = e->signal; k.cluster_power = e->cluster_power; k.time_since_interp = e->time_since_interp;
+  k.perlin_seed = e->perlin_seed;
+  cudaError_t err = cudaSetDevice(cfg->device);
+  if (err != cudaSuccess) return cuda_fail(err);
+  err = mdr::launch_populate(k, *spec, env_mask, const_cast<double*>(h->ua), const_cast<double*>(h->cm),
+                             const_cast<double*>(h->ca), const_cast<double*>(h->hm), const_cast<double*>(h->cap),
+                             const_cast<double*>(h->target), const_cast<double*>(h->deadband),
+                             const_cast<int32_t*>(h->lockout_dur), cfg->precision, draw_index, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? MDR_OK : cuda_fail(err);
 }
 
 extern "C" int mdr_precompute(const MdrConfig* cfg, const MdrHouses* houses, void* stream) {

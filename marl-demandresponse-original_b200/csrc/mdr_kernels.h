@@ -44,6 +44,7 @@ struct KernelParams {
   const double *od_noise, *signal_noise;
   const int32_t* interp_ids;
   const uint8_t* msg_keep;
+  const uint8_t* env_mask;  // mdr_reset of a subset of the envs (generic kernel only), or nullptr
   const int32_t* comm_table;
   const void* interp_table;
   void *obs, *reward;
@@ -76,6 +77,9 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
 int pipe_pro_batch(int envs_per_cta, bool has_obs);
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision);
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream);
+cudaError_t launch_populate(const KernelParams& kp, const MdrPopulationSpec& spec, const uint8_t* env_mask, double* ua, double* cm,
+                            double* ca, double* hm, double* cap, double* target, double* deadband, int32_t* lockout_dur,
+                            int precision, uint64_t draw_index, cudaStream_t stream);
 bool fused_eligible(const KernelParams& kp);
 cudaError_t launch_fused(const KernelParams& kp, const Geometry& g, int precision, int n_steps, cudaStream_t stream);
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);

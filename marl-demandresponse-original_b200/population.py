@@ -165,3 +165,35 @@ def synthetic_interp_table(seed: int = 0, size: int = 4199040):
     """Stand-in for monteCarlo/mergedGridSearchResultFinal.npy (a missing large blob of the
     reference): uniform [0, 6000) W over the full grid shape, flat C order."""
     return np.random.default_rng(seed).uniform(0, 6000, size)
+
+
+def population_spec(flat: FlatConfig):
+    """MdrPopulationSpec for the device-side population draw (mdr_populate): the same config entries
+    reference_order_population() reads, flattened for the kernel."""
+    from . import _lib
+    hd, vd = flat.house_def, flat.hvac_def
+    nh = flat.noise_house["noise_parameters"][flat.noise_house["noise_mode"]]
+    nv = flat.noise_hvac["noise_parameters"][flat.noise_hvac["noise_mode"]]
+    sp = _lib.MdrPopulationSpec()
+    sp.init_air_temp, sp.init_mass_temp = float(hd["init_air_temp"]), float(hd["init_mass_temp"])
+    sp.target_temp, sp.deadband = float(hd["target_temp"]), float(hd["deadband"])
+    sp.ua, sp.cm, sp.ca, sp.hm = float(hd["Ua"]), float(hd["Cm"]), float(hd["Ca"]), float(hd["Hm"])
+    sp.std_start_temp, sp.std_target_temp = float(nh["std_start_temp"]), float(nh["std_target_temp"])
+    sp.factor_thermo_low, sp.factor_thermo_high = float(nh["factor_thermo_low"]), float(nh["factor_thermo_high"])
+    caps = list(nv["cooling_capacity_list"][vd["cooling_capacity"]])
+    if not 1 <= len(caps) <= 8:
+        raise ValueError("cooling_capacity_list must have 1..8 entries for the device-side draw, got %d" % len(caps))
+    for i, c in enumerate(caps):
+        if c < 0:
+            raise ValueError("HVAC - Cooling capacity must be positive.")
+        sp.cap_list[i] = float(c)
+    sp.n_cap = len(caps)
+    sp.lockout_duration, sp.lockout_noise = int(vd["lockout_duration"]), int(vd["lockout_noise"])
+    if sp.lockout_duration - sp.lockout_noise < 0:
+        raise ValueError("HVAC - Lockout duration must be positive.")
+    sp.random_start = int(flat.start_datetime_mode == "random")
+    sp.start_epoch = epoch_seconds(flat.start_datetime)
+    sp.random_phase = int(bool(flat.random_phase_offset))
+    sp.interp_update_period = int(flat.interp_update_period)
+    sp.artificial_ratio, sp.artificial_ratio_range = float(flat.artificial_ratio), float(flat.artificial_signal_ratio_range)
+    return sp

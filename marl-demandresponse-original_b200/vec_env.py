@@ -253,6 +253,39 @@ class VecDemandResponseEnv:
             _lib.check(self.lib.mdr_reset(*self._refs, self._stream()), "mdr_reset")
         return self.obs
 
+    def reset_envs(self, mask=None, *, spec=None, draw_index=None):
+        """Device-side (re)draw of the population and reset: `mask` [E] bool/uint8 selects the envs to
+        reset (None = all); the others are not touched -- a rollout worker can restart finished episodes without a
+        host round trip.  The draw follows utils.applyPropertyNoise / HVAC.__init__ / ClusterHouses.__init__ /
+        PowerGrid.__init__ at the distribution level (Philox streams keyed by seed, draw_index, house/env).
+        Returns the observation tensor (all envs), like reset_tensor()."""
+        from .population import population_spec
+        if spec is None:
+            spec = population_spec(self.flat)
+        self._draws = getattr(self, "_draws", 0) + 1
+        di = self._draws if draw_index is None else int(draw_index)
+        m = None
+        if mask is not None:
+            m = (mask if isinstance(mask, torch.Tensor) else torch.as_tensor(np.asarray(mask)))
+            m = (m.to(self.device) != 0).to(torch.uint8).reshape(self.n_envs).contiguous()
+        mp = C.c_void_p(m.data_ptr()) if m is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mdr_populate(self._refs[0], C.byref(spec), self._refs[1], self._refs[2], mp, di, self._stream()),
+                       "mdr_populate")
+        self.precompute()  # derived coefficients of every house (idempotent for the envs that were not re-drawn)
+        self._set_inputs(None, None, None, None, None, None)
+        self.in_s.env_mask = mp
+        out_obs = self.out_s.obs
+        self.out_s.obs = None
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mdr_reset(*self._refs, self._stream()), "mdr_reset")
+        finally:
+            self.in_s.env_mask = None
+            self.out_s.obs = out_obs
+        self._keep.append(m)
+        return self.observe_tensor() if self.obs is not None else None
+
     def observe_tensor(self, *, msg_keep=None, comm=None):
         """Observation of the current state; nothing advances."""
         if not self._precomputed:
