@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MDR_ABI_VERSION 8
+#define MDR_ABI_VERSION 9
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
@@ -72,7 +72,8 @@ enum { MDR_SIG_FLAT = 0, MDR_SIG_SINUSOIDALS = 1, MDR_SIG_REGULAR_STEPS = 2, MDR
 enum {
   MDR_ACT_ARRAY = 0,    /* MdrStepInputs.actions (the reference's action_dict) */
   MDR_ACT_BANGBANG = 1, /* on-device restatement of agents/bangbang_controllers.py:41-61 (benchmark source) */
-  MDR_ACT_RANDOM = 2    /* Philox Bernoulli(1/2) per house (benchmark source) */
+  MDR_ACT_RANDOM = 2,   /* Philox Bernoulli(1/2) per house (benchmark source) */
+  MDR_ACT_GREEDY = 3    /* on-device restatement of agents/greedy_myopic_controller.py:29-49 (needs MdrHouses.cap) */
 };
 
 /* Flattened form of the reference's nested config dict (config.py), built once per env. */

@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-MDR_ABI_VERSION = 8
+MDR_ABI_VERSION = 9
 MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
@@ -14,7 +14,7 @@ MSG_THERMAL, MSG_HVAC = 1, 2
 PEN = {"individual_L2": 0, "common_L2": 1, "common_max": 2, "mixture": 3}
 BASE = {"constant": 0, "interpolation": 1}
 SIG_FLAT, SIG_SINUSOIDALS, SIG_REGULAR_STEPS, SIG_PERLIN = 0, 1, 2, 3
-ACT = {"array": 0, "bangbang": 1, "random": 2}
+ACT = {"array": 0, "bangbang": 1, "random": 2, "greedy": 3}
 METRIC_NAMES = ("steps", "sum_mean_reward", "sum_mean_temp_offset", "sum_mean_temp_error", "sum_sq_temp_error",
                 "sum_sq_max_temp_error", "max_temp_error", "sum_od_temp", "sum_signal", "sum_consumption",
                 "sum_signal_offset", "sum_signal_error", "sum_sq_signal_error")

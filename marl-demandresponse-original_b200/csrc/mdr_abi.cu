@@ -63,7 +63,7 @@ extern "C" int mdr_validate(const MdrConfig* c) {
   if (c->temp_penalty_mode < MDR_PEN_INDIVIDUAL_L2 || c->temp_penalty_mode > MDR_PEN_MIXTURE) return MDR_ERR_MODE;
   if (c->base_power_mode != MDR_BASE_CONSTANT && c->base_power_mode != MDR_BASE_INTERPOLATION) return MDR_ERR_MODE;
   if (c->signal_mode < MDR_SIG_FLAT || c->signal_mode > MDR_SIG_PERLIN) return MDR_ERR_MODE;
-  if (c->action_source < MDR_ACT_ARRAY || c->action_source > MDR_ACT_RANDOM) return MDR_ERR_MODE;
+  if (c->action_source < MDR_ACT_ARRAY || c->action_source > MDR_ACT_GREEDY) return MDR_ERR_MODE;
   if (c->n_sinusoids < 0 || c->n_sinusoids > MDR_MAX_SINUSOIDS) return MDR_ERR_SHAPE;
   if (c->n_features != mdr_obs_width(c)) return MDR_ERR_SHAPE;
   if (c->n_houses > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
@@ -100,7 +100,7 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   const int threads = house_threads + (extra ? 32 : 0);
   const int nwarps = house_warps;  // staging tiles exist for the house warps only
   const int part_stride = (N + 31) / 32 + 1;
-  const bool need_val = c->base_power_mode == MDR_BASE_INTERPOLATION;
+  const bool need_val = c->base_power_mode == MDR_BASE_INTERPOLATION || c->action_source == MDR_ACT_GREEDY;
   const bool need_pen = c->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2;
   int blocks_per_sm = 768 / threads;
   if (blocks_per_sm < 1) blocks_per_sm = 1;
@@ -212,6 +212,7 @@ static int fill_houses(KernelParams& k, const MdrConfig* c, const MdrHouses* h, 
     const bool need_raw = (c->state_flags & MDR_STATE_THERMAL) || (c->msg_flags & MDR_MSG_THERMAL);
     if (need_raw && (!h->ua || !h->cm || !h->ca || !h->hm)) return MDR_ERR_NULL;
     if ((c->msg_flags & MDR_MSG_HVAC) && !h->cap) return MDR_ERR_NULL;
+    if (c->action_source == MDR_ACT_GREEDY && !h->cap) return MDR_ERR_NULL;
   } else {
     if (!h->ua || !h->cm || !h->ca || !h->hm || !h->cap || !h->target || !h->deadband || !h->lockout_dur)
       return MDR_ERR_NULL;
@@ -349,7 +350,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   k.pro_warp = g.pro_warp;
   k.part_stride = g.part_stride;
   mdr::step_smem_layout(&k, cfg->precision, g.hmax, g.envs_per_cta, g.house_warps, g.rows_per_pass, cfg->n_features,
-                        cfg->base_power_mode == MDR_BASE_INTERPOLATION,
+                        cfg->base_power_mode == MDR_BASE_INTERPOLATION || cfg->action_source == MDR_ACT_GREEDY,
                         cfg->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2, out->obs != nullptr, cfg->n_comm, g.part_stride);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);

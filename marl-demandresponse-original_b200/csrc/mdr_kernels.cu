@@ -65,7 +65,7 @@ inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarp
   size_t o = 0;
   L.off_msg = o; o += align16((size_t)(hmax + genvs_max * n_comm) * 4 * real_bytes);
   L.off_pw = o;  o += align16((size_t)genvs_max * part_stride * sizeof(double));
-  L.off_val = o; o += need_val ? align16((size_t)hmax * sizeof(double)) : 0;
+  L.off_val = o; o += need_val ? align16((size_t)hmax * 3 * sizeof(double)) : 0;  // interpolation values / greedy sort scratch
   L.off_pen = o; o += need_pen ? align16((size_t)hmax * sizeof(double)) : 0;
   L.off_env = o; o += align16((size_t)genvs_max * sizeof(EnvScratch));
   L.off_stage = o;
@@ -491,6 +491,52 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   }
   if (p.solar) cta_sync();  // the thermal update needs this step's solar gain
 
+  // ---------------- on-device GreedyMyopic controller ----------------------
+  // agents/greedy_myopic_controller.py:29-49 on the state the previous step left (what its obs_dict shows):
+  // houses sorted by -(T_air - target) ascending (ties: lower id first), then ONE sequential pass per env that
+  // switches a house on if that keeps the total below the signal, or brings it closer and the house is not
+  // locked out (the reference's operator precedence: the lockout only guards the second clause).  fp64 like pandas.
+  int greedy_cmd = 0;
+  if (!kFast && !reset && p.action_source == MDR_ACT_GREEDY) {
+    double* g_key = s_val;                                        // [hmax] sort key, then P_on by rank
+    double* g_pow = s_val + p.hmax;                               // [hmax] P_on by rank
+    int* g_int = reinterpret_cast<int*>(s_val + 2 * p.hmax);      // [hmax] (house id << 1 | lockout) by rank, then commands
+    const int nth = p.house_warps * 32;
+    const double key = active ? -((double)tt.x - (double)cb.w) : 0.0;
+    if (active) g_key[tid] = key;
+    house_sync(nth);
+    int rank = 0;
+    if (active) {
+      const double* kk = g_key + le * N;
+      for (int j = 0; j < N; ++j) {
+        const double kj = kk[j];
+        rank += (kj < key || (kj == key && j < li)) ? 1 : 0;
+      }
+    }
+    house_sync(nth);
+    if (active) {
+      g_pow[le * N + rank] = p.cap[h] / p.hvac_cop;               // obs["hvac_cooling_capacity"] / obs["hvac_COP"]
+      g_int[le * N + rank] = (li << 1) | ((hv >> 1) & 1);
+    }
+    house_sync(nth);
+    if (active && li == 0) {
+      const double sig = p.signal[e];                             // obs["reg_signal"][0]
+      double total = 0.0;
+      int* gi = g_int + le * N;
+      const double* gp = g_pow + le * N;
+      for (int r = 0; r < N; ++r) {
+        const double pc = gp[r];
+        const int packed = gi[r];
+        const bool on_r = (pc + total < sig) || (fabs(pc + total - sig) < fabs(total - sig) && !(packed & 1));
+        if (on_r) total += pc;
+        gi[r] = (packed & ~1) | (on_r ? 1 : 0);
+      }
+    }
+    house_sync(nth);
+    if (active) greedy_cmd = g_int[le * N + rank] & 1;
+    house_sync(nth);  // s_val is reused by the interpolation refresh
+  }
+
   // ---------------- phase A: per house -------------------------------------------------
   const R target = cb.w, p_on = cb.z, deadband = cc.x, lockdur_r = cc.y;
   int on = hv & 1, lock = (hv >> 1) & 1, sso = hv >> 2;
@@ -502,6 +548,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
     if (!reset) {
       if (p.action_source == MDR_ACT_ARRAY) cmd = cmd != 0;
       else if (p.action_source == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
+      else if (p.action_source == MDR_ACT_GREEDY) cmd = greedy_cmd;
       else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
@@ -1590,7 +1637,8 @@ static cudaError_t launch_fused_t(const KernelParams& kp, const Geometry& g, siz
 
 // plain steps that need nothing from the host between them (see run_fused_kernel)
 bool fused_eligible(const KernelParams& kp) {
-  return kp.is_reset == 0 && kp.obs == nullptr && kp.action_source != MDR_ACT_ARRAY && kp.base_power_mode == MDR_BASE_CONSTANT &&
+  return kp.is_reset == 0 && kp.obs == nullptr && (kp.action_source == MDR_ACT_BANGBANG || kp.action_source == MDR_ACT_RANDOM) &&
+         kp.base_power_mode == MDR_BASE_CONSTANT &&
          kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.od_noise == nullptr && kp.signal_noise == nullptr &&
          (kp.signal_mode != MDR_SIG_PERLIN || kp.perlin_seed != nullptr);
 }
@@ -1762,7 +1810,7 @@ template <typename R>
 static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
   const bool fast = kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 && kp.msg_flags == 0 &&
                     kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
-                    !(kp.comm_defect_prob > 0.0);
+                    !(kp.comm_defect_prob > 0.0) && kp.action_source != MDR_ACT_GREEDY;
   if (fast && kp.C == 10) return launch_step_f<R, true, 10>(kp, g, stream);
   return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
@@ -1848,7 +1896,7 @@ bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision) {
   return precision == MDR_F32 && kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 &&
          kp.msg_flags == 0 && kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
          !(kp.comm_defect_prob > 0.0) && !kp.solar && g.pro_warp >= g.house_warps && g.threads <= 256 &&
-         g.rows_per_pass == 32 && g.pipe_smem_bytes > 0;
+         g.rows_per_pass == 32 && g.pipe_smem_bytes > 0 && kp.action_source != MDR_ACT_GREEDY;
 }
 
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream) {

@@ -540,3 +540,24 @@ class OracleEnv:
             self.grid_step(e, date_time, sig_noise[e], ids)
         obs = self.obs(msg_keep, comm)
         return obs, rewards, s["cluster_power"].copy(), s["signal"].copy()
+
+
+def greedy_myopic_actions(t_air, target, power, lockout, signal):
+    """TEST INFRASTRUCTURE -- agents/greedy_myopic_controller.py:29-49 restated for [E, N] arrays: houses sorted by
+    -(house_temp - house_target_temp) ascending (the reference's pandas quicksort leaves the order of exact ties
+    unspecified; here ties go by house id), then one sequential pass per cluster.  Note the reference's operator
+    precedence: `A or (B and not lockout)` -- the lockout only guards the second clause.  `power` = capacity / COP,
+    `signal` = obs["reg_signal"][0] per cluster.  Returns uint8 [E, N]."""
+    t_air, target, power = np.asarray(t_air, np.float64), np.asarray(target, np.float64), np.asarray(power, np.float64)
+    lockout, signal = np.asarray(lockout), np.asarray(signal, np.float64)
+    e, n = t_air.shape
+    out = np.zeros((e, n), np.uint8)
+    for i in range(e):
+        order = np.argsort(-(t_air[i] - target[i]), kind="stable")
+        total = 0.0
+        for k in order:
+            pc = power[i, k]
+            if (pc + total < signal[i]) or (abs(pc + total - signal[i]) < abs(total - signal[i]) and not lockout[i, k]):
+                total += pc
+                out[i, k] = 1
+    return out

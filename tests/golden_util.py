@@ -29,7 +29,7 @@ def synthetic_table():
 
 
 def names():
-    """trace fixtures (oracle/make_golden.py); mc_* files are table samples (oracle/make_mc_golden.py)"""
+    """trace fixtures (oracle/make_golden.py); mc_* files are not traces: table samples (oracle/make_mc_golden.py), controller decisions (oracle/make_greedy_golden.py)"""
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
                   if not os.path.basename(p).startswith("mc_"))
 

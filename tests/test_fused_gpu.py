@@ -154,3 +154,37 @@ def test_fused_full_size_day_slice_is_deterministic():
     torch.cuda.synchronize()
     assert torch.equal(a.temps, b.temps) and torch.equal(a.hvac, b.hvac) and torch.equal(a.env["signal"], b.env["signal"])
     assert torch.isfinite(a.temps).all()
+
+
+@pytest.mark.parametrize("n_envs,n,signal", [(6, 40, "sinusoidals"), (3, 300, "flat"), (2, 1000, "regular_steps")])
+def test_greedy_myopic_on_device_vs_oracle(n_envs, n, signal):
+    """MDR_ACT_GREEDY (agents/greedy_myopic_controller.py:29-49 on the device) in fp64 against the oracle stepped with
+    oracle.greedy_myopic_actions, which is pinned to the reference controller (tests/golden/mc_greedy_myopic.npz)."""
+    import torch
+    import mdr_b200
+    from oracle import mdr_oracle as orc
+    cfg = _cfg(n, signal, temp_std=0.0)
+    flat = mdr_b200.FlatConfig(cfg)
+    pop = mdr_b200.synthetic_population(flat, n_envs, seed=9)
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp64", seed=9, action_source="greedy", with_obs=True)
+    env.reset_tensor()
+    oracle = orc.OracleEnv(cfg, {kk: v for kk, v in pop.items() if kk != "perlin_seed"})
+    for e in range(n_envs):
+        oracle.grid_step(e, orc.to_datetime(oracle.s["t_epoch"][e]), 0.0)
+    zeros = np.zeros(n_envs)
+    power = oracle.s["cap"] / flat.hvac_cop
+    on_frac = []
+    for _ in range(60):
+        act = orc.greedy_myopic_actions(oracle.s["t_air"], oracle.s["target"], power, oracle.s["lockout"], oracle.s["signal"])
+        o_obs, o_rew, o_p, o_s = oracle.step(act, zeros, zeros)
+        obs, rew, p, s = env.step_tensor(None)
+        assert np.array_equal(env.hvac_on.cpu().numpy(), oracle.s["on"])
+        on_frac.append(float(act.mean()))
+    torch.cuda.synchronize()
+    assert 0.02 < np.mean(on_frac) < 0.98  # the controller actually switches things
+    assert np.array_equal(env.hvac_lockout.cpu().numpy(), oracle.s["lockout"])
+    assert np.array_equal(env.seconds_since_off.cpu().numpy(), oracle.s["sso"])
+    assert np.array_equal(p.cpu().numpy(), o_p)
+    np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(rew.cpu().numpy(), o_rew, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(obs.cpu().numpy(), o_obs, rtol=0, atol=1e-9)

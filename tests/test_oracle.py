@@ -3,6 +3,7 @@
 (2) golden traces recorded from the unmodified reference (tests/golden, oracle/make_golden.py),
 (3) scipy's interpn for the interpolation restatement."""
 import datetime as dt
+import os
 
 import numpy as np
 import pytest
@@ -222,3 +223,14 @@ def test_scalar_port_matches_reference_trace(name):
         if t in g.obs_steps:
             np.testing.assert_allclose(np.array([env.norm_state(obs[i]) for i in range(g.n)]), g.obs[oi], rtol=0, atol=1e-10)
             oi += 1
+
+
+def test_greedy_myopic_oracle_matches_reference_controller():
+    """oracle.greedy_myopic_actions vs decisions recorded from the unmodified agents/greedy_myopic_controller.py
+    (oracle/make_greedy_golden.py): 24 random clusters, incl. signal = 0 and signal above the cluster's maximum."""
+    g = np.load(os.path.join(gu.GOLDEN_DIR, "mc_greedy_myopic.npz"))
+    for k in range(int(g["n_cases"])):
+        c = {name: g["%d_%s" % (k, name)] for name in ("t_air", "target", "cap", "cop", "lockout", "signal", "action")}
+        act = orc.greedy_myopic_actions(c["t_air"][None], c["target"][None], (c["cap"] / c["cop"])[None], c["lockout"][None],
+                                        np.array([float(c["signal"])]))
+        assert np.array_equal(act[0], c["action"]), k
