@@ -1364,7 +1364,7 @@ struct FusedSmem {
 inline FusedSmem fused_smem_layout(int real_bytes, int genvs, int part_stride, bool metrics) {
   FusedSmem L;
   size_t o = 0;
-  L.off_rec = o;  o += align16((size_t)2 * genvs * 32 * sizeof(StepRec));
+  L.off_rec = o;  o += align16((size_t)2 * genvs * 32 * 4 * real_bytes);
   L.off_part = o; o += align16((size_t)2 * genvs * part_stride * real_bytes);
   L.off_pmax = o; o += metrics ? align16((size_t)2 * genvs * part_stride * real_bytes) : 0;
   L.off_red = o;  o += metrics ? align16((size_t)genvs * part_stride * 4 * sizeof(double)) : 0;
@@ -1383,20 +1383,30 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
   const int genvs = min(G, p.E - env0);
   const int K = p.n_fused;
   const int n_batches = (K + 31) >> 5;
-  StepRec* s_rec = reinterpret_cast<StepRec*>(smem_raw + p.off_env);  // [2][G][32]
+  T4* s_rec = reinterpret_cast<T4*>(smem_raw + p.off_env);  // [2][G][32] records (od_new, sig_new, gain, -) in the working precision
   const int dt = p.dt;
 
-  // lane = step of the batch; one env after the other
+  // lane = step of the batch; one env after the other.  The houses consume the records in the working precision
+  // (one 16-byte load per step); the fp64 values of the run's LAST step go straight to the per-env state.
   auto produce = [&](int b) {
     const int j = (b << 5) + lane;
     for (int le2 = 0; le2 < genvs; ++le2) {
       const int e2 = env0 + le2;
       const uint32_t t0 = (uint32_t)p.t_epoch[e2];
-      if (j < K) s_rec[((b & 1) * G + le2) * 32 + lane] = env_record(p, e2, t0 + (uint32_t)(j + 1) * (uint32_t)dt, p.step_index + (uint64_t)j);
+      if (j < K) {
+        const StepRec rec = env_record(p, e2, t0 + (uint32_t)(j + 1) * (uint32_t)dt, p.step_index + (uint64_t)j);
+        s_rec[((b & 1) * G + le2) * 32 + lane] = make4((R)rec.od_new, (R)rec.sig_new, (R)rec.gain, (R)0);
+        if (j == K - 1) {
+          p.od_temp[e2] = rec.od_new;
+          p.signal[e2] = rec.sig_new;
+          if (p.solar) p.solar_gain[e2] = rec.gain;
+        }
+      }
     }
   };
 
   if (warp == p.pro_warp) {  // always a dedicated warp here (launch_fused refuses geometries without one)
+    cta_sync();  // the house threads have read the initial od_temp / signal, which the last record overwrites
     for (int b = 0; b < n_batches; ++b) {
       produce(b);
       cta_sync();  // batch b ready; the house warps have finished batch b-1 (its buffer is free for b+1)
@@ -1422,8 +1432,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
   T4 ca4 = make4((R)0, (R)0, (R)0, (R)0), cb = ca4;
   T2 cc = make2((R)0, (R)1);
   int hv = 0;
-  R od_old = 0;
-  double s_old = 0.0;
+  R od_old = 0, s_old = 0;
   if (active) {
     tt = reinterpret_cast<const T2*>(p.temps)[h];
     hv = p.hvac[h];
@@ -1431,8 +1440,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
     cb = reinterpret_cast<const T4*>(p.coef_b)[h];
     cc = reinterpret_cast<const T2*>(p.coef_c)[h];
     od_old = (R)p.od_temp[e];
-    s_old = p.signal[e];
+    s_old = (R)p.signal[e];
   }
+  cta_sync();  // (see the record warp)
   const R target = cb.w, p_on = cb.z, deadband = cc.x;
   const int lockdur = (int)cc.y;
   int on = hv & 1, lock = (hv >> 1) & 1, sso = hv >> 2;
@@ -1445,18 +1455,28 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
   const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);  // (unconditionally: a full-mask shuffle must not sit behind &&)
   const bool head = active && (lane == 0 || prev_key != key);
   const unsigned seg_mask = __match_any_sync(0xffffffffu, key);
+  // cluster power as an integer redux.sync when every P_on of this CTA is an integral number of watts (the default
+  // capacity lists / COP): the same value as the fp32 shuffle tree (exact either way), a fraction of the instructions
+  const unsigned ip_on = (unsigned)p_on;
+  int all_int;
+  {
+    const int mine = !active || (sizeof(R) == 4 && p_on >= (R)0 && p_on < (R)4194304 && (R)ip_on == p_on);
+    asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.and.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
+                 : "=r"(all_int)
+                 : "r"(mine), "r"(p.house_threads)
+                 : "memory");
+  }
   R b_r = 0, b_off = 0, b_abs = 0, b_sq = 0;                                   // ... of the current 32-step batch
   R e_maxsq = 0, e_max = 0, e_od = 0, e_sig = 0, e_cons = 0, e_doff = 0, e_dabs = 0, e_dsq = 0;
-  double P = 0.0, last_gain = 0.0;
-  R reward = 0;
+  R P = 0, reward = 0;
 
   for (int b = 0; b < n_batches; ++b) {
     cta_sync();  // batch b ready
     const int steps = min(32, K - (b << 5));
-    const StepRec* recs = s_rec + ((b & 1) * G + le) * 32;
+    const T4* recs = s_rec + ((b & 1) * G + le) * 32;
     for (int s = 0; s < steps; ++s) {
       const int j = (b << 5) + s;
-      const StepRec rec = recs[s];
+      const T4 rec = recs[s];  // (od_new, sig_new, gain, -)
       R pw = 0, pen = 0, aerr = 0;
       if (active) {
         int cmd;
@@ -1473,7 +1493,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
         if (!lock && !new_on && sso + dt < lockdur) lock = 1;
         on = new_on;
         // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature and this step's solar gain
-        const R qa = (on ? cb.y : (R)0) + (p.solar ? (R)rec.gain : (R)0);
+        const R qa = (on ? cb.y : (R)0) + (p.solar ? rec.z : (R)0);
         const R tss = od_old + qa * cb.x;
         const R x = tt.x - tss, y = tt.y - tss;
         tt.x = tt.x + (ca4.x * x + ca4.y * y);
@@ -1486,7 +1506,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
       }
       R* part = s_part + (j & 1) * part_buf;
       {
-        const R psum = segmented_sum<R>(pw, key, lane);
+        R psum;
+        if (all_int) psum = (R)__reduce_add_sync(seg_mask, on ? ip_on : 0u);
+        else psum = segmented_sum<R>(pw, key, lane);
         if (head) part[my_part] = psum;
       }
       if (kMetrics) {
@@ -1511,13 +1533,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
         } else {
           for (int w = 0; w < nparts; ++w) Ps += part[part_row + w];
         }
-        P = (double)Ps;
+        P = Ps;
         R rew_r;
         if (sizeof(R) == 4) {
-          const float dn = (float)(P - s_old) * p.f_inv_n;
+          const float dn = ((float)Ps - (float)s_old) * p.f_inv_n;
           rew_r = -((float)pen * p.f_k_temp + dn * dn * p.f_k_sig);
         } else {
-          const double dn = (P - s_old) * p.inv_n;
+          const double dn = ((double)Ps - (double)s_old) * p.inv_n;
           rew_r = (R)(-((double)pen * p.k_temp + dn * dn * p.k_sig));
         }
         reward = rew_r;
@@ -1538,10 +1560,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
             } else {
               for (int w = 0; w < nparts; ++w) mx = fmax(mx, pmx[w]);
             }
-            const R sig = (R)rec.sig_new, d = sig - Ps;
+            const R sig = rec.y, d = sig - Ps;
             e_maxsq += mx * mx;
             e_max = fmax(e_max, mx);
-            e_od += (R)rec.od_new;
+            e_od += rec.x;
             e_sig += sig;
             e_cons += Ps;
             e_doff += d;
@@ -1550,13 +1572,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
           }
         }
       }
-      od_old = (R)rec.od_new;
-      s_old = rec.sig_new;
-      last_gain = rec.gain;
-      if (s == steps - 1 && b == n_batches - 1 && active && li == 0) {
-        p.od_temp[e] = rec.od_new;
-        p.signal[e] = rec.sig_new;
-      }
+      od_old = rec.x;
+      s_old = rec.y;
     }
     if (kMetrics) {
       acc_r += (double)b_r; acc_off += (double)b_off; acc_abs += (double)b_abs; acc_sq += (double)b_sq;
@@ -1575,10 +1592,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
     p.hvac[h] = (sso << 2) | (lock << 1) | on;
     if (p.reward != nullptr) reinterpret_cast<R*>(p.reward)[h] = reward;
     if (li == 0) {
-      p.cluster_power[e] = P;
+      p.cluster_power[e] = (double)P;
       p.t_epoch[e] = p.t_epoch[e] + (int64_t)K * dt;
       p.base_power[e] = p.avg_power_per_hvac * N;
-      if (p.solar) p.solar_gain[e] = last_gain;
     }
   }
   if (kMetrics) {
