@@ -1056,6 +1056,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
   const int ring_mask = 2 * p.pro_batch - 1;
   const int ring_shift = 31 - __clz(ring_mask + 1);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
   if (tid == 0) {
     for (int i = 0; i <= ring_mask; ++i) {
       mbar_init(&ctl.full[i], 1);
@@ -1065,6 +1066,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   }
   __syncthreads();
   if (warp >= p.house_warps) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
     const int B = p.pro_batch;
     for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
     return;
@@ -1124,6 +1126,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   int tile = blockIdx.x;
   int cmd_next = 0;
   int any_due = 0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
   if (tile < n_tiles) {
     issue_tile(tile, 0);
     cmd_next = fetch_action(tile);
@@ -1859,26 +1862,34 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   kp.n_tiles = g.ctas;
   int grid = sm_count[dev] * ctas_per_sm[dev];
   if (grid > g.ctas) grid = g.ctas;
-  if (g.l2_window_bytes == 0) {
-    step_pipe_kernel<kC, kAct, kObs><<<grid, g.threads, g.pipe_smem_bytes, stream>>>(kp);
-    return cudaGetLastError();
+  // Programmatic dependent launch: the CTAs of step t+1 may become resident (and set up their mbarriers and index
+  // arithmetic) while the last CTAs of step t are still draining; they block in griddepcontrol.wait before touching
+  // global memory, so the data dependency on the whole previous grid is unchanged.
+  cudaLaunchAttribute attrs[2];
+  int n_attrs = 0;
+  static const bool pdl = !(getenv("MDR_NO_PDL") && getenv("MDR_NO_PDL")[0] == '1');
+  if (pdl) {
+    attrs[n_attrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n_attrs].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attrs;
   }
-  // keep the per-house state/coefficients L2-resident across steps (they are re-read every step,
-  // the observation rows only stream through)
-  cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeAccessPolicyWindow;
-  attr.val.accessPolicyWindow.base_ptr = const_cast<void*>(g.l2_window_base);
-  attr.val.accessPolicyWindow.num_bytes = g.l2_window_bytes;
-  attr.val.accessPolicyWindow.hitRatio = g.l2_hit_ratio;
-  attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (g.l2_window_bytes != 0) {
+    // keep the per-house state/coefficients L2-resident across steps (opt-in)
+    cudaLaunchAttribute& attr = attrs[n_attrs++];
+    attr.id = cudaLaunchAttributeAccessPolicyWindow;
+    attr.val.accessPolicyWindow.base_ptr = const_cast<void*>(g.l2_window_base);
+    attr.val.accessPolicyWindow.num_bytes = g.l2_window_bytes;
+    attr.val.accessPolicyWindow.hitRatio = g.l2_hit_ratio;
+    attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  }
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(grid);
   lc.blockDim = dim3(g.threads);
   lc.dynamicSmemBytes = g.pipe_smem_bytes;
   lc.stream = stream;
-  lc.attrs = &attr;
-  lc.numAttrs = 1;
+  lc.attrs = attrs;
+  lc.numAttrs = n_attrs;
   return cudaLaunchKernelEx(&lc, step_pipe_kernel<kC, kAct, kObs>, kp);
 }
 
