@@ -295,7 +295,7 @@ def gpu_arm(args):
                     "steps": k_e2e, "api": "VecDemandResponseEnv.step_host -> mdr_step_host (pinned host buffers)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_house_step": algo,
-                         "kernel": geom["kernel"], "launch_us": launch_s * 1e6},
+                         "kernel": geom["kernel"], "launch_us": launch_s * 1e6 * fused, "fused_k": fused},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
