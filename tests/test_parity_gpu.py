@@ -213,3 +213,61 @@ def test_checkpoint_and_deepcopy():
     for other in outs[1:]:
         for x, y in zip(outs[0], other):
             assert (x == y).all()
+
+
+@pytest.mark.parametrize("n_envs,n,interp,signal,nb_comm", [
+    (9, 50, False, "perlin", 10),          # c2 shape, 4 envs per tile, ragged last tile
+    (7, 100, True, "perlin", 10),          # c4 shape: deferred interpolation refresh, all houses sampled
+    (5, 160, True, "sinusoidals", 10),     # N > interp_nb_agents: replayed sample ids in the deferred refresh
+    (11, 30, True, "regular_steps", 4),    # generic message count (kC = 0 instantiation)
+    (40, 7, False, "flat", 10),            # neighbour count clipped to N - 1, many envs per tile
+    (3, 224, False, "perlin", 10),         # largest cluster the pipelined kernel takes
+])
+def test_pipelined_kernel_matches_oracle(n_envs, n, interp, signal, nb_comm):
+    """The persistent pipelined fp32 kernel (no message drops, default flags -> `pipelined` geometry) against the
+    oracle, including steps on which the interpolation refresh is due (deferred post-pass), and against the generic
+    kernel on the same inputs (MDR_NO_PIPELINE=1): integer state bit-exact, reals within the fp32 tolerance."""
+    import os
+    import mdr_b200
+    steps = 160 if interp else 30
+    cfg, flat, pop, d = _random_case(n_envs, n, 300 + n, interp, False, steps, "individual_L2", signal)
+    cfg["default_env_prop"]["cluster_prop"]["nb_agents_comm"] = nb_comm
+    flat = mdr_b200.FlatConfig(cfg)
+    table = gu.synthetic_table() if interp else None
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
+    twin = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
+    assert env.launch_geometry()["kernel"].startswith("mdr::step_pipe_kernel")
+    oracle = orc.OracleEnv(cfg, {k: v for k, v in pop.items() if k != "perlin_seed"},
+                           interp=orc.PowerInterp(table, gu.INTERP_GRID, gu.INTERP_KEYS) if interp else None)
+    for e in range(n_envs):
+        oracle.grid_step(e, orc.to_datetime(oracle.s["t_epoch"][e]), d["sig_noise"][0, e], d["ids"][0, e])
+    env.reset_tensor(signal_noise=d["sig_noise"][0], interp_ids=d["ids"][0])
+    twin.reset_tensor(signal_noise=d["sig_noise"][0], interp_ids=d["ids"][0])
+    tol, tolw = TOL["fp32"], TOL_W["fp32"]
+    refreshes = 0
+    for t in range(steps):
+        base_before = oracle.s["base_power"].copy()
+        o_obs, o_rew, o_p, o_s = oracle.step(d["actions"][t], d["od_noise"][t], d["sig_noise"][t], d["ids"][t])
+        refreshes += int((oracle.s["base_power"] != base_before).any())
+        kw = dict(od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t], interp_ids=d["ids"][t])
+        obs, rew, p, s = env.step_tensor(d["actions"][t], **kw)
+        os.environ["MDR_NO_PIPELINE"] = "1"
+        try:
+            g_obs, g_rew, g_p, g_s = twin.step_tensor(d["actions"][t], **kw)
+        finally:
+            os.environ.pop("MDR_NO_PIPELINE", None)
+        assert np.array_equal(env.hvac.cpu().numpy(), twin.hvac.cpu().numpy()), t
+        assert np.array_equal(env.hvac_on.cpu().numpy(), oracle.s["on"]), t
+        assert np.array_equal(env.hvac_lockout.cpu().numpy(), oracle.s["lockout"]), t
+        assert np.array_equal(env.seconds_since_off.cpu().numpy(), oracle.s["sso"]), t
+        assert np.array_equal(p.cpu().numpy(), o_p) and np.array_equal(g_p.cpu().numpy(), o_p), t
+        assert np.array_equal(env.time_since_interp.cpu().numpy(), twin.time_since_interp.cpu().numpy()), t
+        np.testing.assert_allclose(s.cpu().numpy(), o_s, err_msg="signal %d" % t, **tolw)
+        np.testing.assert_allclose(s.cpu().numpy(), g_s.cpu().numpy(), err_msg="signal vs generic %d" % t, **tolw)
+        np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], err_msg="t_air %d" % t, **tol)
+        np.testing.assert_allclose(rew.cpu().numpy(), o_rew, err_msg="reward %d" % t, **tol)
+        np.testing.assert_allclose(obs.cpu().numpy(), o_obs, err_msg="obs %d" % t, **tol)
+        np.testing.assert_allclose(obs.cpu().numpy(), g_obs.cpu().numpy(), err_msg="obs vs generic %d" % t, **tol)
+    assert np.array_equal(env.t_epoch.cpu().numpy(), oracle.s["t_epoch"])
+    if interp:
+        assert refreshes >= 2  # the deferred refresh pass ran at least twice
