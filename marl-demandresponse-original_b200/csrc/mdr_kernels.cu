@@ -1,16 +1,22 @@
-// Fused MADemandResponseEnv step for B200 (sm_100a): one CTA owns G whole envs (clusters),
-// one thread owns one house.  Replaces the Python object loops of
+// MADemandResponseEnv step path for B200 (sm_100a): one CTA owns G whole envs (clusters), one thread owns
+// one house.  Replaces the Python object loops of
 //   ClusterHouses.step        env/MA_DemandResponse.py:1005-1055
 //   HVAC.step                 env/MA_DemandResponse.py:463-492
 //   SingleHouse.update_temperature  :664-738
 //   compute_rewards           :330-373
 //   PowerGrid.step            :1236-1316 (+ interpolatePower :1195-1234)
 //   make_cluster_obs_dict + normStateDict  :904-1003, utils.py:740-880
-// Phases inside the single launch (block barriers between them):
-//   A  per house : load packed state/coefficients (8/16-byte coalesced), lockout state machine,
-//                  2x2 affine ETP update, store state, stage message + power in shared memory
-//   B  per env   : one warp reduces the env's power (shuffle tree), lane 0 advances the clock,
-//                  draws/replays the outdoor temperature, evaluates the grid signal
+// This file: shared device code (interpolation, grid signal, per-env prologue), the reset-time precompute
+// kernel, the generic step kernel (every mode, fp32/fp64, reset/observe, one tile per CTA) and the launchers.
+//   mdr_pipe.cuh      persistent software-pipelined fp32 kernel of the default configuration (the hot kernel)
+//   mdr_fused.cuh     K steps per launch with the house state in registers + metric accumulators (deploy loop)
+//   mdr_populate.cuh  device-side population draw / masked partial reset
+// Phases of the generic kernel (block barriers between them):
+//   0  per env   : a dedicated warp advances the clock, draws/replays the outdoor temperature and noise,
+//                  evaluates the grid signal (concurrently with phase A)
+//   A  per house : load packed state/coefficients (8/16-byte coalesced), [greedy controller], lockout state
+//                  machine, 2x2 affine ETP update, store state, stage message + power in shared memory
+//   B  per env   : cluster power from warp partials; mean/max penalties for the common_* reward modes
 //   C/D (refresh steps only) per house multilinear table interpolation -> per env base power
 //   E  per house : reward, observation row assembled in a per-warp shared-memory tile from the
 //                  neighbours' staged messages, tile written with one bulk (TMA) store
@@ -831,964 +837,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   if (issued && lane == 0) bulk_wait_read_all();
 }
 
-// ----------------------------------------------------------------------------------------
-// Persistent, software-pipelined variant of the fast path (fp32, default observation layout,
-// solar gain off, plain steps).  The CTAs stay resident (SMs x CTAs/SM of them) and loop over
-// tiles of G envs:
-//   * the house threads' inputs of tile i+1 are fetched with cp.async into a second shared-memory
-//     stage while tile i is computed (each thread copies and later reads only its own record, so
-//     cp.async.wait_group is the only synchronisation the inputs need);
-//   * the dedicated prologue warp runs `pro_batch` tiles per pass and up to 2*pro_batch tiles ahead,
-//     handing a 64-byte PipeEnv record per env over through an mbarrier ring, and writes the
-//     per-env outputs (clock, outdoor temperature, signal) itself;
-//   * the bulk (TMA) observation store of tile i drains while tile i+1 is loaded and updated.
-// Barrier 1 = house warps only (message window + power partial sums); everything that is constant
-// over the tile loop (shared-memory addresses, neighbour window, partial-sum slots) is computed
-// once per thread before the loop.
-// ----------------------------------------------------------------------------------------
-// Trace build (-DMDR_TRACE): lane 0 of every warp of CTA MDR_TRACE_CTA stamps globaltimer at fixed
-// points of its first MDR_TRACE_TILES tiles; tools/trace_tile.py reads the buffer back.
-#ifdef MDR_TRACE
-#ifndef MDR_TRACE_CTA
-#define MDR_TRACE_CTA 200
-#endif
-#define MDR_TRACE_TILES 24
-#define MDR_TRACE_POINTS 10
-__device__ unsigned long long g_trace[8 * MDR_TRACE_TILES * MDR_TRACE_POINTS];
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define MDR_STAMP_AT(w, t, k)                                                                        \
-  do {                                                                                                \
-    if (blockIdx.x == MDR_TRACE_CTA && (threadIdx.x & 31) == 0 && (t) < MDR_TRACE_TILES)              \
-      g_trace[((w) * MDR_TRACE_TILES + (t)) * MDR_TRACE_POINTS + (k)] = global_ns();                  \
-  } while (0)
-#define MDR_STAMP(k) MDR_STAMP_AT(warp, it, k)
-}  // namespace mdr
-// trace builds only (tools/trace_tile.py): copies the globaltimer stamps of the traced CTA to the host
-extern "C" int mdr_debug_trace(unsigned long long* host, size_t n, int clear) {
-  if (cudaDeviceSynchronize() != cudaSuccess) return -5;
-  if (cudaMemcpyFromSymbol(host, mdr::g_trace, n * sizeof(unsigned long long)) != cudaSuccess) return -5;
-  if (clear) {
-    void* ptr = nullptr;
-    cudaGetSymbolAddress(&ptr, mdr::g_trace);
-    cudaMemset(ptr, 0, n * sizeof(unsigned long long));
-  }
-  return 0;
-}
-namespace mdr {
-#else
-#define MDR_STAMP_AT(w, t, k) do { } while (0)
-#define MDR_STAMP(k) do { } while (0)
-#endif
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async_16(void* s, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void* s, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(s)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(void* s, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
-
-// mbarrier hand-over between the prologue warp (producer of PipeEnv records) and the house warps
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-// shared-memory control block of the pipelined kernel (at off_ctl).  The PipeEnv ring has
-// ring = 2 * pro_batch <= kMaxRing slots; slot = it % ring for the it-th tile of this CTA.
-constexpr int kMaxRing = 16;
-struct PipeCtl {
-  uint64_t full[kMaxRing];   // prologue -> house warps: slot is ready            (count 1)
-  uint64_t empty[kMaxRing];  // house warps -> prologue: slot may be overwritten   (count house_warps)
-  int tile_due[kMaxRing];    // any env of the tile has an interpolation refresh due
-};
-
-// The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
-// groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  The deeper the
-// batch, the further the prologue's dependent fp64 / Philox / global-load chains are from the
-// house warps' critical path.
-// One pass: tiles it0 .. it0+B-1 of this CTA (B a power of two <= pro_batch).
-__device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  PipeEnv* s_env = reinterpret_cast<PipeEnv*>(smem_raw + p.off_env);
-  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
-  const int ring = 2 * p.pro_batch;
-  const int ring_shift = 31 - __clz(ring);
-  const int lane = threadIdx.x & 31;
-  const int lanes_per_tile = 32 / B;
-  int L = 16;  // lanes cooperating on one env (2 * nb_octaves + 1 = 11 Philox draws per env)
-  while (L > 1 && L * p.G > lanes_per_tile) L >>= 1;
-  const int groups = lanes_per_tile / L;  // envs of a tile processed at once (>= 1: G * pro_batch <= 32)
-  const int tlane = lane & (lanes_per_tile - 1);
-  const int sub = tlane & (L - 1), grp = tlane / L;
-  const int my_k = lane / lanes_per_tile;  // which tile of the pass this lane works for
-  const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
-  const int it = it0 + my_k;
-  const int tile = blockIdx.x + it * gridDim.x;
-  const bool tile_valid = tile < p.n_tiles;
-  const int slot = it & (ring - 1);
-  MDR_STAMP_AT(7, it0, 8);
-  // the house warps must have released the pass's ring slots.  Warp-uniform loop over the B barriers:
-  // per-lane-group waits on different mbarriers (a divergent try_wait spin) were measured to return
-  // up to 8 us late (tools/trace_tile.py)
-  for (int k = 0; k < B; ++k) {
-    const int itk = it0 + k;
-    if (blockIdx.x + itk * gridDim.x < p.n_tiles && (itk >> ring_shift) >= 1)
-      mbar_wait(&ctl.empty[itk & (ring - 1)], (((itk >> ring_shift) & 1) ^ 1));
-  }
-  MDR_STAMP_AT(7, it0, 0);
-  const int tile_c = tile_valid ? tile : blockIdx.x;  // lanes of an absent tile compute but never write
-  const int env0 = tile_c * p.G;
-  const int genvs = min(p.G, p.E - env0);
-  PipeEnv* buf = s_env + slot * p.G;
-  EnvScratch unused;
-  int my_due = 0;
-  for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count (G, not genvs)
-    const int le2 = first + grp;
-    const bool valid = tile_valid && le2 < genvs;
-    const int lec = le2 < genvs ? le2 : genvs - 1;
-    my_due |= env_prologue<true>(p, unused, buf[lec], env0 + lec, sub, L, valid, false, false);
-  }
-  const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
-  if (tile_valid && tlane == 0) ctl.tile_due[slot] = (due_ballot & group_mask) != 0;
-  __syncwarp();
-  if (tile_valid && tlane == 0) mbar_arrive(&ctl.full[slot]);
-  MDR_STAMP_AT(7, it0, 7);
-}
-
-// Deferred interpolation refresh (every interp_update_period seconds; PowerGrid.step :1250-1255,
-// interpolatePower :1195-1234).  It runs on 1 step in 75, needs fp64 and a 32-corner table walk per
-// house, and would cost the tile loop registers if it sat inside it.  So the tile loop treats a due
-// env like any other (the prologue parks its perlin value and marks it), and this pass -- after the
-// loop, same launch, same CTA, same tile order -- evaluates the table on the houses' NEW state,
-// re-evaluates the signal and patches observation feature 9 (the only output that depends on it).
-__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
-  float* s_fsig = reinterpret_cast<float*>(smem_raw + p.off_pw);  // [G], the power partials are dead by now
-  const int tid = threadIdx.x;
-  const int N = p.N, G = p.G, GN = G * N;
-  const int nb = p.interp_nb_agents;
-  const int nsamp = N <= nb ? N : nb;
-  const int T = p.hmax;
-  // the bulk stores of this warp's rows must have landed before feature 9 is patched
-  if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  __syncwarp();
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const int H = min(GN, (p.E - tile * G) * N);
-    const bool active = tid < H;
-    const int e = tile * G + le;
-    const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
-    const bool due = active && p.time_since_interp[e] < 0;
-    int any;
-    asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.or.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
-                 : "=r"(any)
-                 : "r"((int)due), "r"(T)
-                 : "memory");
-    if (!any) continue;
-    double od_new = 0.0;
-    if (due) od_new = p.od_temp[e];
-    if (due && li < nsamp) {
-      int src = li;
-      if (N > nb) {
-        if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
-        else {
-          const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
-                                     STREAM_IDS + 16 * (uint32_t)li, p.seed);
-          src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
-        }
-      }
-      const size_t hs = (size_t)e * N + src;
-      const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
-      const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-      s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, 0.0, 0.0);
-    }
-    house_sync(T);
-    if (due && li == 0) {
-      double base = 0.0;
-      for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);  // id order, :1218-1232
-      if (N > nb) base = mul_rn(base, (double)N / (double)nb);
-      const Calendar cal = calendar_time((uint32_t)p.t_epoch[e]);
-      const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
-      const double sig_noise = p.base_power[e];  // parked by the prologue
-      const double sig = grid_signal(p, base, time_sec, sig_noise, p.artificial_ratio[e], p.max_power[e]);
-      p.base_power[e] = base;
-      p.time_since_interp[e] = 0;
-      p.signal[e] = sig;
-      s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
-    }
-    house_sync(T);
-    if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
-    house_sync(T);  // s_val / s_fsig are reused by the next due tile
-  }
-}
-
-template <int kC, int kAct, bool kObs>
-__global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
-  const int ring_mask = 2 * p.pro_batch - 1;
-  const int ring_shift = 31 - __clz(ring_mask + 1);
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
-  if (tid == 0) {
-    for (int i = 0; i <= ring_mask; ++i) {
-      mbar_init(&ctl.full[i], 1);
-      mbar_init(&ctl.empty[i], p.house_warps);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp >= p.house_warps) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
-    const int B = p.pro_batch;
-    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
-    return;
-  }
-
-  // ---------------- per-thread constants of the tile loop ------------------------------------
-  const int N = p.N, G = p.G;
-  const int C = kC > 0 ? kC : p.C;
-  const int half = C >> 1;
-  const int ns = N + C;
-  const int GN = G * N;                 // houses of a full tile
-  const int T = p.hmax;                 // house threads of the CTA (multiple of 32)
-  const int le = tid < GN ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
-  const int li = tid - le * N;
-  // own slot in message window 0 ([half halo | N houses | halo] per env); window 1 follows
-  float4* const msg0 = reinterpret_cast<float4*>(smem_raw + p.off_msg) + (le * ns + half + li);
-  const int msg_buf = G * ns;
-  const bool halo_hi = li < C - half;   // my message is also the wrap-around halo after the last house
-  const bool halo_lo = li >= N - half;  // ... and before the first one
-  // warp-partial power sums: [2][G][part_stride]
-  float* const part0 = reinterpret_cast<float*>(smem_raw + p.off_pw) + le * p.part_stride;
-  const int part_buf = G * p.part_stride;
-  const int first_warp = (le * N) >> 5;
-  const int my_part = warp - first_warp;
-  const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
-  float* const row = reinterpret_cast<float*>(smem_raw + p.off_stage) + tid * p.F;  // rows contiguous like in HBM
-  PipeEnv* const s_env = reinterpret_cast<PipeEnv*>(smem_raw + p.off_env);
-  // cp.async input stage s (in_stride bytes each): [coef_a T x 16][coef_b T x 16][temps T x 8][coef_c T x 8][hvac T x 4]
-  unsigned char* const in_a = smem_raw + p.off_in + tid * 16;
-  unsigned char* const in_t = smem_raw + p.off_in + T * 32 + tid * 8;
-  unsigned char* const in_h = smem_raw + p.off_in + T * 48 + tid * 4;
-  const int in_stride = p.in_stride;
-  const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
-  const int n_tiles = p.n_tiles;
-  const int tile_stride = gridDim.x;
-  const float inv_norm = p.f_inv_norm_reg_sig;
-
-  auto tile_houses = [&](int tile) { return min(GN, (p.E - tile * G) * N); };
-  auto issue_tile = [&](int tile, int s) {
-    if (tid < tile_houses(tile)) {
-      const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
-      const int so = s * in_stride;
-      cp_async_16(in_a + so, reinterpret_cast<const float4*>(p.coef_a) + h);
-      cp_async_16(in_a + so + T * 16, reinterpret_cast<const float4*>(p.coef_b) + h);
-      cp_async_8(in_t + so, reinterpret_cast<const float2*>(p.temps) + h);
-      cp_async_8(in_t + so + T * 8, reinterpret_cast<const float2*>(p.coef_c) + h);
-      cp_async_4(in_h + so, p.hvac + h);
-    }
-  };
-  // the action byte of the next tile travels in a register (kept as loaded: converting here would
-  // stall on the load instead of letting it fly)
-  auto fetch_action = [&](int tile) -> int {
-    if (kAct == MDR_ACT_ARRAY && tid < tile_houses(tile)) return p.actions[(unsigned)tile * (unsigned)GN + (unsigned)tid];
-    return 0;
-  };
-
-  int tile = blockIdx.x;
-  int cmd_next = 0;
-  int any_due = 0;
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
-  if (tile < n_tiles) {
-    issue_tile(tile, 0);
-    cmd_next = fetch_action(tile);
-  }
-  cp_async_commit();
-
-  for (int it = 0; tile < n_tiles; ++it, tile += tile_stride) {
-    const int sbuf = it & 1;
-    const int H = tile_houses(tile);
-    const bool active = tid < H;
-    const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
-    const int e = tile * G + le;
-    MDR_STAMP(0);
-    int cmd = cmd_next;
-    const int next = tile + tile_stride;
-    if (next < n_tiles) {
-      issue_tile(next, sbuf ^ 1);
-      cmd_next = fetch_action(next);
-    }
-    cp_async_commit();
-    // hand-over from the prologue warp (normally produced more than a tile ago).  Waiting here rather than
-    // at the end of the tile (with the house threads prefetching od_temp themselves) measured the same.
-    const int slot = it & ring_mask;
-    const PipeEnv* const env_buf = s_env + slot * G;
-    mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);
-    const float od_old = env_buf[le].od_old;
-    MDR_STAMP(1);
-    cp_async_wait<1>();  // this thread's copies of the current tile have landed
-    MDR_STAMP(2);
-
-    // ---------------- phase A: per house ---------------------------------------------------
-    float t_air = 0, t_mass = 0, target = 0, p_on = 0, deadband = 0, inv_lock = 1, pen = 0, pw = 0;
-    int on = 0, lock = 0, sso = 0;
-    float4* const msg = msg0 + sbuf * msg_buf;
-    if (active) {
-      const int so = sbuf * in_stride;
-      const float4 ca4 = *reinterpret_cast<const float4*>(in_a + so);
-      const float4 cb = *reinterpret_cast<const float4*>(in_a + so + T * 16);
-      const float2 tt = *reinterpret_cast<const float2*>(in_t + so);
-      const float2 cc = *reinterpret_cast<const float2*>(in_t + so + T * 8);
-      const int hv = *reinterpret_cast<const int*>(in_h + so);
-      target = cb.w; p_on = cb.z; deadband = cc.x;
-      inv_lock = __fdividef(1.0f, cc.y);
-      on = hv & 1; sso = hv >> 2;
-      if (kAct == MDR_ACT_ARRAY) cmd = cmd != 0;
-      else if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
-      else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
-      // HVAC.step, :475-492
-      const int dt = p.dt;
-      const int lockdur = (int)cc.y;
-      if (!on) sso += dt;
-      lock = !(on || sso >= lockdur);
-      const int new_on = lock ? 0 : cmd;
-      if (!lock && new_on) sso = 0;
-      if (!lock && !new_on && sso + dt < lockdur) lock = 1;
-      on = new_on;
-      // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature
-      const float qa = on ? cb.y : 0.0f;
-      const float tss = od_old + qa * cb.x;
-      const float x = tt.x - tss, y = tt.y - tss;
-      t_air = tt.x + (ca4.x * x + ca4.y * y);
-      t_mass = tt.y + (ca4.z * x + ca4.w * y);
-      reinterpret_cast<float2*>(p.temps)[h] = make_float2(t_air, t_mass);
-      p.hvac[h] = (sso << 2) | (lock << 1) | on;
-      pw = on ? p_on : 0.0f;
-      // SingleHouse.message :624-662 normalised as utils.py:842-868 (sso is scaled by the receiver)
-      const float4 m = make_float4((t_air - target) * 0.2f, (float)sso, pw * inv_norm, p_on * inv_norm);
-      msg[0] = m;
-      if (halo_hi) msg[N] = m;
-      if (halo_lo) msg[-N] = m;
-      // utils.deadbandL2, utils.py:1266-1274
-      const float hi = target + deadband * 0.5f, lo = target - deadband * 0.5f;
-      if (hi < t_air) pen = (t_air - hi) * (t_air - hi);
-      else if (lo > t_air) pen = (lo - t_air) * (lo - t_air);
-    }
-    float* const part = part0 + sbuf * part_buf;
-    {
-      const int key = active ? le : -1;
-      // fp32 partial sums are exact here: integer-valued watts, at most 224 houses (< 2^24 W)
-      const float psum = segmented_sum<float>(pw, key, lane);
-      const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-      if (active && (lane == 0 || prev_key != key)) part[my_part] = psum;
-    }
-    MDR_STAMP(3);
-    // the staging rows of this warp may still be read by the previous tile's bulk store (waited for
-    // BEFORE the barrier: the two waits then overlap; after it they add up -- measured +5% on c4)
-    if (kObs && it > 0) {
-      if (lane == 0) bulk_wait_read_all();
-      __syncwarp();
-    }
-    MDR_STAMP(4);
-    // the only CTA-wide rendezvous of a tile: message window + power partials are complete.
-    // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
-    house_sync(T);
-    MDR_STAMP(5);
-
-    float P = 0;
-    if (active) {
-      // an env of <= 224 houses spans at most 8 warps; same summation order as a counted loop
-#pragma unroll
-      for (int w = 0; w < 8; ++w)
-        if (w < nparts) P += part[w];
-      if (li == 0) p.cluster_power[e] = (double)P;
-    }
-    if (kObs && active) {
-      // fast-path row: [T_air, T_mass, target, deadband, cap, on, lockout, sso, 1, signal, power | C x 4 messages]
-      row[0] = (t_air - 20.0f) * 0.2f;
-      row[1] = (t_mass - 20.0f) * 0.2f;
-      row[2] = (target - 20.0f) * 0.2f;
-      row[3] = deadband;
-      row[4] = p_on * p.f_cop_over_def_cap;
-      row[5] = (float)on;
-      row[6] = (float)lock;
-      row[7] = (float)sso * inv_lock;
-      row[8] = 1.0f;
-      row[10] = P * p.f_inv_norm_sig_agents;
-      // neighbours (:816-828) = the C window entries around this house, skipping itself
-      const float4* win = msg - half;
-      float* mrow = row + 11;
-#pragma unroll
-      for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
-        const float4 m = win[k + (k >= half ? 1 : 0)];
-        mrow[4 * k + 0] = m.x;
-        mrow[4 * k + 1] = m.y * inv_lock;
-        mrow[4 * k + 2] = m.z;
-        mrow[4 * k + 3] = m.w;
-      }
-    }
-    MDR_STAMP(6);
-    any_due |= ctl.tile_due[slot];
-    if (active) {
-      // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
-      const float dn = (float)((double)P - env_buf[le].s_old) * p.f_inv_n;
-      if (p.reward != nullptr) reinterpret_cast<float*>(p.reward)[h] = -(pen * p.f_k_temp + dn * dn * p.f_k_sig);
-      if (kObs) row[9] = env_buf[le].f_sig;
-    }
-    if (kObs) {
-      const int wrow0 = warp * 32;
-      const int nrows_w = min(32, H - wrow0);
-      if (nrows_w > 0) {
-        const int F = p.F;
-        float* dst = reinterpret_cast<float*>(p.obs) + (size_t)((unsigned)tile * (unsigned)GN + (unsigned)wrow0) * F;
-        const float* src = reinterpret_cast<const float*>(smem_raw + p.off_stage) + wrow0 * F;
-        const uint32_t bytes = (uint32_t)(nrows_w * F * sizeof(float));
-        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
-        if (bulk_ok) {
-          // measured alternatives (tools/microbench): a coalesced st.global.v4 copy loop is ~4% slower,
-          // an L2 evict_first hint on this store changes nothing
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) bulk_store_s2g(dst, src, bytes);
-        } else {
-          __syncwarp();
-          for (int i = lane; i < nrows_w * F; i += 32) dst[i] = src[i];
-          __syncwarp();
-        }
-      }
-    }
-    // this warp is done with ring slot `slot`: let the prologue warp reuse it for tile it+ring
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&ctl.empty[slot]);
-    MDR_STAMP(7);
-  }
-  cp_async_wait<0>();
-  if (kObs && lane == 0) bulk_wait_read_all();
-  if (interp_mode && any_due) pipe_refresh_pass(p, le, li);  // CTA-uniform: every house thread read the same flags
-}
-
-// ----------------------------------------------------------------------------------------
-// Fused multi-step kernel (the "deploy" loop, main-deploy.py:102-209): K consecutive env steps in ONE
-// launch for configurations whose per-step inputs are all produced on the device (on-device action
-// source, Philox noise, constant base power, no observation consumer).  A CTA owns G whole envs for
-// the entire run: house state and coefficients stay in registers, nothing but the final state, the
-// last reward and the per-env metric accumulators ever goes back to HBM.
-//   * the per-env part of a step (clock, outdoor temperature, noise, grid signal) does not depend on
-//     the houses here, so one warp computes it for 32 STEPS AT ONCE -- lane = step, every Philox draw
-//     is counter-based on (env, step) -- into a double-buffered record ring, one batch ahead;
-//   * the house warps then run 32 steps per batch with one house-warp barrier per step (cluster power
-//     and, with metrics, the per-step max temperature error cross the warps through shared memory);
-//   * metrics (main-deploy.py:124-209, metrics.py:22-47) that are sums over houses AND steps are kept
-//     per thread in fp64 and reduced once at the end; only the per-step max needs the per-step exchange.
-// Same arithmetic and the same Philox counters as K launches of the per-step kernels.
-// ----------------------------------------------------------------------------------------
-struct StepRec { double od_new, sig_new, gain; };
-
-// one (env, step) record; mirrors env_prologue for base_power_mode == constant and on-device draws
-__device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32_t t, uint64_t step_index) {
-  Calendar cal = calendar_time(t);
-  if (p.solar) calendar_date(cal);
-  const bool perlin = p.signal_mode == MDR_SIG_PERLIN;
-  double sig_noise = 0.0;
-  if (perlin) {  // utils.Perlin.calculate_noise (utils.py:1247-1253) with Philox lattice gradients
-    const int nb = p.perlin_nb_octaves;
-    const double x = (double)cal.sod * p.inv_perlin_period;
-    const uint64_t pkey = p.seed ^ (uint64_t)__double_as_longlong(p.perlin_seed[e2]);
-    // same association as the 16-lane butterfly of env_prologue is not reproducible with one lane; the
-    // terms are summed in draw order (difference ~1 ulp of a value that is replayed in parity tests)
-    for (int d = 0; d < 2 * nb; ++d) {
-      const int j = d >> 1, corner = d & 1;
-      const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
-      const double fl = floor(xo);
-      const uint4 r = philox4x32((uint32_t)((int)fl + corner), 0u, (uint32_t)j, STREAM_PERLIN, pkey);
-      const double dist = xo - (fl + corner);
-      const float fd = 1.0f - fabsf((float)dist);
-      const float fade = fd * fd * fd * (fd * (fd * 6.0f - 15.0f) + 10.0f);
-      const float g = 2.0f * (((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f)) - 1.0f;
-      const float wgt = j == nb - 1 ? 1.0f / (float)((1 << nb) - 1) : 1.0f / (float)(1 << j);
-      sig_noise += (double)(fade * g * wgt) * dist;
-    }
-  }
-  const double od_noise =
-      p.temp_std * normal_from(philox4x32((uint32_t)e2, (uint32_t)step_index, (uint32_t)(step_index >> 32), STREAM_OD, p.seed));
-  // ClusterHouses.compute_OD_temp, :1070-1081
-  const double time_day = cal.hour + cal.minute * (1.0 / 60.0);
-  StepRec rec;
-  rec.od_new = p.od_amplitude * sin(p.two_pi_over_24 * (time_day + (-6 + p.phase[e2]))) + p.od_bias;
-  rec.od_new += od_noise;
-  rec.gain = p.solar ? solar_gain(cal, p.window_area, p.shading_coeff) : 0.0;
-  const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
-  rec.sig_new = grid_signal(p, p.avg_power_per_hvac * p.N, time_sec, sig_noise, p.artificial_ratio[e2], p.max_power[e2]);
-  return rec;
-}
-
-template <typename R>
-__device__ __forceinline__ R segmented_max(R v, int key, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const R tv = __shfl_down_sync(0xffffffffu, v, o);
-    const int tk = __shfl_down_sync(0xffffffffu, key, o);
-    if (lane + o < 32 && tk == key) v = fmax(v, tv);
-  }
-  return v;
-}
-
-struct FusedSmem {
-  size_t off_rec, off_part, off_pmax, off_red, total;
-};
-inline FusedSmem fused_smem_layout(int real_bytes, int genvs, int part_stride, bool metrics) {
-  FusedSmem L;
-  size_t o = 0;
-  L.off_rec = o;  o += align16((size_t)2 * genvs * 32 * 4 * real_bytes);
-  L.off_part = o; o += align16((size_t)2 * genvs * part_stride * real_bytes);
-  L.off_pmax = o; o += metrics ? align16((size_t)2 * genvs * part_stride * real_bytes) : 0;
-  L.off_red = o;  o += metrics ? align16((size_t)genvs * part_stride * 4 * sizeof(double)) : 0;
-  L.total = o;
-  return L;
-}
-
-template <typename R, int kMaxThreads, int kAct, bool kMetrics>
-__global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_fused_kernel(const __grid_constant__ KernelParams p) {
-  using T2 = typename Vec<R>::T2;
-  using T4 = typename Vec<R>::T4;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = p.N, G = p.G;
-  const int env0 = blockIdx.x * G;
-  const int genvs = min(G, p.E - env0);
-  const int K = p.n_fused;
-  const int n_batches = (K + 31) >> 5;
-  T4* s_rec = reinterpret_cast<T4*>(smem_raw + p.off_env);  // [2][G][32] records (od_new, sig_new, gain, -) in the working precision
-  const int dt = p.dt;
-
-  // lane = step of the batch; one env after the other.  The houses consume the records in the working precision
-  // (one 16-byte load per step); the fp64 values of the run's LAST step go straight to the per-env state.
-  auto produce = [&](int b) {
-    const int j = (b << 5) + lane;
-    for (int le2 = 0; le2 < genvs; ++le2) {
-      const int e2 = env0 + le2;
-      const uint32_t t0 = (uint32_t)p.t_epoch[e2];
-      if (j < K) {
-        const StepRec rec = env_record(p, e2, t0 + (uint32_t)(j + 1) * (uint32_t)dt, p.step_index + (uint64_t)j);
-        s_rec[((b & 1) * G + le2) * 32 + lane] = make4((R)rec.od_new, (R)rec.sig_new, (R)rec.gain, (R)0);
-        if (j == K - 1) {
-          p.od_temp[e2] = rec.od_new;
-          p.signal[e2] = rec.sig_new;
-          if (p.solar) p.solar_gain[e2] = rec.gain;
-        }
-      }
-    }
-  };
-
-  if (warp == p.pro_warp) {  // always a dedicated warp here (launch_fused refuses geometries without one)
-    cta_sync();  // the house threads have read the initial od_temp / signal, which the last record overwrites
-    for (int b = 0; b < n_batches; ++b) {
-      produce(b);
-      cta_sync();  // batch b ready; the house warps have finished batch b-1 (its buffer is free for b+1)
-    }
-    return;
-  }
-
-  const int H = genvs * N;
-  const bool active = tid < H;
-  const int le = active ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;
-  const int li = tid - le * N;
-  const int e = env0 + le;
-  const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
-  R* s_part = reinterpret_cast<R*>(smem_raw + p.off_pw);    // [2][G][part_stride]
-  R* s_pmax = reinterpret_cast<R*>(smem_raw + p.off_pen);   // [2][G][part_stride] (metrics only)
-  const int first_warp = (le * N) >> 5;
-  const int my_part = le * p.part_stride + (warp - first_warp);
-  const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
-  const int part_buf = G * p.part_stride;
-  const int part_row = le * p.part_stride;
-
-  T2 tt = make2((R)0, (R)0);
-  T4 ca4 = make4((R)0, (R)0, (R)0, (R)0), cb = ca4;
-  T2 cc = make2((R)0, (R)1);
-  int hv = 0;
-  R od_old = 0, s_old = 0;
-  if (active) {
-    tt = reinterpret_cast<const T2*>(p.temps)[h];
-    hv = p.hvac[h];
-    ca4 = reinterpret_cast<const T4*>(p.coef_a)[h];
-    cb = reinterpret_cast<const T4*>(p.coef_b)[h];
-    cc = reinterpret_cast<const T2*>(p.coef_c)[h];
-    od_old = (R)p.od_temp[e];
-    s_old = (R)p.signal[e];
-  }
-  cta_sync();  // (see the record warp)
-  const R target = cb.w, p_on = cb.z, deadband = cc.x;
-  const int lockdur = (int)cc.y;
-  int on = hv & 1, lock = (hv >> 1) & 1, sso = hv >> 2;
-  const R hi = target + deadband / 2, lo = target - deadband / 2;
-  double acc_r = 0.0, acc_off = 0.0, acc_abs = 0.0, acc_sq = 0.0;              // per house, over the steps
-  double m_maxsq = 0.0, m_max = 0.0, m_od = 0.0, m_sig = 0.0, m_cons = 0.0;   // per env (first house thread)
-  double m_doff = 0.0, m_dabs = 0.0, m_dsq = 0.0;
-  // lanes of this warp that belong to the same env (loop invariant)
-  const int key = active ? le : -1;
-  const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);  // (unconditionally: a full-mask shuffle must not sit behind &&)
-  const bool head = active && (lane == 0 || prev_key != key);
-  const unsigned seg_mask = __match_any_sync(0xffffffffu, key);
-  // cluster power as an integer redux.sync when every P_on of this CTA is an integral number of watts (the default
-  // capacity lists / COP): the same value as the fp32 shuffle tree (exact either way), a fraction of the instructions
-  const unsigned ip_on = (unsigned)p_on;
-  int all_int;
-  {
-    const int mine = !active || (sizeof(R) == 4 && p_on >= (R)0 && p_on < (R)4194304 && (R)ip_on == p_on);
-    asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.and.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
-                 : "=r"(all_int)
-                 : "r"(mine), "r"(p.house_threads)
-                 : "memory");
-  }
-  R b_r = 0, b_off = 0, b_abs = 0, b_sq = 0;                                   // ... of the current 32-step batch
-  R e_maxsq = 0, e_max = 0, e_od = 0, e_sig = 0, e_cons = 0, e_doff = 0, e_dabs = 0, e_dsq = 0;
-  R P = 0, reward = 0;
-
-  for (int b = 0; b < n_batches; ++b) {
-    cta_sync();  // batch b ready
-    const int steps = min(32, K - (b << 5));
-    const T4* recs = s_rec + ((b & 1) * G + le) * 32;
-    for (int s = 0; s < steps; ++s) {
-      const int j = (b << 5) + s;
-      const T4 rec = recs[s];  // (od_new, sig_new, gain, -)
-      R pw = 0, pen = 0, aerr = 0;
-      if (active) {
-        int cmd;
-        if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
-        else {
-          const uint64_t si = p.step_index + (uint64_t)j;
-          cmd = philox4x32(h, (uint32_t)si, (uint32_t)(si >> 32), STREAM_ACT, p.seed).x & 1;
-        }
-        // HVAC.step, :475-492
-        if (!on) sso += dt;
-        lock = !(on || sso >= lockdur);
-        const int new_on = lock ? 0 : cmd;
-        if (!lock && new_on) sso = 0;
-        if (!lock && !new_on && sso + dt < lockdur) lock = 1;
-        on = new_on;
-        // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature and this step's solar gain
-        const R qa = (on ? cb.y : (R)0) + (p.solar ? rec.z : (R)0);
-        const R tss = od_old + qa * cb.x;
-        const R x = tt.x - tss, y = tt.y - tss;
-        tt.x = tt.x + (ca4.x * x + ca4.y * y);
-        tt.y = tt.y + (ca4.z * x + ca4.w * y);
-        pw = on ? p_on : (R)0;
-        // utils.deadbandL2, utils.py:1266-1274
-        if (hi < tt.x) pen = (tt.x - hi) * (tt.x - hi);
-        else if (lo > tt.x) pen = (lo - tt.x) * (lo - tt.x);
-        aerr = fabs(tt.x - target);
-      }
-      R* part = s_part + (j & 1) * part_buf;
-      {
-        R psum;
-        if (all_int) psum = (R)__reduce_add_sync(seg_mask, on ? ip_on : 0u);
-        else psum = segmented_sum<R>(pw, key, lane);
-        if (head) part[my_part] = psum;
-      }
-      if (kMetrics) {
-        R pm;
-        if (sizeof(R) == 4) {
-          // |err| >= 0: its bit pattern orders like an unsigned integer, so one redux.sync over the env's lanes does it
-          pm = (R)__uint_as_float(__reduce_max_sync(seg_mask, __float_as_uint((float)aerr)));
-        } else {
-          pm = segmented_max<R>(aerr, key, lane);
-        }
-        if (head) s_pmax[(j & 1) * part_buf + my_part] = pm;
-      }
-      house_sync(p.house_threads);  // partials are double buffered by step parity: one rendezvous per step
-      if (active) {
-        // fp32 mode keeps the per-step arithmetic of the pipelined kernel (fp32 power sums are exact: integer-valued
-        // watts), fp64 mode that of the generic kernel; reg_signal_penalty :244-247 with the OLD signal, weighting :364-372
-        R Ps = 0;
-        if (nparts <= 8) {
-#pragma unroll
-          for (int w = 0; w < 8; ++w)
-            if (w < nparts) Ps += part[part_row + w];
-        } else {
-          for (int w = 0; w < nparts; ++w) Ps += part[part_row + w];
-        }
-        P = Ps;
-        R rew_r;
-        if (sizeof(R) == 4) {
-          const float dn = ((float)Ps - (float)s_old) * p.f_inv_n;
-          rew_r = -((float)pen * p.f_k_temp + dn * dn * p.f_k_sig);
-        } else {
-          const double dn = ((double)Ps - (double)s_old) * p.inv_n;
-          rew_r = (R)(-((double)pen * p.k_temp + dn * dn * p.k_sig));
-        }
-        reward = rew_r;
-        if (kMetrics) {
-          // batch-local accumulators in the working precision, flushed into fp64 every 32 steps
-          const R err = tt.x - target;
-          b_r += rew_r;
-          b_off += err;
-          b_abs += aerr;
-          b_sq += err * err;
-          if (li == 0) {
-            R mx = 0;
-            const R* pmx = s_pmax + (j & 1) * part_buf + part_row;
-            if (nparts <= 8) {
-#pragma unroll
-              for (int w = 0; w < 8; ++w)
-                if (w < nparts) mx = fmax(mx, pmx[w]);
-            } else {
-              for (int w = 0; w < nparts; ++w) mx = fmax(mx, pmx[w]);
-            }
-            const R sig = rec.y, d = sig - Ps;
-            e_maxsq += mx * mx;
-            e_max = fmax(e_max, mx);
-            e_od += rec.x;
-            e_sig += sig;
-            e_cons += Ps;
-            e_doff += d;
-            e_dabs += fabs(d);
-            e_dsq += d * d;
-          }
-        }
-      }
-      od_old = rec.x;
-      s_old = rec.y;
-    }
-    if (kMetrics) {
-      acc_r += (double)b_r; acc_off += (double)b_off; acc_abs += (double)b_abs; acc_sq += (double)b_sq;
-      b_r = b_off = b_abs = b_sq = 0;
-      if (li == 0) {
-        m_maxsq += (double)e_maxsq; m_max = fmax(m_max, (double)e_max); m_od += (double)e_od; m_sig += (double)e_sig;
-        m_cons += (double)e_cons; m_doff += (double)e_doff; m_dabs += (double)e_dabs; m_dsq += (double)e_dsq;
-        e_maxsq = e_od = e_sig = e_cons = e_doff = e_dabs = e_dsq = 0;
-      }
-    }
-  }
-
-  // ---------------- write-back ---------------------------------------------------------------
-  if (active) {
-    reinterpret_cast<T2*>(p.temps)[h] = tt;
-    p.hvac[h] = (sso << 2) | (lock << 1) | on;
-    if (p.reward != nullptr) reinterpret_cast<R*>(p.reward)[h] = reward;
-    if (li == 0) {
-      p.cluster_power[e] = (double)P;
-      p.t_epoch[e] = p.t_epoch[e] + (int64_t)K * dt;
-      p.base_power[e] = p.avg_power_per_hvac * N;
-    }
-  }
-  if (kMetrics) {
-    // per-env totals of the per-house accumulators: warp-segmented sums, then the env's first thread adds the
-    // warp partials in warp order (deterministic)
-    double* s_red = reinterpret_cast<double*>(smem_raw + p.off_val);  // [G][part_stride][4]
-    const double v0 = segmented_sum<double>(acc_r, key, lane), v1 = segmented_sum<double>(acc_off, key, lane);
-    const double v2 = segmented_sum<double>(acc_abs, key, lane), v3 = segmented_sum<double>(acc_sq, key, lane);
-    if (head) {
-      double* d = s_red + (size_t)my_part * 4;
-      d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3;
-    }
-    house_sync(p.house_threads);
-    if (active && li == 0) {
-      double t[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int w = 0; w < nparts; ++w)
-        for (int k = 0; k < 4; ++k) t[k] += s_red[(size_t)(le * p.part_stride + w) * 4 + k];
-      double* m = p.metrics + (size_t)e * MDR_N_METRICS;
-      m[MDR_M_STEPS] += (double)K;
-      m[MDR_M_SUM_MEAN_REWARD] += t[0] * p.inv_n;
-      m[MDR_M_SUM_MEAN_TEMP_OFFSET] += t[1] * p.inv_n;
-      m[MDR_M_SUM_MEAN_TEMP_ERROR] += t[2] * p.inv_n;
-      m[MDR_M_SUM_SQ_TEMP_ERROR] += t[3];
-      m[MDR_M_SUM_SQ_MAX_TEMP_ERROR] += m_maxsq;
-      m[MDR_M_MAX_TEMP_ERROR] = fmax(m[MDR_M_MAX_TEMP_ERROR], m_max);
-      m[MDR_M_SUM_OD_TEMP] += m_od;
-      m[MDR_M_SUM_SIGNAL] += m_sig;
-      m[MDR_M_SUM_CONSUMPTION] += m_cons;
-      m[MDR_M_SUM_SIGNAL_OFFSET] += m_doff;
-      m[MDR_M_SUM_SIGNAL_ERROR] += m_dabs;
-      m[MDR_M_SUM_SQ_SIGNAL_ERROR] += m_dsq;
-    }
-  }
-}
-
-template <typename R, int kMaxThreads, int kAct>
-static cudaError_t launch_fused_m(const KernelParams& kp, const Geometry& g, size_t smem, cudaStream_t stream) {
-  if (kp.metrics != nullptr) {
-    cudaError_t err = cudaFuncSetAttribute(run_fused_kernel<R, kMaxThreads, kAct, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    run_fused_kernel<R, kMaxThreads, kAct, true><<<g.ctas, g.threads, smem, stream>>>(kp);
-  } else {
-    cudaError_t err = cudaFuncSetAttribute(run_fused_kernel<R, kMaxThreads, kAct, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    run_fused_kernel<R, kMaxThreads, kAct, false><<<g.ctas, g.threads, smem, stream>>>(kp);
-  }
-  return cudaGetLastError();
-}
-
-template <typename R, int kAct>
-static cudaError_t launch_fused_t(const KernelParams& kp, const Geometry& g, size_t smem, cudaStream_t stream) {
-  if (g.threads <= 256) return launch_fused_m<R, 256, kAct>(kp, g, smem, stream);
-  if (g.threads <= 512) return launch_fused_m<R, 512, kAct>(kp, g, smem, stream);
-  return launch_fused_m<R, 1024, kAct>(kp, g, smem, stream);
-}
-
-// plain steps that need nothing from the host between them (see run_fused_kernel)
-bool fused_eligible(const KernelParams& kp) {
-  return kp.is_reset == 0 && kp.obs == nullptr && (kp.action_source == MDR_ACT_BANGBANG || kp.action_source == MDR_ACT_RANDOM) &&
-         kp.base_power_mode == MDR_BASE_CONSTANT &&
-         kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.od_noise == nullptr && kp.signal_noise == nullptr &&
-         (kp.signal_mode != MDR_SIG_PERLIN || kp.perlin_seed != nullptr);
-}
-
-cudaError_t launch_fused(const KernelParams& kp_in, const Geometry& g, int precision, int n_steps, cudaStream_t stream) {
-  if (g.pro_warp < g.house_warps) return cudaErrorInvalidConfiguration;  // needs the dedicated record warp (N <= 992)
-  KernelParams kp = kp_in;
-  kp.n_fused = n_steps;
-  const int rb = precision;
-  const FusedSmem L = fused_smem_layout(rb, g.envs_per_cta, g.part_stride, kp.metrics != nullptr);
-  kp.off_env = (int)L.off_rec; kp.off_pw = (int)L.off_part; kp.off_pen = (int)L.off_pmax; kp.off_val = (int)L.off_red;
-  if (precision == MDR_F32)
-    return kp.action_source == MDR_ACT_BANGBANG ? launch_fused_t<float, MDR_ACT_BANGBANG>(kp, g, L.total, stream)
-                                                 : launch_fused_t<float, MDR_ACT_RANDOM>(kp, g, L.total, stream);
-  return kp.action_source == MDR_ACT_BANGBANG ? launch_fused_t<double, MDR_ACT_BANGBANG>(kp, g, L.total, stream)
-                                               : launch_fused_t<double, MDR_ACT_RANDOM>(kp, g, L.total, stream);
-}
-
-// ----------------------------------------------------------------------------------------
-// Device-side population draw: the reset-time randomness of
-// utils.applyPropertyNoise (utils.py:573-709), HVAC.__init__ (:430-434), ClusterHouses.__init__
-// (:789-793) and PowerGrid.__init__ (:1116, :1182-1184) from counter-based Philox streams keyed by
-// (house or env, draw_index) -- distribution-level (not bit-level) parity with python's `random`.
-// One CTA per env; an optional env mask re-draws only some envs (partial reset) and leaves every
-// byte of the others untouched.
-// ----------------------------------------------------------------------------------------
-enum : uint32_t { STREAM_POP_HOUSE = 6, STREAM_POP_ENV = 7 };
-
-__device__ __forceinline__ double gauss01(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {  // Box-Muller, fp64
-  const double u1 = u01(a, b), u2 = u01(c, d);
-  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-}
-// random.triangular(low, high, mode) as CPython implements it
-__device__ __forceinline__ double triangular(double u, double low, double high, double mode) {
-  if (high == low) return low;
-  double c = (mode - low) / (high - low);
-  if (u > c) {
-    u = 1.0 - u;
-    c = 1.0 - c;
-    const double t = low; low = high; high = t;
-  }
-  return low + (high - low) * sqrt(u * c);
-}
-
-__global__ void __launch_bounds__(128) populate_kernel(const __grid_constant__ KernelParams p, const MdrPopulationSpec s,
-                                                       const uint8_t* __restrict__ env_mask, double* raw_ua, double* raw_cm,
-                                                       double* raw_ca, double* raw_hm, double* raw_cap, double* raw_target,
-                                                       double* raw_deadband, int32_t* lockout_dur, uint64_t draw_index) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* s_cap = reinterpret_cast<double*>(smem_raw);  // [N] for the id-ordered max_power sum (:796-802)
-  const int e = blockIdx.x;
-  if (env_mask != nullptr && env_mask[e] == 0) return;
-  const int N = p.N;
-  const uint32_t d_lo = (uint32_t)draw_index, d_hi = (uint32_t)(draw_index >> 32);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const unsigned h = (unsigned)e * (unsigned)N + (unsigned)i;
-    const uint4 r0 = philox4x32(h, d_lo, d_hi, STREAM_POP_HOUSE, p.seed);
-    const uint4 r1 = philox4x32(h, d_lo, d_hi, STREAM_POP_HOUSE + 16, p.seed);
-    const uint4 r2 = philox4x32(h, d_lo, d_hi, STREAM_POP_HOUSE + 32, p.seed);
-    const uint4 r3 = philox4x32(h, d_lo, d_hi, STREAM_POP_HOUSE + 48, p.seed);
-    const uint4 r4 = philox4x32(h, d_lo, d_hi, STREAM_POP_HOUSE + 64, p.seed);
-    // apply_house_noise, utils.py:623-666
-    const double t_air = s.init_air_temp + fabs(s.std_start_temp * gauss01(r0.x, r0.y, r0.z, r0.w));
-    const double t_mass = s.init_mass_temp + fabs(s.std_start_temp * gauss01(r1.x, r1.y, r1.z, r1.w));
-    const double target = s.target_temp + fabs(s.std_target_temp * gauss01(r2.x, r2.y, r2.z, r2.w));
-    const double lo = s.factor_thermo_low, hi = s.factor_thermo_high;
-    raw_ua[h] = s.ua * triangular(u01(r3.x, r3.y), lo, hi, 1.0);
-    raw_cm[h] = s.cm * triangular(u01(r3.z, r3.w), lo, hi, 1.0);
-    raw_ca[h] = s.ca * triangular(u01(r4.x, r4.y), lo, hi, 1.0);
-    const uint4 r5 = philox4x32(h, d_lo, d_hi, STREAM_POP_HOUSE + 80, p.seed);
-    raw_hm[h] = s.hm * triangular(u01(r4.z, r4.w), lo, hi, 1.0);
-    raw_target[h] = target;
-    raw_deadband[h] = s.deadband;
-    // apply_hvac_noise (random.choices of the capacity list), utils.py:669-676
-    const int ncap = s.n_cap > 0 ? s.n_cap : 1;
-    const double cap = s.cap_list[min(ncap - 1, (int)(u01(r5.x, r5.y) * ncap))];
-    raw_cap[h] = cap;
-    s_cap[i] = cap;
-    // HVAC.__init__ lockout noise: randint(-noise, +noise), :430-434
-    const int span = 2 * s.lockout_noise + 1;
-    const int dur = s.lockout_duration - s.lockout_noise + min(span - 1, (int)(u01(r5.z, r5.w) * span));
-    lockout_dur[h] = dur;
-    if (p.temps != nullptr) {
-      if (p.off_in == MDR_F32) reinterpret_cast<float2*>(p.temps)[h] = make_float2((float)t_air, (float)t_mass);
-      else reinterpret_cast<double2*>(p.temps)[h] = make_double2(t_air, t_mass);
-    }
-    p.hvac[h] = dur << 2;  // off, not locked out, seconds_since_off = lockout duration (:433)
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint4 q0 = philox4x32((uint32_t)e, d_lo, d_hi, STREAM_POP_ENV, p.seed);
-    const uint4 q1 = philox4x32((uint32_t)e, d_lo, d_hi, STREAM_POP_ENV + 16, p.seed);
-    const uint4 q2 = philox4x32((uint32_t)e, d_lo, d_hi, STREAM_POP_ENV + 32, p.seed);
-    // get_random_date_time, utils.py:701-709
-    int64_t t = s.start_epoch;
-    if (s.random_start) {
-      const int days = min(363, (int)(((uint64_t)q0.x * 364ull) >> 32));
-      const int secs = min(86399, (int)(((uint64_t)q0.y * 86400ull) >> 32));
-      t += (int64_t)days * 86400 + secs;
-    }
-    const double phase = s.random_phase ? u01(q0.z, q0.w) * 24.0 : 0.0;  // ClusterHouses.__init__, :789-792
-    const Calendar cal = calendar_time((uint32_t)t);
-    const double time_day = cal.hour + cal.minute * (1.0 / 60.0);
-    const double od = p.od_amplitude * sin(p.two_pi_over_24 * (time_day + (-6 + phase))) + p.od_bias +
-                      p.temp_std * gauss01(q1.x, q1.y, q1.z, q1.w);  // :793, :1070-1081
-    double mp = 0.0;
-    for (int i = 0; i < N; ++i) mp += s_cap[i] / p.hvac_cop;  // sequential, id order (:796-802)
-    p.t_epoch[e] = t;
-    const_cast<double*>(p.phase)[e] = phase;
-    p.od_temp[e] = od;
-    // PowerGrid.__init__, :1116: ratio * range ** (U * 2 - 1); :1182-1184: perlin seed = random()
-    const_cast<double*>(p.artificial_ratio)[e] = s.artificial_ratio * pow(s.artificial_ratio_range, u01(q2.x, q2.y) * 2.0 - 1.0);
-    const_cast<double*>(p.max_power)[e] = mp;
-    p.base_power[e] = 0.0;
-    p.signal[e] = 0.0;
-    p.cluster_power[e] = 0.0;
-    if (p.solar_gain != nullptr) p.solar_gain[e] = 0.0;
-    if (p.time_since_interp != nullptr) p.time_since_interp[e] = s.interp_update_period + 1;
-    if (p.perlin_seed != nullptr) const_cast<double*>(p.perlin_seed)[e] = u01(q2.z, q2.w);
-  }
-}
-
-cudaError_t launch_populate(const KernelParams& kp_in, const MdrPopulationSpec& spec, const uint8_t* env_mask, double* ua,
-                            double* cm, double* ca, double* hm, double* cap, double* target, double* deadband,
-                            int32_t* lockout_dur, int precision, uint64_t draw_index, cudaStream_t stream) {
-  KernelParams kp = kp_in;
-  kp.off_in = precision;  // (re-used as the precision tag: the kernel is not templated)
-  const size_t smem = (size_t)kp.N * sizeof(double);
-  populate_kernel<<<kp.E, 128, smem, stream>>>(kp, spec, env_mask, ua, cm, ca, hm, cap, target, deadband, lockout_dur, draw_index);
-  return cudaGetLastError();
-}
+#include "mdr_pipe.cuh"
+#include "mdr_fused.cuh"
+#include "mdr_populate.cuh"
 
 // ----------------------------------------------------------------------------------------
 // host-side launch helpers

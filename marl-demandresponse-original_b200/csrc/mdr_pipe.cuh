@@ -1,0 +1,468 @@
+// Persistent software-pipelined step kernel (fp32 fast path), its prologue warp and deferred interpolation refresh.
+// Included by mdr_kernels.cu inside namespace mdr (after the shared device helpers); not a standalone translation unit.
+#pragma once
+
+// ----------------------------------------------------------------------------------------
+// Persistent, software-pipelined variant of the fast path (fp32, default observation layout,
+// solar gain off, plain steps).  The CTAs stay resident (SMs x CTAs/SM of them) and loop over
+// tiles of G envs:
+//   * the house threads' inputs of tile i+1 are fetched with cp.async into a second shared-memory
+//     stage while tile i is computed (each thread copies and later reads only its own record, so
+//     cp.async.wait_group is the only synchronisation the inputs need);
+//   * the dedicated prologue warp runs `pro_batch` tiles per pass and up to 2*pro_batch tiles ahead,
+//     handing a 64-byte PipeEnv record per env over through an mbarrier ring, and writes the
+//     per-env outputs (clock, outdoor temperature, signal) itself;
+//   * the bulk (TMA) observation store of tile i drains while tile i+1 is loaded and updated.
+// Barrier 1 = house warps only (message window + power partial sums); everything that is constant
+// over the tile loop (shared-memory addresses, neighbour window, partial-sum slots) is computed
+// once per thread before the loop.
+// ----------------------------------------------------------------------------------------
+// Trace build (-DMDR_TRACE): lane 0 of every warp of CTA MDR_TRACE_CTA stamps globaltimer at fixed
+// points of its first MDR_TRACE_TILES tiles; tools/trace_tile.py reads the buffer back.
+#ifdef MDR_TRACE
+#ifndef MDR_TRACE_CTA
+#define MDR_TRACE_CTA 200
+#endif
+#define MDR_TRACE_TILES 24
+#define MDR_TRACE_POINTS 10
+__device__ unsigned long long g_trace[8 * MDR_TRACE_TILES * MDR_TRACE_POINTS];
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define MDR_STAMP_AT(w, t, k)                                                                        \
+  do {                                                                                                \
+    if (blockIdx.x == MDR_TRACE_CTA && (threadIdx.x & 31) == 0 && (t) < MDR_TRACE_TILES)              \
+      g_trace[((w) * MDR_TRACE_TILES + (t)) * MDR_TRACE_POINTS + (k)] = global_ns();                  \
+  } while (0)
+#define MDR_STAMP(k) MDR_STAMP_AT(warp, it, k)
+}  // namespace mdr
+// trace builds only (tools/trace_tile.py): copies the globaltimer stamps of the traced CTA to the host
+extern "C" int mdr_debug_trace(unsigned long long* host, size_t n, int clear) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -5;
+  if (cudaMemcpyFromSymbol(host, mdr::g_trace, n * sizeof(unsigned long long)) != cudaSuccess) return -5;
+  if (clear) {
+    void* ptr = nullptr;
+    cudaGetSymbolAddress(&ptr, mdr::g_trace);
+    cudaMemset(ptr, 0, n * sizeof(unsigned long long));
+  }
+  return 0;
+}
+namespace mdr {
+#else
+#define MDR_STAMP_AT(w, t, k) do { } while (0)
+#define MDR_STAMP(k) do { } while (0)
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_16(void* s, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+// mbarrier hand-over between the prologue warp (producer of PipeEnv records) and the house warps
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// shared-memory control block of the pipelined kernel (at off_ctl).  The PipeEnv ring has
+// ring = 2 * pro_batch <= kMaxRing slots; slot = it % ring for the it-th tile of this CTA.
+constexpr int kMaxRing = 16;
+struct PipeCtl {
+  uint64_t full[kMaxRing];   // prologue -> house warps: slot is ready            (count 1)
+  uint64_t empty[kMaxRing];  // house warps -> prologue: slot may be overwritten   (count house_warps)
+  int tile_due[kMaxRing];    // any env of the tile has an interpolation refresh due
+};
+
+// The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
+// groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  The deeper the
+// batch, the further the prologue's dependent fp64 / Philox / global-load chains are from the
+// house warps' critical path.
+// One pass: tiles it0 .. it0+B-1 of this CTA (B a power of two <= pro_batch).
+__device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PipeEnv* s_env = reinterpret_cast<PipeEnv*>(smem_raw + p.off_env);
+  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  const int ring = 2 * p.pro_batch;
+  const int ring_shift = 31 - __clz(ring);
+  const int lane = threadIdx.x & 31;
+  const int lanes_per_tile = 32 / B;
+  int L = 16;  // lanes cooperating on one env (2 * nb_octaves + 1 = 11 Philox draws per env)
+  while (L > 1 && L * p.G > lanes_per_tile) L >>= 1;
+  const int groups = lanes_per_tile / L;  // envs of a tile processed at once (>= 1: G * pro_batch <= 32)
+  const int tlane = lane & (lanes_per_tile - 1);
+  const int sub = tlane & (L - 1), grp = tlane / L;
+  const int my_k = lane / lanes_per_tile;  // which tile of the pass this lane works for
+  const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
+  const int it = it0 + my_k;
+  const int tile = blockIdx.x + it * gridDim.x;
+  const bool tile_valid = tile < p.n_tiles;
+  const int slot = it & (ring - 1);
+  MDR_STAMP_AT(7, it0, 8);
+  // the house warps must have released the pass's ring slots.  Warp-uniform loop over the B barriers:
+  // per-lane-group waits on different mbarriers (a divergent try_wait spin) were measured to return
+  // up to 8 us late (tools/trace_tile.py)
+  for (int k = 0; k < B; ++k) {
+    const int itk = it0 + k;
+    if (blockIdx.x + itk * gridDim.x < p.n_tiles && (itk >> ring_shift) >= 1)
+      mbar_wait(&ctl.empty[itk & (ring - 1)], (((itk >> ring_shift) & 1) ^ 1));
+  }
+  MDR_STAMP_AT(7, it0, 0);
+  const int tile_c = tile_valid ? tile : blockIdx.x;  // lanes of an absent tile compute but never write
+  const int env0 = tile_c * p.G;
+  const int genvs = min(p.G, p.E - env0);
+  PipeEnv* buf = s_env + slot * p.G;
+  EnvScratch unused;
+  int my_due = 0;
+  for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count (G, not genvs)
+    const int le2 = first + grp;
+    const bool valid = tile_valid && le2 < genvs;
+    const int lec = le2 < genvs ? le2 : genvs - 1;
+    my_due |= env_prologue<true>(p, unused, buf[lec], env0 + lec, sub, L, valid, false, false);
+  }
+  const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
+  if (tile_valid && tlane == 0) ctl.tile_due[slot] = (due_ballot & group_mask) != 0;
+  __syncwarp();
+  if (tile_valid && tlane == 0) mbar_arrive(&ctl.full[slot]);
+  MDR_STAMP_AT(7, it0, 7);
+}
+
+// Deferred interpolation refresh (every interp_update_period seconds; PowerGrid.step :1250-1255,
+// interpolatePower :1195-1234).  It runs on 1 step in 75, needs fp64 and a 32-corner table walk per
+// house, and would cost the tile loop registers if it sat inside it.  So the tile loop treats a due
+// env like any other (the prologue parks its perlin value and marks it), and this pass -- after the
+// loop, same launch, same CTA, same tile order -- evaluates the table on the houses' NEW state,
+// re-evaluates the signal and patches observation feature 9 (the only output that depends on it).
+__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
+  float* s_fsig = reinterpret_cast<float*>(smem_raw + p.off_pw);  // [G], the power partials are dead by now
+  const int tid = threadIdx.x;
+  const int N = p.N, G = p.G, GN = G * N;
+  const int nb = p.interp_nb_agents;
+  const int nsamp = N <= nb ? N : nb;
+  const int T = p.hmax;
+  // the bulk stores of this warp's rows must have landed before feature 9 is patched
+  if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int H = min(GN, (p.E - tile * G) * N);
+    const bool active = tid < H;
+    const int e = tile * G + le;
+    const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+    const bool due = active && p.time_since_interp[e] < 0;
+    int any;
+    asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.or.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
+                 : "=r"(any)
+                 : "r"((int)due), "r"(T)
+                 : "memory");
+    if (!any) continue;
+    double od_new = 0.0;
+    if (due) od_new = p.od_temp[e];
+    if (due && li < nsamp) {
+      int src = li;
+      if (N > nb) {
+        if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
+        else {
+          const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                                     STREAM_IDS + 16 * (uint32_t)li, p.seed);
+          src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
+        }
+      }
+      const size_t hs = (size_t)e * N + src;
+      const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
+      const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
+      s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, 0.0, 0.0);
+    }
+    house_sync(T);
+    if (due && li == 0) {
+      double base = 0.0;
+      for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);  // id order, :1218-1232
+      if (N > nb) base = mul_rn(base, (double)N / (double)nb);
+      const Calendar cal = calendar_time((uint32_t)p.t_epoch[e]);
+      const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
+      const double sig_noise = p.base_power[e];  // parked by the prologue
+      const double sig = grid_signal(p, base, time_sec, sig_noise, p.artificial_ratio[e], p.max_power[e]);
+      p.base_power[e] = base;
+      p.time_since_interp[e] = 0;
+      p.signal[e] = sig;
+      s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
+    }
+    house_sync(T);
+    if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
+    house_sync(T);  // s_val / s_fsig are reused by the next due tile
+  }
+}
+
+template <int kC, int kAct, bool kObs>
+__global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  const int ring_mask = 2 * p.pro_batch - 1;
+  const int ring_shift = 31 - __clz(ring_mask + 1);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
+  if (tid == 0) {
+    for (int i = 0; i <= ring_mask; ++i) {
+      mbar_init(&ctl.full[i], 1);
+      mbar_init(&ctl.empty[i], p.house_warps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp >= p.house_warps) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
+    const int B = p.pro_batch;
+    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
+    return;
+  }
+
+  // ---------------- per-thread constants of the tile loop ------------------------------------
+  const int N = p.N, G = p.G;
+  const int C = kC > 0 ? kC : p.C;
+  const int half = C >> 1;
+  const int ns = N + C;
+  const int GN = G * N;                 // houses of a full tile
+  const int T = p.hmax;                 // house threads of the CTA (multiple of 32)
+  const int le = tid < GN ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
+  const int li = tid - le * N;
+  // own slot in message window 0 ([half halo | N houses | halo] per env); window 1 follows
+  float4* const msg0 = reinterpret_cast<float4*>(smem_raw + p.off_msg) + (le * ns + half + li);
+  const int msg_buf = G * ns;
+  const bool halo_hi = li < C - half;   // my message is also the wrap-around halo after the last house
+  const bool halo_lo = li >= N - half;  // ... and before the first one
+  // warp-partial power sums: [2][G][part_stride]
+  float* const part0 = reinterpret_cast<float*>(smem_raw + p.off_pw) + le * p.part_stride;
+  const int part_buf = G * p.part_stride;
+  const int first_warp = (le * N) >> 5;
+  const int my_part = warp - first_warp;
+  const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
+  float* const row = reinterpret_cast<float*>(smem_raw + p.off_stage) + tid * p.F;  // rows contiguous like in HBM
+  PipeEnv* const s_env = reinterpret_cast<PipeEnv*>(smem_raw + p.off_env);
+  // cp.async input stage s (in_stride bytes each): [coef_a T x 16][coef_b T x 16][temps T x 8][coef_c T x 8][hvac T x 4]
+  unsigned char* const in_a = smem_raw + p.off_in + tid * 16;
+  unsigned char* const in_t = smem_raw + p.off_in + T * 32 + tid * 8;
+  unsigned char* const in_h = smem_raw + p.off_in + T * 48 + tid * 4;
+  const int in_stride = p.in_stride;
+  const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
+  const int n_tiles = p.n_tiles;
+  const int tile_stride = gridDim.x;
+  const float inv_norm = p.f_inv_norm_reg_sig;
+
+  auto tile_houses = [&](int tile) { return min(GN, (p.E - tile * G) * N); };
+  auto issue_tile = [&](int tile, int s) {
+    if (tid < tile_houses(tile)) {
+      const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+      const int so = s * in_stride;
+      cp_async_16(in_a + so, reinterpret_cast<const float4*>(p.coef_a) + h);
+      cp_async_16(in_a + so + T * 16, reinterpret_cast<const float4*>(p.coef_b) + h);
+      cp_async_8(in_t + so, reinterpret_cast<const float2*>(p.temps) + h);
+      cp_async_8(in_t + so + T * 8, reinterpret_cast<const float2*>(p.coef_c) + h);
+      cp_async_4(in_h + so, p.hvac + h);
+    }
+  };
+  // the action byte of the next tile travels in a register (kept as loaded: converting here would
+  // stall on the load instead of letting it fly)
+  auto fetch_action = [&](int tile) -> int {
+    if (kAct == MDR_ACT_ARRAY && tid < tile_houses(tile)) return p.actions[(unsigned)tile * (unsigned)GN + (unsigned)tid];
+    return 0;
+  };
+
+  int tile = blockIdx.x;
+  int cmd_next = 0;
+  int any_due = 0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
+  if (tile < n_tiles) {
+    issue_tile(tile, 0);
+    cmd_next = fetch_action(tile);
+  }
+  cp_async_commit();
+
+  for (int it = 0; tile < n_tiles; ++it, tile += tile_stride) {
+    const int sbuf = it & 1;
+    const int H = tile_houses(tile);
+    const bool active = tid < H;
+    const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+    const int e = tile * G + le;
+    MDR_STAMP(0);
+    int cmd = cmd_next;
+    const int next = tile + tile_stride;
+    if (next < n_tiles) {
+      issue_tile(next, sbuf ^ 1);
+      cmd_next = fetch_action(next);
+    }
+    cp_async_commit();
+    // hand-over from the prologue warp (normally produced more than a tile ago).  Waiting here rather than
+    // at the end of the tile (with the house threads prefetching od_temp themselves) measured the same.
+    const int slot = it & ring_mask;
+    const PipeEnv* const env_buf = s_env + slot * G;
+    mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);
+    const float od_old = env_buf[le].od_old;
+    MDR_STAMP(1);
+    cp_async_wait<1>();  // this thread's copies of the current tile have landed
+    MDR_STAMP(2);
+
+    // ---------------- phase A: per house ---------------------------------------------------
+    float t_air = 0, t_mass = 0, target = 0, p_on = 0, deadband = 0, inv_lock = 1, pen = 0, pw = 0;
+    int on = 0, lock = 0, sso = 0;
+    float4* const msg = msg0 + sbuf * msg_buf;
+    if (active) {
+      const int so = sbuf * in_stride;
+      const float4 ca4 = *reinterpret_cast<const float4*>(in_a + so);
+      const float4 cb = *reinterpret_cast<const float4*>(in_a + so + T * 16);
+      const float2 tt = *reinterpret_cast<const float2*>(in_t + so);
+      const float2 cc = *reinterpret_cast<const float2*>(in_t + so + T * 8);
+      const int hv = *reinterpret_cast<const int*>(in_h + so);
+      target = cb.w; p_on = cb.z; deadband = cc.x;
+      inv_lock = __fdividef(1.0f, cc.y);
+      on = hv & 1; sso = hv >> 2;
+      if (kAct == MDR_ACT_ARRAY) cmd = cmd != 0;
+      else if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
+      else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
+      // HVAC.step, :475-492
+      const int dt = p.dt;
+      const int lockdur = (int)cc.y;
+      if (!on) sso += dt;
+      lock = !(on || sso >= lockdur);
+      const int new_on = lock ? 0 : cmd;
+      if (!lock && new_on) sso = 0;
+      if (!lock && !new_on && sso + dt < lockdur) lock = 1;
+      on = new_on;
+      // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature
+      const float qa = on ? cb.y : 0.0f;
+      const float tss = od_old + qa * cb.x;
+      const float x = tt.x - tss, y = tt.y - tss;
+      t_air = tt.x + (ca4.x * x + ca4.y * y);
+      t_mass = tt.y + (ca4.z * x + ca4.w * y);
+      reinterpret_cast<float2*>(p.temps)[h] = make_float2(t_air, t_mass);
+      p.hvac[h] = (sso << 2) | (lock << 1) | on;
+      pw = on ? p_on : 0.0f;
+      // SingleHouse.message :624-662 normalised as utils.py:842-868 (sso is scaled by the receiver)
+      const float4 m = make_float4((t_air - target) * 0.2f, (float)sso, pw * inv_norm, p_on * inv_norm);
+      msg[0] = m;
+      if (halo_hi) msg[N] = m;
+      if (halo_lo) msg[-N] = m;
+      // utils.deadbandL2, utils.py:1266-1274
+      const float hi = target + deadband * 0.5f, lo = target - deadband * 0.5f;
+      if (hi < t_air) pen = (t_air - hi) * (t_air - hi);
+      else if (lo > t_air) pen = (lo - t_air) * (lo - t_air);
+    }
+    float* const part = part0 + sbuf * part_buf;
+    {
+      const int key = active ? le : -1;
+      // fp32 partial sums are exact here: integer-valued watts, at most 224 houses (< 2^24 W)
+      const float psum = segmented_sum<float>(pw, key, lane);
+      const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+      if (active && (lane == 0 || prev_key != key)) part[my_part] = psum;
+    }
+    MDR_STAMP(3);
+    // the staging rows of this warp may still be read by the previous tile's bulk store (waited for
+    // BEFORE the barrier: the two waits then overlap; after it they add up -- measured +5% on c4)
+    if (kObs && it > 0) {
+      if (lane == 0) bulk_wait_read_all();
+      __syncwarp();
+    }
+    MDR_STAMP(4);
+    // the only CTA-wide rendezvous of a tile: message window + power partials are complete.
+    // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
+    house_sync(T);
+    MDR_STAMP(5);
+
+    float P = 0;
+    if (active) {
+      // an env of <= 224 houses spans at most 8 warps; same summation order as a counted loop
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if (w < nparts) P += part[w];
+      if (li == 0) p.cluster_power[e] = (double)P;
+    }
+    if (kObs && active) {
+      // fast-path row: [T_air, T_mass, target, deadband, cap, on, lockout, sso, 1, signal, power | C x 4 messages]
+      row[0] = (t_air - 20.0f) * 0.2f;
+      row[1] = (t_mass - 20.0f) * 0.2f;
+      row[2] = (target - 20.0f) * 0.2f;
+      row[3] = deadband;
+      row[4] = p_on * p.f_cop_over_def_cap;
+      row[5] = (float)on;
+      row[6] = (float)lock;
+      row[7] = (float)sso * inv_lock;
+      row[8] = 1.0f;
+      row[10] = P * p.f_inv_norm_sig_agents;
+      // neighbours (:816-828) = the C window entries around this house, skipping itself
+      const float4* win = msg - half;
+      float* mrow = row + 11;
+#pragma unroll
+      for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
+        const float4 m = win[k + (k >= half ? 1 : 0)];
+        mrow[4 * k + 0] = m.x;
+        mrow[4 * k + 1] = m.y * inv_lock;
+        mrow[4 * k + 2] = m.z;
+        mrow[4 * k + 3] = m.w;
+      }
+    }
+    MDR_STAMP(6);
+    any_due |= ctl.tile_due[slot];
+    if (active) {
+      // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
+      const float dn = (float)((double)P - env_buf[le].s_old) * p.f_inv_n;
+      if (p.reward != nullptr) reinterpret_cast<float*>(p.reward)[h] = -(pen * p.f_k_temp + dn * dn * p.f_k_sig);
+      if (kObs) row[9] = env_buf[le].f_sig;
+    }
+    if (kObs) {
+      const int wrow0 = warp * 32;
+      const int nrows_w = min(32, H - wrow0);
+      if (nrows_w > 0) {
+        const int F = p.F;
+        float* dst = reinterpret_cast<float*>(p.obs) + (size_t)((unsigned)tile * (unsigned)GN + (unsigned)wrow0) * F;
+        const float* src = reinterpret_cast<const float*>(smem_raw + p.off_stage) + wrow0 * F;
+        const uint32_t bytes = (uint32_t)(nrows_w * F * sizeof(float));
+        const bool bulk_ok = ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0;
+        if (bulk_ok) {
+          // measured alternatives (tools/microbench): a coalesced st.global.v4 copy loop is ~4% slower,
+          // an L2 evict_first hint on this store changes nothing
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) bulk_store_s2g(dst, src, bytes);
+        } else {
+          __syncwarp();
+          for (int i = lane; i < nrows_w * F; i += 32) dst[i] = src[i];
+          __syncwarp();
+        }
+      }
+    }
+    // this warp is done with ring slot `slot`: let the prologue warp reuse it for tile it+ring
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ctl.empty[slot]);
+    MDR_STAMP(7);
+  }
+  cp_async_wait<0>();
+  if (kObs && lane == 0) bulk_wait_read_all();
+  if (interp_mode && any_due) pipe_refresh_pass(p, le, li);  // CTA-uniform: every house thread read the same flags
+}
+
