@@ -258,8 +258,8 @@ int mdr_observe(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *en
    requires on-device action/noise sources).  One kernel launch per step -- except that steps which need
    nothing from the host between them (on-device action source, no replayed noise, constant base power,
    individual_L2 penalty, out->obs == NULL) run as ONE fused launch with the house state in registers
-   (the main-deploy.py:102-209 loop); only that path accumulates envs->metrics, any other
-   configuration with metrics != NULL returns MDR_ERR_UNSUPPORTED. */
+   (the main-deploy.py:102-209 loop).  envs->metrics, when given, is accumulated by that path and by single-step
+   launches of every other configuration (which then run the generic kernel, not the pipelined one). */
 int mdr_step(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
              const MdrStepInputs *in, const MdrOutputs *out, int32_t n_steps, void *stream);
 

@@ -80,7 +80,7 @@ extern "C" int mdr_validate(const MdrConfig* c) {
 
 static void fill_config(KernelParams& k, const MdrConfig* c);
 
-static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
+static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool need_met = false) {
   const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
   if (N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
   const char* tt_env = getenv("MDR_TARGET_THREADS");  // tuning knob: house threads per CTA
@@ -108,12 +108,12 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g) {
   int rpp = 0;
   size_t smem = 0;
   for (int r = 32; r >= 1; r >>= 1) {
-    smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride);
+    smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride, need_met);
     if (smem <= budget) { rpp = r; break; }
   }
   if (rpp == 0) {
     for (int r = 32; r >= 1; r >>= 1) {
-      smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride);
+      smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride, need_met);
       if (smem <= (size_t)MDR_MAX_SMEM_BYTES) { rpp = r; break; }
     }
   }
@@ -332,7 +332,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   st = fill_step(k, cfg, envs, in, out, is_reset);
   if (st != MDR_OK) return st;
   Geometry g;
-  st = choose_geometry(cfg, out->obs != nullptr, &g);
+  st = choose_geometry(cfg, out->obs != nullptr, &g, k.metrics != nullptr);
   if (st != MDR_OK) return st;
   k.G = g.envs_per_cta;
   k.hmax = g.hmax;
@@ -351,7 +351,8 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   k.part_stride = g.part_stride;
   mdr::step_smem_layout(&k, cfg->precision, g.hmax, g.envs_per_cta, g.house_warps, g.rows_per_pass, cfg->n_features,
                         cfg->base_power_mode == MDR_BASE_INTERPOLATION || cfg->action_source == MDR_ACT_GREEDY,
-                        cfg->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2, out->obs != nullptr, cfg->n_comm, g.part_stride);
+                        cfg->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2, out->obs != nullptr, cfg->n_comm, g.part_stride,
+                        k.metrics != nullptr);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);
   const char* no_pipe = getenv("MDR_NO_PIPELINE");
@@ -372,7 +373,6 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     err = mdr::launch_fused(k, g, cfg->precision, n_steps, stream);
     return err == cudaSuccess ? MDR_OK : cuda_fail(err);
   }
-  if (k.metrics != nullptr) return MDR_ERR_UNSUPPORTED;
   for (int i = 0; i < n_steps; ++i) {
     err = pipe ? mdr::launch_pipe(k, g, stream) : mdr::launch_step_any(k, g, cfg->precision, stream);
     if (err != cudaSuccess) return cuda_fail(err);

@@ -61,12 +61,12 @@ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // shared-memory carve-up (must match between host sizing and the kernel)
 struct SmemLayout {
-  size_t off_msg, off_pw, off_val, off_pen, off_env, off_stage, total;
+  size_t off_msg, off_pw, off_val, off_pen, off_env, off_met, off_stage, total;
 };
 
 // hmax = threads per CTA (>= G*N); the message window holds G*(N+C) entries (wrap-around halos)
 inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarps, int rows_per_pass, int n_features,
-                              bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride) {
+                              bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met) {
   SmemLayout L;
   size_t o = 0;
   L.off_msg = o; o += align16((size_t)(hmax + genvs_max * n_comm) * 4 * real_bytes);
@@ -74,6 +74,7 @@ inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarp
   L.off_val = o; o += need_val ? align16((size_t)hmax * 3 * sizeof(double)) : 0;  // interpolation values / greedy sort scratch
   L.off_pen = o; o += need_pen ? align16((size_t)hmax * sizeof(double)) : 0;
   L.off_env = o; o += align16((size_t)genvs_max * sizeof(EnvScratch));
+  L.off_met = o; o += need_met ? align16((size_t)genvs_max * part_stride * 5 * sizeof(double)) : 0;
   L.off_stage = o;
   o += has_obs ? align16((size_t)nwarps * rows_per_pass * n_features * real_bytes) : 0;
   L.total = o;
@@ -717,12 +718,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
       p.time_since_interp[e] = 0;
       p.signal[e] = sig;
       es.f_sig = sig * p.inv_norm_sig_agents;
+      es.sig_new = sig;
     }
     cta_sync();
   }
 
   // ---------------- phase E: reward + observation ----------------------------------------
-  if (active && !reset && p.reward != nullptr) {
+  R reward_r = 0;
+  if (active && !reset && (p.reward != nullptr || p.metrics != nullptr)) {
     const EnvScratch& es = s_env[le];
     double tp = (double)pen;
     if (pen_mode == MDR_PEN_COMMON_L2) tp = es.pen_mean;
@@ -732,7 +735,60 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
            (p.mix_alpha_ind + p.mix_alpha_common + p.mix_alpha_max);
     // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
     const double dn = (P - es.s_old) * p.inv_n;
-    reinterpret_cast<R*>(p.reward)[h] = (R)(-(tp * p.k_temp + dn * dn * p.k_sig));
+    reward_r = (R)(-(tp * p.k_temp + dn * dn * p.k_sig));
+    if (p.reward != nullptr) reinterpret_cast<R*>(p.reward)[h] = reward_r;
+  }
+
+  // ---------------- metric accumulators for single-step launches of ANY configuration ----------
+  // (array actions, interpolation, every penalty mode): the quantities main-deploy.py:124-149 and
+  // metrics.py:22-30 accumulate, reduced per env in a fixed order and += into MdrEnvs.metrics
+  if (!kFast && !reset && p.metrics != nullptr) {
+    double* s_met = reinterpret_cast<double*>(smem_raw + p.off_met);  // [G][part_stride][5]
+    const int key = active ? le : -1;
+    const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = active && (lane == 0 || prev_key != key);
+    const double err = active ? (double)tt.x - (double)target : 0.0;
+    const double v0 = segmented_sum<double>(active ? (double)reward_r : 0.0, key, lane);
+    const double v1 = segmented_sum<double>(err, key, lane), v2 = segmented_sum<double>(fabs(err), key, lane);
+    const double v3 = segmented_sum<double>(err * err, key, lane);
+    double v4 = fabs(err);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tv = __shfl_down_sync(0xffffffffu, v4, o);
+      const int tk = __shfl_down_sync(0xffffffffu, key, o);
+      if (lane + o < 32 && tk == key) v4 = fmax(v4, tv);
+    }
+    const int first_warp = (le * N) >> 5;
+    if (head) {
+      double* d = s_met + (size_t)(le * p.part_stride + (warp - first_warp)) * 5;
+      d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3; d[4] = v4;
+    }
+    house_sync(p.house_warps * 32);
+    if (active && li == 0) {
+      const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
+      double t[4] = {0.0, 0.0, 0.0, 0.0}, mx = 0.0;
+      for (int w = 0; w < nparts; ++w) {
+        const double* d = s_met + (size_t)(le * p.part_stride + w) * 5;
+        for (int k = 0; k < 4; ++k) t[k] += d[k];
+        mx = fmax(mx, d[4]);
+      }
+      const EnvScratch& es = s_env[le];
+      const double dsp = es.sig_new - P;  // NEW signal (after a refresh, if one was due) minus this step's consumption
+      double* m = p.metrics + (size_t)e * MDR_N_METRICS;
+      m[MDR_M_STEPS] += 1.0;
+      m[MDR_M_SUM_MEAN_REWARD] += t[0] * p.inv_n;
+      m[MDR_M_SUM_MEAN_TEMP_OFFSET] += t[1] * p.inv_n;
+      m[MDR_M_SUM_MEAN_TEMP_ERROR] += t[2] * p.inv_n;
+      m[MDR_M_SUM_SQ_TEMP_ERROR] += t[3];
+      m[MDR_M_SUM_SQ_MAX_TEMP_ERROR] += mx * mx;
+      m[MDR_M_MAX_TEMP_ERROR] = fmax(m[MDR_M_MAX_TEMP_ERROR], mx);
+      m[MDR_M_SUM_OD_TEMP] += es.od_new;
+      m[MDR_M_SUM_SIGNAL] += es.sig_new;
+      m[MDR_M_SUM_CONSUMPTION] += P;
+      m[MDR_M_SUM_SIGNAL_OFFSET] += dsp;
+      m[MDR_M_SUM_SIGNAL_ERROR] += fabs(dsp);
+      m[MDR_M_SUM_SQ_SIGNAL_ERROR] += dsp * dsp;
+    }
   }
 
   if (p.obs == nullptr) return;
@@ -880,7 +936,7 @@ template <typename R>
 static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
   const bool fast = kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 && kp.msg_flags == 0 &&
                     kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
-                    !(kp.comm_defect_prob > 0.0) && kp.action_source != MDR_ACT_GREEDY;
+                    !(kp.comm_defect_prob > 0.0) && kp.action_source != MDR_ACT_GREEDY && kp.metrics == nullptr;
   if (fast && kp.C == 10) return launch_step_f<R, true, 10>(kp, g, stream);
   return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
@@ -974,7 +1030,7 @@ bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision) {
   return precision == MDR_F32 && kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 &&
          kp.msg_flags == 0 && kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
          !(kp.comm_defect_prob > 0.0) && !kp.solar && g.pro_warp >= g.house_warps && g.threads <= 256 &&
-         g.rows_per_pass == 32 && g.pipe_smem_bytes > 0 && kp.action_source != MDR_ACT_GREEDY;
+         g.rows_per_pass == 32 && g.pipe_smem_bytes > 0 && kp.action_source != MDR_ACT_GREEDY && kp.metrics == nullptr;
 }
 
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream) {
@@ -1005,12 +1061,13 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
 }
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
-                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride) {
+                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met) {
   const SmemLayout L = smem_layout(real_bytes, hmax, genvs, nwarps, rows_per_pass, n_features, need_val, need_pen, has_obs,
-                                   n_comm, part_stride);
+                                   n_comm, part_stride, need_met);
   if (kp) {
     kp->off_msg = (int)L.off_msg; kp->off_pw = (int)L.off_pw; kp->off_val = (int)L.off_val;
     kp->off_pen = (int)L.off_pen; kp->off_env = (int)L.off_env; kp->off_stage = (int)L.off_stage;
+    kp->off_met = (int)L.off_met;
   }
   return L.total;
 }

@@ -14,7 +14,7 @@ namespace mdr {
 struct KernelParams {
   // shape / geometry
   int E, N, C, F, G, hmax, rows_per_pass, dt;
-  int off_msg, off_pw, off_val, off_pen, off_env, off_stage, off_in, off_ctl;  // shared-memory carve-up (bytes)
+  int off_msg, off_pw, off_val, off_pen, off_env, off_stage, off_in, off_ctl, off_met;  // shared-memory carve-up (bytes)
   int ns, house_threads, in_stride;                            // N + C, house_warps * 32, bytes of one cp.async input stage
   int pro_batch;                                              // pipelined kernel: tiles the prologue warp produces per pass
   int n_tiles;                                                // pipelined kernel: number of G-env tiles
@@ -71,7 +71,7 @@ struct Geometry {
 };
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
-                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride);
+                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met);
 size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int n_features, bool need_val, bool has_obs,
                         int n_comm, int part_stride, int pro_batch);
 int pipe_pro_batch(int envs_per_cta, bool has_obs);

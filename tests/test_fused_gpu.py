@@ -130,16 +130,48 @@ def test_device_metrics_match_per_step_recomputation(precision):
     torch.testing.assert_close(a.metrics, ref, rtol=rtol, atol=1e-6 if precision == "fp64" else 1e-2)
     summ = a.metrics_summary()
     assert torch.all(summ["steps"] == k) and torch.isfinite(summ["rmse_temp"]).all()
-    # metrics with a configuration that cannot take the fused path are refused, not silently dropped
+
+
+@pytest.mark.parametrize("precision,penalty,interp", [("fp64", "mixture", True), ("fp32", "individual_L2", False), ("fp64", "common_max", False)])
+def test_single_step_metrics_with_array_actions(precision, penalty, interp):
+    """Configurations that cannot take the fused path (policy actions from an array, interpolated base power, common_*
+    penalties) accumulate the same 13 quantities in the generic single-step kernel."""
+    import torch
     import mdr_b200
-    cfg2 = _cfg(n, "perlin")
-    cfg2["default_env_prop"]["reward_prop"]["temp_penalty_mode"] = "common_L2"
-    flat2 = mdr_b200.FlatConfig(cfg2)
-    env2 = mdr_b200.VecDemandResponseEnv(cfg2, mdr_b200.synthetic_population(flat2, 4, seed=1), action_source="bangbang", with_obs=False)
-    env2.reset_tensor()
-    env2.enable_metrics()
-    with pytest.raises(mdr_b200.MdrError):
-        env2.run(3)
+    import golden_util as gu
+    from mdr_b200 import _lib
+    n_envs, n, k = 6, 45, 160 if interp else 40
+    cfg = _cfg(n, "perlin")
+    cfg["default_env_prop"]["reward_prop"]["temp_penalty_mode"] = penalty
+    cfg["default_env_prop"]["power_grid_prop"]["base_power_mode"] = "interpolation" if interp else "constant"
+    flat = mdr_b200.FlatConfig(cfg)
+    pop = mdr_b200.synthetic_population(flat, n_envs, seed=4)
+    table = gu.synthetic_table() if interp else None
+    a = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, seed=4, interp_table=table)
+    b = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, seed=4, interp_table=table)
+    a.reset_tensor()
+    b.reset_tensor()
+    a.enable_metrics()
+    ref = torch.zeros(n_envs, _lib.N_METRICS, dtype=torch.float64, device="cuda")
+    target = b.coef_b[..., 3].double()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(k):
+        act = (torch.rand(n_envs, n, device="cuda", generator=g) < 0.4).to(torch.uint8)
+        a.step_tensor(act)
+        _, rew, p, s = b.step_tensor(act)
+        err = b.t_air.double() - target
+        d = s - p
+        mx = err.abs().max(1).values
+        upd = [torch.ones(n_envs, device="cuda", dtype=torch.float64), rew.double().sum(1) / n, err.sum(1) / n, err.abs().sum(1) / n,
+               (err * err).sum(1), mx * mx, None, b.env["od_temp"], s, p, d, d.abs(), d * d]
+        for i, u in enumerate(upd):
+            if u is not None:
+                ref[:, i] += u
+        ref[:, 6] = torch.maximum(ref[:, 6], mx)
+    torch.cuda.synchronize()
+    # (b runs the pipelined kernel in fp32, a the generic one: compare at the precision's tolerance)
+    torch.testing.assert_close(a.metrics, ref, rtol=1e-9 if precision == "fp64" else 2e-4, atol=1e-6 if precision == "fp64" else 1e-2)
+    assert torch.equal(a.hvac, b.hvac)
 
 
 def test_fused_full_size_day_slice_is_deterministic():
