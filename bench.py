@@ -34,6 +34,9 @@ WORKLOADS = {
     # name: (envs per GPU, houses per env, base power mode, action source, observation written)
     "c4": dict(envs=16384, houses=100, interp=True, action_source="array", obs=True,
                desc="BASELINE config 4 per-GPU shard: 16384 envs x 100 houses, on-device interpolation"),
+    "c1": dict(envs=1, houses=1000, interp=True, action_source="array", obs=True, precision="fp64",
+               desc="BASELINE config 1: single env, 1,000 houses, regulation signal, nb_agents_comm=10, fp64 equivalence "
+                    "run (ONE CTA: launch-latency-bound, a parity configuration rather than a throughput one)"),
     "c2": dict(envs=4096, houses=50, interp=False, action_source="array", obs=True,
                desc="BASELINE config 2: 4096 envs x 50 houses (PPO/MAPPO rollout shape)"),
     "c3": dict(envs=10000, houses=100, interp=False, action_source="bangbang", obs=False,
@@ -310,7 +313,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "fp64"], help="default: the workload's (fp32; c1: fp64)")
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=4000,
@@ -319,6 +322,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.precision is None:
+        args.precision = WORKLOADS[args.workload].get("precision", "fp32")
     if args.impl == "reference":
         reference_arm(args)
     else:
