@@ -131,6 +131,20 @@ __device__ __forceinline__ double solar_gain(const Calendar& c, double window_ar
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double perlin_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
 
+// Lattice gradient g_o(i) in (-1, 1): a pure function of (lattice point, octave, env key).  A two-round
+// multiply-xorshift integer hash ("lowbias32" constants) instead of a Philox block: the prologue warp evaluates
+// 2 * nb_octaves of these per env and step on its critical path, and a noise texture needs decorrelation, not a
+// cryptographic generator (the Philox streams stay for the draws that model random variables).
+__device__ __forceinline__ float perlin_gradient(int lattice, int octave, uint64_t key) {
+  uint32_t x = ((uint32_t)lattice * 0x9E3779B1u) ^ (uint32_t)key ^ (((uint32_t)(key >> 32)) + (uint32_t)octave * 0x85EBCA77u);
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return 2.0f * (((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f)) - 1.0f;
+}
+
 // ---------------------------------------------------------------------------------------
 // warp reductions (fixed shuffle tree => run-to-run deterministic)
 // ---------------------------------------------------------------------------------------

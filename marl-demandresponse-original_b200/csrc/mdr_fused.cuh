@@ -25,7 +25,7 @@ __device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32
   if (p.solar) calendar_date(cal);
   const bool perlin = p.signal_mode == MDR_SIG_PERLIN;
   double sig_noise = 0.0;
-  if (perlin) {  // utils.Perlin.calculate_noise (utils.py:1247-1253) with Philox lattice gradients
+  if (perlin) {  // utils.Perlin.calculate_noise (utils.py:1247-1253) with hashed lattice gradients
     const int nb = p.perlin_nb_octaves;
     const double x = (double)cal.sod * p.inv_perlin_period;
     const uint64_t pkey = p.seed ^ (uint64_t)__double_as_longlong(p.perlin_seed[e2]);
@@ -35,11 +35,10 @@ __device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32
       const int j = d >> 1, corner = d & 1;
       const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
       const double fl = floor(xo);
-      const uint4 r = philox4x32((uint32_t)((int)fl + corner), 0u, (uint32_t)j, STREAM_PERLIN, pkey);
       const double dist = xo - (fl + corner);
       const float fd = 1.0f - fabsf((float)dist);
       const float fade = fd * fd * fd * (fd * (fd * 6.0f - 15.0f) + 10.0f);
-      const float g = 2.0f * (((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f)) - 1.0f;
+      const float g = perlin_gradient((int)fl + corner, j, pkey);
       const float wgt = j == nb - 1 ? 1.0f / (float)((1 << nb) - 1) : 1.0f / (float)(1 << j);
       sig_noise += (double)(fade * g * wgt) * dist;
     }

@@ -260,7 +260,7 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
   Calendar cal = calendar_time(t);
   if (p.solar || (p.state_flags & MDR_STATE_DAY)) calendar_date(cal);
   if (draw_od || draw_perlin) {  // warp-uniform
-    // utils.Perlin.calculate_noise (utils.py:1247-1253) with Philox lattice gradients: draw d < 2*nb is
+    // utils.Perlin.calculate_noise (utils.py:1247-1253) with hashed lattice gradients: draw d < 2*nb is
     // lattice corner (d & 1) of octave (d >> 1); the last draw is the outdoor-temperature normal
     const int nb = p.perlin_nb_octaves;
     const int n_perlin = draw_perlin ? 2 * nb : 0;
@@ -273,11 +273,10 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
         const int j = d >> 1, corner = d & 1;
         const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
         const double fl = floor(xo);
-        const uint4 r = philox4x32((uint32_t)((int)fl + corner), 0u, (uint32_t)j, STREAM_PERLIN, pkey);
         const double dist = xo - (fl + corner);
         const float fd = 1.0f - fabsf((float)dist);
         const float fade = fd * fd * fd * (fd * (fd * 6.0f - 15.0f) + 10.0f);
-        const float g = 2.0f * (((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f)) - 1.0f;
+        const float g = perlin_gradient((int)fl + corner, j, pkey);
         const float wgt = j == nb - 1 ? 1.0f / (float)((1 << nb) - 1) : 1.0f / (float)(1 << j);
         terms += (double)(fade * g * wgt) * dist;
       } else {

@@ -130,3 +130,32 @@ def test_production_mode_device_rng_is_reproducible_and_plausible():
     assert 25.0 < float(od.min()) and float(od.max()) < 37.5
     resid = od[1:] - od[:-1]
     assert 0.4 < float(resid.std()) < 1.0  # difference of two N(0, 0.5) draws: std ~0.71
+
+
+def test_device_perlin_signal_statistics():
+    """Production-mode grid signal (device perlin: utils.Perlin over hashed lattice gradients, parity of the value itself
+    is unpinned -- DESIGN.md section 4): bounded, centred on the base power, smooth in time, different per env."""
+    import torch
+    n_envs, n, steps = 512, 10, 400
+    import mdr_b200
+    cfg, _, pop, _ = _make(n_envs, n, with_obs=False)
+    cfg["default_env_prop"]["power_grid_prop"]["signal_mode"] = "perlin"
+    flat = mdr_b200.FlatConfig(cfg)
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", seed=11, with_obs=False)
+    env.reset_tensor()
+    act = torch.zeros(n_envs, n, dtype=torch.uint8, device="cuda")
+    sig = torch.empty(steps, n_envs, dtype=torch.float64, device="cuda")
+    for t in range(steps):
+        sig[t] = env.step_tensor(act)[3]
+    base = flat.avg_power_per_hvac * n
+    ratio = env.env["artificial_ratio"]
+    noise = sig / (base * ratio) - 1.0          # = amplitude * perlin(t), clipped at -1 and by max_power
+    amp = float(flat.signal_params["amplitude_ratios"])
+    assert float(noise.min()) >= -1.0 - 1e-9 and float(noise.abs().max()) < 1.5 * amp
+    assert abs(float(noise.mean())) < 0.03 * amp                      # centred
+    assert float(noise.std()) > 0.05 * amp                            # not degenerate
+    d1 = (noise[1:] - noise[:-1]).abs().mean()
+    assert float(d1) < 0.25 * float(noise.std())                      # smooth: small step-to-step change
+    c = torch.corrcoef(noise[:, :64].T)
+    off = c - torch.eye(64, device="cuda", dtype=c.dtype)
+    assert float(off.abs().mean()) < 0.2                              # envs are decorrelated (own perlin seed)

@@ -35,6 +35,7 @@ env.step_tensor(a)
 lib.mdr_debug_trace(buf, n, 0)
 t = np.frombuffer(buf, dtype=np.uint64).reshape(8, TILES, POINTS).astype(np.int64)
 t0 = t[t > 0].min()
+print("absolute ns: first stamp %d, last stamp %d (span %.1f us)" % (t0, t.max(), (t.max() - t0) / 1e3))
 rel = np.where(t > 0, (t - t0) / 1e3, np.nan)
 names = ["tile start", "issued next+record", "inputs landed", "phase A done", "drain done", "after barrier", "rows done",
          "tile end"]
