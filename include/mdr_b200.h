@@ -256,8 +256,9 @@ int mdr_observe(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *en
 
 /* MADemandResponseEnv.step (:174-210) for every env of the shard, `n_steps` times (n_steps > 1
    requires on-device action/noise sources).  One kernel launch per step -- except that steps which need
-   nothing from the host between them (on-device action source, no replayed noise, constant base power,
-   individual_L2 penalty, out->obs == NULL) run as ONE fused launch with the house state in registers
+   nothing from the host between them (on-device action source, no replayed noise, individual_L2 penalty,
+   out->obs == NULL, constant base power -- or interpolated base power with n_houses <= interp_nb_agents, no
+   solar gain and a signal mode other than regular_steps) run as ONE fused launch with the house state in registers
    (the main-deploy.py:102-209 loop).  envs->metrics, when given, is accumulated by that path and by single-step
    launches of every other configuration (which then run the generic kernel, not the pipelined one). */
 int mdr_step(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,

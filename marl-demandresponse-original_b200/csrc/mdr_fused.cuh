@@ -5,7 +5,7 @@
 // ----------------------------------------------------------------------------------------
 // Fused multi-step kernel (the "deploy" loop, main-deploy.py:102-209): K consecutive env steps in ONE
 // launch for configurations whose per-step inputs are all produced on the device (on-device action
-// source, Philox noise, constant base power, no observation consumer).  A CTA owns G whole envs for
+// source, Philox noise, constant or -- kInterp -- interpolated base power, no observation consumer).  A CTA owns G whole envs for
 // the entire run: house state and coefficients stay in registers, nothing but the final state, the
 // last reward and the per-env metric accumulators ever goes back to HBM.
 //   * the per-env part of a step (clock, outdoor temperature, noise, grid signal) does not depend on
@@ -20,7 +20,21 @@
 struct StepRec { double od_new, sig_new, gain; };
 
 // one (env, step) record; mirrors env_prologue for base_power_mode == constant and on-device draws
-__device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32_t t, uint64_t step_index) {
+// PowerGrid.step signal shapes (:1257-1314) are linear in the base power except regular_steps: signal =
+// min(ratio * base * factor, max_power).  With interpolated base power the record warp cannot know the base of a
+// future step (it depends on the houses at the refresh), so it hands over the factor instead.
+__device__ __forceinline__ double signal_factor(const KernelParams& p, int time_sec, double noise) {
+  const double two_pi = 2.0 * 3.141592653589793;
+  if (p.signal_mode == MDR_SIG_SINUSOIDALS) {
+    double f = 1.0;
+    for (int i = 0; i < p.n_sinusoids; ++i) f += p.sin_ratios[i] * sin(mul_rn(two_pi, (double)time_sec) / p.sin_periods[i]);
+    return f;
+  }
+  if (p.signal_mode == MDR_SIG_PERLIN) return fmax(0.0, 1.0 + p.perlin_amplitude * noise);
+  return 1.0;  // flat
+}
+
+__device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32_t t, uint64_t step_index, bool factor_only) {
   Calendar cal = calendar_time(t);
   if (p.solar) calendar_date(cal);
   const bool perlin = p.signal_mode == MDR_SIG_PERLIN;
@@ -52,7 +66,8 @@ __device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32
   rec.od_new += od_noise;
   rec.gain = p.solar ? solar_gain(cal, p.window_area, p.shading_coeff) : 0.0;
   const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
-  rec.sig_new = grid_signal(p, p.avg_power_per_hvac * p.N, time_sec, sig_noise, p.artificial_ratio[e2], p.max_power[e2]);
+  rec.sig_new = factor_only ? signal_factor(p, time_sec, sig_noise)
+                            : grid_signal(p, p.avg_power_per_hvac * p.N, time_sec, sig_noise, p.artificial_ratio[e2], p.max_power[e2]);
   return rec;
 }
 
@@ -68,21 +83,22 @@ __device__ __forceinline__ R segmented_max(R v, int key, int lane) {
 }
 
 struct FusedSmem {
-  size_t off_rec, off_part, off_pmax, off_red, total;
+  size_t off_rec, off_part, off_pmax, off_red, off_interp, total;
 };
-inline FusedSmem fused_smem_layout(int real_bytes, int genvs, int part_stride, bool metrics) {
+inline FusedSmem fused_smem_layout(int real_bytes, int genvs, int part_stride, bool metrics, int hmax, bool interp) {
   FusedSmem L;
   size_t o = 0;
   L.off_rec = o;  o += align16((size_t)2 * genvs * 32 * 4 * real_bytes);
   L.off_part = o; o += align16((size_t)2 * genvs * part_stride * real_bytes);
   L.off_pmax = o; o += metrics ? align16((size_t)2 * genvs * part_stride * real_bytes) : 0;
   L.off_red = o;  o += metrics ? align16((size_t)genvs * part_stride * 4 * sizeof(double)) : 0;
+  L.off_interp = o; o += interp ? align16(((size_t)hmax + 2 * genvs) * sizeof(double)) : 0;  // values | base | last factor
   L.total = o;
   return L;
 }
 
-template <typename R, int kMaxThreads, int kAct, bool kMetrics>
-__global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_fused_kernel(const __grid_constant__ KernelParams p) {
+template <typename R, int kMaxThreads, int kAct, bool kMetrics, bool kInterp>
+__global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? (kInterp && kMetrics ? 2 : 3) : 1) run_fused_kernel(const __grid_constant__ KernelParams p) {
   using T2 = typename Vec<R>::T2;
   using T4 = typename Vec<R>::T4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -103,11 +119,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
       const int e2 = env0 + le2;
       const uint32_t t0 = (uint32_t)p.t_epoch[e2];
       if (j < K) {
-        const StepRec rec = env_record(p, e2, t0 + (uint32_t)(j + 1) * (uint32_t)dt, p.step_index + (uint64_t)j);
+        const StepRec rec = env_record(p, e2, t0 + (uint32_t)(j + 1) * (uint32_t)dt, p.step_index + (uint64_t)j, kInterp);
         s_rec[((b & 1) * G + le2) * 32 + lane] = make4((R)rec.od_new, (R)rec.sig_new, (R)rec.gain, (R)0);
         if (j == K - 1) {
           p.od_temp[e2] = rec.od_new;
-          p.signal[e2] = rec.sig_new;
+          if (kInterp) reinterpret_cast<double*>(smem_raw + p.off_in)[p.hmax + G + le2] = rec.sig_new;  // last factor, fp64
+          else p.signal[e2] = rec.sig_new;
           if (p.solar) p.solar_gain[e2] = rec.gain;
         }
       }
@@ -150,6 +167,18 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
     cc = reinterpret_cast<const T2*>(p.coef_c)[h];
     od_old = (R)p.od_temp[e];
     s_old = (R)p.signal[e];
+  }
+  // interpolated base power (kInterp): per-env base / refresh clock live in registers of every house thread
+  double base_cur = 0.0;
+  R ratio_r = 0, maxp_r = 0;
+  int tsi = 0, ikey = 0;
+  double* s_ival = reinterpret_cast<double*>(smem_raw + p.off_in);  // [hmax] table values | [G] new base | [G] last factor
+  if (kInterp && active) {
+    base_cur = p.base_power[e];
+    ratio_r = (R)p.artificial_ratio[e];
+    maxp_r = (R)p.max_power[e];
+    tsi = p.time_since_interp[e];
+    ikey = p.interp_key[h];
   }
   cta_sync();  // (see the record warp)
   const R target = cb.w, p_on = cb.z, deadband = cc.x;
@@ -230,7 +259,37 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
         }
         if (head) s_pmax[(j & 1) * part_buf + my_part] = pm;
       }
-      house_sync(p.house_threads);  // partials are double buffered by step parity: one rendezvous per step
+      R sig_new = rec.y;
+      if (!kInterp) {
+        house_sync(p.house_threads);  // partials are double buffered by step parity: one rendezvous per step
+      } else {
+        // PowerGrid.step :1250-1255: the refresh clock advances, a due env re-interpolates its base power from the
+        // houses' NEW state (N <= interp_nb_agents here: every house, summed in id order like :1218-1232)
+        tsi += dt;
+        const bool due = active && tsi >= p.interp_update_period;
+        if (due) tsi = 0;
+        int any_due;
+        asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.or.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
+                     : "=r"(any_due)
+                     : "r"((int)due), "r"(p.house_threads)
+                     : "memory");
+        if (any_due) {
+          if (due) {
+            const double tg = (double)target;
+            s_ival[tid] = interp_eval<R>(p, ikey, (double)tt.x - tg, (double)tt.y - tg, (double)rec.x - tg, 0.0, 0.0);
+          }
+          house_sync(p.house_threads);
+          if (due && li == 0) {
+            double bsum = 0.0;
+            for (int i = 0; i < N; ++i) bsum = add_rn(bsum, s_ival[le * N + i]);
+            s_ival[p.hmax + le] = bsum;
+          }
+          house_sync(p.house_threads);
+          if (due) base_cur = s_ival[p.hmax + le];
+        }
+        if (sizeof(R) == 4) sig_new = fminf((float)ratio_r * ((float)base_cur * (float)rec.y), (float)maxp_r);
+        else sig_new = (R)fmin((double)ratio_r * (base_cur * (double)rec.y), (double)maxp_r);
+      }
       if (active) {
         // fp32 mode keeps the per-step arithmetic of the pipelined kernel (fp32 power sums are exact: integer-valued
         // watts), fp64 mode that of the generic kernel; reg_signal_penalty :244-247 with the OLD signal, weighting :364-372
@@ -269,7 +328,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
             } else {
               for (int w = 0; w < nparts; ++w) mx = fmax(mx, pmx[w]);
             }
-            const R sig = rec.y, d = sig - Ps;
+            const R sig = sig_new, d = sig - Ps;
             e_maxsq += mx * mx;
             e_max = fmax(e_max, mx);
             e_od += rec.x;
@@ -282,7 +341,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
         }
       }
       od_old = rec.x;
-      s_old = rec.y;
+      s_old = sig_new;
     }
     if (kMetrics) {
       acc_r += (double)b_r; acc_off += (double)b_off; acc_abs += (double)b_abs; acc_sq += (double)b_sq;
@@ -303,7 +362,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
     if (li == 0) {
       p.cluster_power[e] = (double)P;
       p.t_epoch[e] = p.t_epoch[e] + (int64_t)K * dt;
-      p.base_power[e] = p.avg_power_per_hvac * N;
+      if (kInterp) {
+        p.base_power[e] = base_cur;
+        p.time_since_interp[e] = tsi;
+        // the run's last signal in fp64 from the fp64 factor the record warp left behind
+        p.signal[e] = fmin(mul_rn(mul_rn(base_cur, s_ival[p.hmax + G + le]), p.artificial_ratio[e]), p.max_power[e]);
+      } else {
+        p.base_power[e] = p.avg_power_per_hvac * N;
+      }
     }
   }
   if (kMetrics) {
@@ -339,18 +405,23 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? 3 : 1) run_f
   }
 }
 
+template <typename R, int kMaxThreads, int kAct, bool kMetrics, bool kInterp>
+static cudaError_t launch_fused_k(const KernelParams& kp, const Geometry& g, size_t smem, cudaStream_t stream) {
+  cudaError_t err = cudaFuncSetAttribute(run_fused_kernel<R, kMaxThreads, kAct, kMetrics, kInterp>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
+  if (err != cudaSuccess) return err;
+  run_fused_kernel<R, kMaxThreads, kAct, kMetrics, kInterp><<<g.ctas, g.threads, smem, stream>>>(kp);
+  return cudaGetLastError();
+}
+
 template <typename R, int kMaxThreads, int kAct>
 static cudaError_t launch_fused_m(const KernelParams& kp, const Geometry& g, size_t smem, cudaStream_t stream) {
-  if (kp.metrics != nullptr) {
-    cudaError_t err = cudaFuncSetAttribute(run_fused_kernel<R, kMaxThreads, kAct, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    run_fused_kernel<R, kMaxThreads, kAct, true><<<g.ctas, g.threads, smem, stream>>>(kp);
-  } else {
-    cudaError_t err = cudaFuncSetAttribute(run_fused_kernel<R, kMaxThreads, kAct, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    run_fused_kernel<R, kMaxThreads, kAct, false><<<g.ctas, g.threads, smem, stream>>>(kp);
-  }
-  return cudaGetLastError();
+  const bool interp = kp.base_power_mode == MDR_BASE_INTERPOLATION;
+  if (kp.metrics != nullptr)
+    return interp ? launch_fused_k<R, kMaxThreads, kAct, true, true>(kp, g, smem, stream)
+                  : launch_fused_k<R, kMaxThreads, kAct, true, false>(kp, g, smem, stream);
+  return interp ? launch_fused_k<R, kMaxThreads, kAct, false, true>(kp, g, smem, stream)
+                : launch_fused_k<R, kMaxThreads, kAct, false, false>(kp, g, smem, stream);
 }
 
 template <typename R, int kAct>
@@ -362,8 +433,13 @@ static cudaError_t launch_fused_t(const KernelParams& kp, const Geometry& g, siz
 
 // plain steps that need nothing from the host between them (see run_fused_kernel)
 bool fused_eligible(const KernelParams& kp) {
+  // interpolated base power: every house is sampled (N <= interp_nb_agents), no solar gain (hour/date of the
+  // interpolation point are 0 then), and a signal shape that is linear in the base power
+  const bool base_ok = kp.base_power_mode == MDR_BASE_CONSTANT ||
+                       (kp.N <= kp.interp_nb_agents && !kp.solar && kp.signal_mode != MDR_SIG_REGULAR_STEPS &&
+                        kp.interp_table != nullptr && kp.interp_key != nullptr);
   return kp.is_reset == 0 && kp.obs == nullptr && (kp.action_source == MDR_ACT_BANGBANG || kp.action_source == MDR_ACT_RANDOM) &&
-         kp.base_power_mode == MDR_BASE_CONSTANT &&
+         base_ok &&
          kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.od_noise == nullptr && kp.signal_noise == nullptr &&
          (kp.signal_mode != MDR_SIG_PERLIN || kp.perlin_seed != nullptr);
 }
@@ -373,8 +449,10 @@ cudaError_t launch_fused(const KernelParams& kp_in, const Geometry& g, int preci
   KernelParams kp = kp_in;
   kp.n_fused = n_steps;
   const int rb = precision;
-  const FusedSmem L = fused_smem_layout(rb, g.envs_per_cta, g.part_stride, kp.metrics != nullptr);
+  const FusedSmem L = fused_smem_layout(rb, g.envs_per_cta, g.part_stride, kp.metrics != nullptr, g.hmax,
+                                        kp.base_power_mode == MDR_BASE_INTERPOLATION);
   kp.off_env = (int)L.off_rec; kp.off_pw = (int)L.off_part; kp.off_pen = (int)L.off_pmax; kp.off_val = (int)L.off_red;
+  kp.off_in = (int)L.off_interp;
   if (precision == MDR_F32)
     return kp.action_source == MDR_ACT_BANGBANG ? launch_fused_t<float, MDR_ACT_BANGBANG>(kp, g, L.total, stream)
                                                  : launch_fused_t<float, MDR_ACT_RANDOM>(kp, g, L.total, stream);

@@ -220,3 +220,67 @@ def test_greedy_myopic_on_device_vs_oracle(n_envs, n, signal):
     np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(rew.cpu().numpy(), o_rew, rtol=0, atol=1e-9)
     np.testing.assert_allclose(obs.cpu().numpy(), o_obs, rtol=0, atol=1e-9)
+
+
+def _interp_env(n_envs, n, precision, source, signal, temp_std=None, seed=5):
+    import mdr_b200
+    import golden_util as gu
+    cfg = _cfg(n, signal, temp_std=temp_std)
+    cfg["default_env_prop"]["power_grid_prop"]["base_power_mode"] = "interpolation"
+    flat = mdr_b200.FlatConfig(cfg)
+    pop = mdr_b200.synthetic_population(flat, n_envs, seed=seed)
+    env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, seed=seed, action_source=source, with_obs=False,
+                                        interp_table=gu.synthetic_table())
+    env.reset_tensor()
+    return cfg, flat, pop, env
+
+
+@pytest.mark.parametrize("precision,n_envs,n,source,signal", [
+    ("fp64", 5, 40, "bangbang", "perlin"), ("fp32", 200, 100, "bangbang", "perlin"), ("fp64", 3, 100, "random", "sinusoidals"),
+    ("fp32", 7, 13, "random", "flat")])
+def test_fused_with_interpolated_base_power_equals_single_steps(precision, n_envs, n, source, signal):
+    """Interpolated base power inside the fused kernel (refresh every 75 steps from the houses' state): 230 fused steps
+    (three refreshes, at different offsets for the two calls) == 230 single-step launches."""
+    import torch
+    _, _, _, a = _interp_env(n_envs, n, precision, source, signal)
+    _, _, _, b = _interp_env(n_envs, n, precision, source, signal)
+    a.enable_metrics()
+    a.run(100)
+    _, rew_a, p_a, s_a = a.run(130)
+    _, rew_b, p_b, s_b = _per_step(b, 230)
+    torch.cuda.synchronize()
+    assert torch.equal(a.hvac, b.hvac) and torch.equal(a.t_epoch, b.t_epoch) and torch.equal(p_a, p_b)
+    assert torch.equal(a.time_since_interp, b.time_since_interp)
+    tol = dict(rtol=0, atol=1e-9) if precision == "fp64" else dict(rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(a.temps, b.temps, **tol)
+    torch.testing.assert_close(rew_a, rew_b, **tol)
+    rs = 1e-12 if precision == "fp64" else 1e-5
+    torch.testing.assert_close(a.env["base_power"], b.env["base_power"], rtol=rs, atol=1e-6)
+    torch.testing.assert_close(s_a, s_b, rtol=rs, atol=1e-6)
+    assert float(a.metrics[:, 0].min()) == 230
+
+
+def test_fused_interpolation_fp64_vs_oracle():
+    import torch
+    import golden_util as gu
+    from oracle import mdr_oracle as orc
+    n_envs, n, k = 3, 31, 200
+    cfg, flat, pop, env = _interp_env(n_envs, n, "fp64", "bangbang", "sinusoidals", temp_std=0.0)
+    table = gu.synthetic_table()
+    oracle = orc.OracleEnv(cfg, {kk: v for kk, v in pop.items() if kk != "perlin_seed"},
+                           interp=orc.PowerInterp(table, gu.INTERP_GRID, gu.INTERP_KEYS))
+    for e in range(n_envs):
+        oracle.grid_step(e, orc.to_datetime(oracle.s["t_epoch"][e]), 0.0)
+    zeros = np.zeros(n_envs)
+    for _ in range(k):
+        act = (oracle.s["t_air"] > oracle.s["target"]).astype(np.uint8)
+        _, o_rew, o_p, o_s = oracle.step(act, zeros, zeros)
+    _, rew, p, s = env.run(k)
+    torch.cuda.synchronize()
+    assert np.array_equal(env.hvac_on.cpu().numpy(), oracle.s["on"])
+    assert np.array_equal(env.seconds_since_off.cpu().numpy(), oracle.s["sso"])
+    assert np.array_equal(p.cpu().numpy(), o_p)
+    np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(env.env["base_power"].cpu().numpy(), oracle.s["base_power"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(s.cpu().numpy(), o_s, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(rew.cpu().numpy(), o_rew, rtol=0, atol=1e-9)
