@@ -33,6 +33,11 @@ def comm_table(mode, n, nb_agents_comm, row_size=5, distance_comm=2, sampler=Non
             group.remove(i)
             rows.append(group)
         table = np.asarray(rows).reshape(n, -1)
+        if table.size and int(table.max()) >= n:
+            # reference quirk (:834): `base + nb_comm <= nb_agents` lets the last full group run one id past the end
+            # when base + nb_comm == nb_agents; the reference then dies with KeyError in make_cluster_obs_dict
+            # (:958, self.houses[id]).  Fail the same way, but at construction instead of at the first observation.
+            raise KeyError(int(table.max()))
     elif mode == "random_fixed":
         if sampler is None:
             raise ValueError("random_fixed needs a sampler")

@@ -139,7 +139,10 @@ class VecDemandResponseEnv:
 
     def set_comm_table(self, table):
         """int32 [N, C] shared by all envs, or [E, N, C] per env (random_fixed / random_sample)."""
-        t = torch.as_tensor(np.ascontiguousarray(np.asarray(table, dtype=np.int32))).to(self.device)
+        arr = np.ascontiguousarray(np.asarray(table, dtype=np.int32))
+        if arr.size and (int(arr.min()) < 0 or int(arr.max()) >= self.n_houses):
+            raise ValueError("comm table holds house ids outside [0, %d)" % self.n_houses)
+        t = torch.as_tensor(arr).to(self.device)
         if t.dim() == 3:
             if t.shape != (self.n_envs, self.n_houses, self.n_comm):
                 raise ValueError("per-env comm table must be [E, N, C]")

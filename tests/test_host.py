@@ -180,3 +180,17 @@ def test_default_config_equals_reference_config():
         assert mine[k] == cfg[k], k
     ref_grid = json.load(open(os.path.join(ref_stubs.REFERENCE_ROOT, "monteCarlo", "interp_parameters_dict.json")))
     assert ref_grid == mdr_b200.default_config.INTERP_GRID == gu.INTERP_GRID
+
+
+def test_closed_groups_overrun_fails_like_the_reference():
+    """env/MA_DemandResponse.py:834 admits a group that runs one id past the last house when base + nb_comm == nb_agents;
+    the reference then raises KeyError while building the first observation.  Here construction fails instead of a kernel
+    silently gathering a foreign message."""
+    import pytest
+    from mdr_b200.config_flatten import comm_table
+    with pytest.raises(KeyError):
+        comm_table("closed_groups", 9, 4)     # groups of 5: base 5 + 4 == 9
+    t = comm_table("closed_groups", 10, 4)    # fits exactly
+    assert t.shape == (10, 4) and int(t.max()) == 9
+    t = comm_table("closed_groups", 12, 3)    # SURVEY appendix A.3
+    assert list(t[11]) == [8, 9, 10]
