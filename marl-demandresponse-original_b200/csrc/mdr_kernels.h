@@ -19,6 +19,7 @@ struct KernelParams {
   int pro_batch;                                              // pipelined kernel: tiles the prologue warp produces per pass
   int n_tiles;                                                // pipelined kernel: number of G-env tiles
   int n_fused;                                                // fused multi-step kernel: steps of this launch
+  int precision;                                              // MDR_F32 / MDR_F64 (kernels that are not templated on it)
   int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
   unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)

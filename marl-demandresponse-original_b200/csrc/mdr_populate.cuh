@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) populate_kernel(const __grid_constant__ K
     const int dur = s.lockout_duration - s.lockout_noise + min(span - 1, (int)(u01(r5.z, r5.w) * span));
     lockout_dur[h] = dur;
     if (p.temps != nullptr) {
-      if (p.off_in == MDR_F32) reinterpret_cast<float2*>(p.temps)[h] = make_float2((float)t_air, (float)t_mass);
+      if (p.precision == MDR_F32) reinterpret_cast<float2*>(p.temps)[h] = make_float2((float)t_air, (float)t_mass);
       else reinterpret_cast<double2*>(p.temps)[h] = make_double2(t_air, t_mass);
     }
     p.hvac[h] = dur << 2;  // off, not locked out, seconds_since_off = lockout duration (:433)
@@ -110,7 +110,7 @@ cudaError_t launch_populate(const KernelParams& kp_in, const MdrPopulationSpec& 
                             double* cm, double* ca, double* hm, double* cap, double* target, double* deadband,
                             int32_t* lockout_dur, int precision, uint64_t draw_index, cudaStream_t stream) {
   KernelParams kp = kp_in;
-  kp.off_in = precision;  // (re-used as the precision tag: the kernel is not templated)
+  kp.precision = precision;
   const size_t smem = (size_t)kp.N * sizeof(double);
   populate_kernel<<<kp.E, 128, smem, stream>>>(kp, spec, env_mask, ua, cm, ca, hm, cap, target, deadband, lockout_dur, draw_index);
   return cudaGetLastError();

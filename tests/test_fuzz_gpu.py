@@ -93,3 +93,59 @@ def test_random_configuration_matches_oracle(case):
         np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], err_msg="t_air %d" % t, **tol)
         np.testing.assert_allclose(rew.cpu().numpy(), o_rew, err_msg="reward %d" % t, **tol)
         np.testing.assert_allclose(obs.cpu().numpy(), o_obs, err_msg="obs %d" % t, **tol)
+
+
+def _draw_fused(rng):
+    n = int(rng.choice([1, 3, 17, 32, 50, 64, 100, 150, 224, 400, 992]))
+    interp = bool(rng.random() < 0.4) and n <= 100
+    return dict(n=n, n_envs=int(rng.integers(1, 9)) if n <= 224 else int(rng.integers(1, 3)), interp=interp,
+                signal=str(rng.choice(["flat", "sinusoidals", "perlin"] + ([] if interp else ["regular_steps"]))),
+                source=str(rng.choice(["bangbang", "random"])), solar=bool(rng.random() < 0.3) and not interp,
+                metrics=bool(rng.random() < 0.5), precision=str(rng.choice(["fp64", "fp32"])),
+                k=int(rng.choice([1, 7, 32, 33, 90, 161])), seed=int(rng.integers(0, 10**6)))
+
+
+@pytest.mark.parametrize("case", [_draw_fused(np.random.default_rng(5000 + i)) for i in range(20)],
+                         ids=lambda c: "n%d_e%d_k%d_%s_%s%s%s" % (c["n"], c["n_envs"], c["k"], c["signal"][:4], c["precision"],
+                                                                   "_interp" if c["interp"] else "", "_m" if c["metrics"] else ""))
+def test_random_fused_run_equals_single_steps(case):
+    """The fused multi-step kernel on random shapes / modes / step counts (batch boundaries at 32, refresh boundaries at
+    75) against the same number of single-step launches."""
+    import os
+    import torch
+    import mdr_b200
+    c = case
+    cfg = mdr_b200.make_default_config()
+    ep = cfg["default_env_prop"]
+    ep["cluster_prop"]["nb_agents"] = c["n"]
+    ep["power_grid_prop"]["base_power_mode"] = "interpolation" if c["interp"] else "constant"
+    ep["power_grid_prop"]["signal_mode"] = c["signal"]
+    cfg["default_house_prop"]["solar_gain_bool"] = c["solar"]
+    flat = mdr_b200.FlatConfig(cfg)
+    pop = mdr_b200.synthetic_population(flat, c["n_envs"], seed=c["seed"])
+    table = gu.synthetic_table() if c["interp"] else None
+    mk = lambda: mdr_b200.VecDemandResponseEnv(cfg, pop, precision=c["precision"], seed=c["seed"], action_source=c["source"],
+                                               with_obs=False, interp_table=table)
+    a, b = mk(), mk()
+    a.reset_tensor()
+    b.reset_tensor()
+    if c["metrics"]:
+        a.enable_metrics()
+    _, rew_a, p_a, s_a = a.run(c["k"])
+    os.environ["MDR_NO_FUSED"] = "1"
+    try:
+        for _ in range(c["k"]):
+            _, rew_b, p_b, s_b = b.step_tensor(None)
+    finally:
+        os.environ.pop("MDR_NO_FUSED", None)
+    torch.cuda.synchronize()
+    assert torch.equal(a.hvac, b.hvac) and torch.equal(a.t_epoch, b.t_epoch) and torch.equal(p_a, p_b)
+    assert torch.equal(a.time_since_interp, b.time_since_interp)
+    tol = dict(rtol=0, atol=1e-9) if c["precision"] == "fp64" else dict(rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(a.temps, b.temps, **tol)
+    torch.testing.assert_close(rew_a, rew_b, **tol)
+    rs = 1e-12 if c["precision"] == "fp64" else 1e-5
+    torch.testing.assert_close(s_a, s_b, rtol=rs, atol=1e-6)
+    torch.testing.assert_close(a.env["od_temp"], b.env["od_temp"], rtol=0, atol=1e-9)
+    if c["metrics"]:
+        assert float(a.metrics[:, 0].min()) == c["k"] and torch.isfinite(a.metrics).all()
