@@ -143,6 +143,8 @@ class MADemandResponseEnv:
         self._tsi = flat.interp_update_period + 1
         self._static = {k: np.asarray(pop[k][0]) for k in ("ua", "cm", "ca", "hm", "cap", "target", "deadband",
                                                             "lockout_dur")}
+        self._static_lists = {k: (v.astype(np.int64) if k == "lockout_dur" else v.astype(np.float64)).tolist()
+                              for k, v in self._static.items()}
         self._static.update(max_power=float(pop["max_power"][0]), phase=float(pop["phase"][0]),
                             artificial_ratio=float(pop["artificial_ratio"][0]))
         # PowerGrid.step(start_datetime) at :133 -- interpolation ids are drawn first (:1214), then perlin
@@ -188,14 +190,19 @@ class MADemandResponseEnv:
                 self._comm_host = comm[0]
         return comm, keep
 
+    _ENV_SCALARS = ("od_temp", "signal", "cluster_power", "base_power", "solar_gain")
+
     def _pull_state(self):
+        """Host copy of the state the dict API exposes: three device-to-host copies (temperatures, packed HVAC state,
+        the five per-env scalars gathered into one tensor)."""
+        import torch
         v = self._vec
-        temps = v.temps[0].cpu().numpy().astype(np.float64)
+        temps = v.temps[0].double().cpu().numpy()
         hv = v.hvac[0].cpu().numpy()
+        scal = torch.stack([v.env[k][0] for k in self._ENV_SCALARS]).cpu().tolist()
         h = dict(self._static)
         h.update(t_air=temps[:, 0], t_mass=temps[:, 1], on=hv & 1, lockout=(hv >> 1) & 1, sso=hv >> 2)
-        for k in ("od_temp", "signal", "cluster_power", "base_power", "solar_gain"):
-            h[k] = float(v.env[k][0].item())
+        h.update(zip(self._ENV_SCALARS, scal))
         self._host = h
 
     # ------------------------------------------------------------------
@@ -226,55 +233,58 @@ class MADemandResponseEnv:
         if self._perlin is not None:
             self.power_grid.nb_steps += 1
         obs_dict = self._make_obs_dict()
-        rewards_dict = {i: float(reward[0, i]) for i in self.agent_ids}
-        dones_dict = {i: False for i in self.agent_ids}
+        rewards_dict = dict(zip(self.agent_ids, reward[0].astype(np.float64).tolist()))
+        dones_dict = dict.fromkeys(self.agent_ids, False)
         info_dict = {"cluster_hvac_power": float(power[0])}
         return obs_dict, rewards_dict, dones_dict, info_dict
 
+    _OBS_KEYS = ("OD_temp", "datetime", "house_temp", "house_mass_temp", "hvac_turned_on", "hvac_seconds_since_off",
+                 "hvac_lockout", "house_target_temp", "house_deadband", "house_Ua", "house_Cm", "house_Ca", "house_Hm",
+                 "house_solar_gain", "hvac_COP", "hvac_cooling_capacity", "hvac_latent_cooling_fraction",
+                 "hvac_lockout_duration", "message", "reg_signal", "cluster_hvac_power")
+
     def _make_obs_dict(self):
-        """make_cluster_obs_dict + merge_cluster_powergrid_obs (:904-1003, :212-232) from host copies."""
+        """make_cluster_obs_dict + merge_cluster_powergrid_obs (:904-1003, :212-232) from host copies.  Same keys, key
+        order and python types as the reference; built column-wise (`tolist` + `zip`) because at this point the python
+        dictionaries, not the step, are what a drop-in user waits for.  A sender's message dict is built once and
+        shared by its receivers (the reference builds equal copies; nothing downstream mutates them)."""
+        from itertools import repeat
         h, flat = self._host, self.flat
         mp = self.default_env_prop["message_properties"]
-        p_max = h["cap"] / flat.hvac_cop
-        obs = {}
-        comm = self._comm_host
-        keep = self._msg_keep
-        for i in self.agent_ids:
-            d = {
-                "OD_temp": h["od_temp"], "datetime": self.datetime,
-                "house_temp": float(h["t_air"][i]), "house_mass_temp": float(h["t_mass"][i]),
-                "hvac_turned_on": bool(h["on"][i]), "hvac_seconds_since_off": int(h["sso"][i]),
-                "hvac_lockout": bool(h["lockout"][i]),
-                "house_target_temp": float(h["target"][i]), "house_deadband": float(h["deadband"][i]),
-                "house_Ua": float(h["ua"][i]), "house_Cm": float(h["cm"][i]), "house_Ca": float(h["ca"][i]),
-                "house_Hm": float(h["hm"][i]), "house_solar_gain": h["solar_gain"],
-                "hvac_COP": flat.hvac_cop, "hvac_cooling_capacity": float(h["cap"][i]),
-                "hvac_latent_cooling_fraction": flat.hvac_latent, "hvac_lockout_duration": int(h["lockout_dur"][i]),
-            }
-            msgs = []
-            for k in range(flat.n_comm):
-                j = int(comm[i][k])
-                ok = True if keep is None else bool(keep[0, i, k])
-                m = {
-                    "current_temp_diff_to_target": float(h["t_air"][j] - h["target"][j]) if ok else 0,
-                    "hvac_seconds_since_off": int(h["sso"][j]) if ok else 0,
-                    "hvac_curr_consumption": (float(p_max[j]) if h["on"][j] else 0) if ok else 0,
-                    "hvac_max_consumption": float(p_max[j]) if ok else 0,
-                    "hvac_lockout_duration": int(h["lockout_dur"][j]) if ok else 0,
-                }
-                if mp["thermal"]:
-                    m.update(house_Ua=float(h["ua"][j]) if ok else 0, house_Cm=float(h["cm"][j]) if ok else 0,
-                             house_Ca=float(h["ca"][j]) if ok else 0, house_Hm=float(h["hm"][j]) if ok else 0)
-                if mp["hvac"]:
-                    m.update(hvac_COP=flat.hvac_cop if ok else 0,
-                             hvac_cooling_capacity=float(h["cap"][j]) if ok else 0,
-                             hvac_latent_cooling_fraction=flat.hvac_latent if ok else 0)
-                msgs.append(m)
-            d["message"] = msgs
-            d["reg_signal"] = h["signal"]
-            d["cluster_hvac_power"] = h["cluster_power"]
-            obs[i] = d
-        return obs
+        n, c = flat.n_houses, flat.n_comm
+        p_max = (h["cap"] / flat.hvac_cop)
+        t_air, target, sso, on = h["t_air"], h["target"], h["sso"], h["on"]
+        # one message per sender (SingleHouse.message :624-662)
+        cols = [("current_temp_diff_to_target", (t_air - target).tolist()), ("hvac_seconds_since_off", sso.tolist()),
+                ("hvac_curr_consumption", [pm if o else 0 for pm, o in zip(p_max.tolist(), on.tolist())]),
+                ("hvac_max_consumption", p_max.tolist()), ("hvac_lockout_duration", h["lockout_dur"].tolist())]
+        if mp["thermal"]:
+            cols += [("house_Ua", h["ua"].tolist()), ("house_Cm", h["cm"].tolist()), ("house_Ca", h["ca"].tolist()),
+                     ("house_Hm", h["hm"].tolist())]
+        if mp["hvac"]:
+            cols += [("hvac_COP", [flat.hvac_cop] * n), ("hvac_cooling_capacity", h["cap"].tolist()),
+                     ("hvac_latent_cooling_fraction", [flat.hvac_latent] * n)]
+        mkeys = [k for k, _ in cols]
+        sent = [dict(zip(mkeys, row)) for row in zip(*(v for _, v in cols))]
+        messages = [[]] * n
+        if c > 0:
+            comm = self._comm_host
+            comm_rows = comm.tolist() if hasattr(comm, "tolist") else [list(r) for r in comm]
+            keep = self._msg_keep
+            if keep is None:
+                messages = [[sent[j] for j in row[:c]] for row in comm_rows]
+            else:
+                dropped = dict.fromkeys(mkeys, 0)  # np.random.rand() <= comm_defect_prob, :992-1001
+                keep_rows = keep[0].tolist()
+                messages = [[sent[j] if ok else dropped for j, ok in zip(row[:c], krow)] for row, krow in zip(comm_rows, keep_rows)]
+        columns = (repeat(h["od_temp"]), repeat(self.datetime), t_air.tolist(), h["t_mass"].tolist(),
+                   [bool(x) for x in on.tolist()], sso.tolist(), [bool(x) for x in h["lockout"].tolist()],
+                   self._static_lists["target"], self._static_lists["deadband"], self._static_lists["ua"],
+                   self._static_lists["cm"], self._static_lists["ca"], self._static_lists["hm"], repeat(h["solar_gain"]),
+                   repeat(flat.hvac_cop), self._static_lists["cap"], repeat(flat.hvac_latent),
+                   self._static_lists["lockout_dur"], messages, repeat(h["signal"]), repeat(h["cluster_power"]))
+        keys = self._OBS_KEYS
+        return {i: dict(zip(keys, row)) for i, row in zip(self.agent_ids, zip(*columns))}
 
     # tensor view of the last observation: the normStateDict matrix [N, F] on the device
     def obs_tensor(self):
