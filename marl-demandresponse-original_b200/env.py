@@ -193,13 +193,22 @@ class MADemandResponseEnv:
     _ENV_SCALARS = ("od_temp", "signal", "cluster_power", "base_power", "solar_gain")
 
     def _pull_state(self):
-        """Host copy of the state the dict API exposes: three device-to-host copies (temperatures, packed HVAC state,
-        the five per-env scalars gathered into one tensor)."""
+        """Host copy of the state the dict API exposes: three asynchronous device-to-host copies into pinned memory
+        (temperatures, packed HVAC state, the five per-env scalars gathered into one tensor) and one synchronisation."""
         import torch
         v = self._vec
-        temps = v.temps[0].double().cpu().numpy()
-        hv = v.hvac[0].cpu().numpy()
-        scal = torch.stack([v.env[k][0] for k in self._ENV_SCALARS]).cpu().tolist()
+        if getattr(self, "_pin", None) is None or self._pin[0].shape[0] != v.n_houses:
+            self._pin = (torch.empty(v.n_houses, 2, dtype=v.dtype, pin_memory=True),
+                         torch.empty(v.n_houses, dtype=torch.int32, pin_memory=True),
+                         torch.empty(len(self._ENV_SCALARS), dtype=torch.float64, pin_memory=True))
+        pt, ph, ps = self._pin
+        pt.copy_(v.temps[0], non_blocking=True)
+        ph.copy_(v.hvac[0], non_blocking=True)
+        ps.copy_(torch.stack([v.env[k][0] for k in self._ENV_SCALARS]), non_blocking=True)
+        torch.cuda.current_stream(v.device).synchronize()  # one synchronisation for the three copies
+        temps = pt.numpy().astype(np.float64)
+        hv = ph.numpy().copy()
+        scal = ps.tolist()
         h = dict(self._static)
         h.update(t_air=temps[:, 0], t_mass=temps[:, 1], on=hv & 1, lockout=(hv >> 1) & 1, sso=hv >> 2)
         h.update(zip(self._ENV_SCALARS, scal))
@@ -228,7 +237,7 @@ class MADemandResponseEnv:
         ids, noise = self._grid_draws(self.datetime)                # PowerGrid.step :1236-1316
         self._msg_keep, self._msg_comm = keep, comm
         _, reward, power, _ = self._vec.step_host(actions[None], od_noise=od_noise, signal_noise=noise,
-                                                  interp_ids=ids, msg_keep=keep, comm=comm)
+                                                  interp_ids=ids, msg_keep=keep, comm=comm, want_obs=False)
         self._pull_state()
         if self._perlin is not None:
             self.power_grid.nb_steps += 1
@@ -294,9 +303,10 @@ class MADemandResponseEnv:
         new = object.__new__(type(self))
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("cluster", "power_grid"):
+            if k in ("cluster", "power_grid", "_pin"):
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
+        new._pin = None  # pinned staging buffers are per object
         new.cluster = _ClusterView(new)
         new.power_grid = _PowerGridView(new)
         return new

@@ -378,7 +378,8 @@ class VecDemandResponseEnv:
             "rmse_signal_per_agent": torch.sqrt(col["sum_sq_signal_error"] / steps) / n,
         }
 
-    def step_host(self, host_actions, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None, comm=None):
+    def step_host(self, host_actions, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None, comm=None,
+                  want_obs=True):
         """End-to-end step with HOST buffers (what the dict API and the e2e benchmark call):
         H2D of the uint8 actions, the fused step, D2H of obs / reward / power / signal into pinned
         host memory, stream synchronised.  Returns numpy views of the pinned buffers."""
@@ -395,11 +396,19 @@ class VecDemandResponseEnv:
         pb["actions"].numpy()[...] = np.asarray(host_actions).reshape(e, n) != 0
         self._set_inputs(None, od_noise, signal_noise, interp_ids, msg_keep, comm)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.mdr_step_host(*self._refs, p(pb["actions"]), p(pb["obs"]), p(pb["reward"]),
-                                              p(pb["power"]), p(pb["signal"]), self._stream()), "mdr_step_host")
+        skip_obs = not want_obs and self.obs is not None
+        if skip_obs:  # the caller builds its observation from the state (dict API): no row assembly, no obs D2H
+            self.out_s.obs = None
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mdr_step_host(*self._refs, p(pb["actions"]), None if skip_obs else p(pb["obs"]),
+                                                  p(pb["reward"]), p(pb["power"]), p(pb["signal"]), self._stream()),
+                           "mdr_step_host")
+        finally:
+            if skip_obs:
+                self.out_s.obs = C.c_void_p(self.obs.data_ptr())
         self.step_index += 1
-        return (None if pb["obs"] is None else pb["obs"].numpy(), pb["reward"].numpy(), pb["power"].numpy(),
+        return (None if pb["obs"] is None or skip_obs else pb["obs"].numpy(), pb["reward"].numpy(), pb["power"].numpy(),
                 pb["signal"].numpy())
 
     # ------------------------------------------------------------------ views of the state
