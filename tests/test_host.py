@@ -194,3 +194,20 @@ def test_closed_groups_overrun_fails_like_the_reference():
     assert t.shape == (10, 4) and int(t.max()) == 9
     t = comm_table("closed_groups", 12, 3)
     assert list(t[11]) == [8, 9, 10]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`python bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): one JSON line with the
+    contract's keys, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "30", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "house_steps_per_sec" and line["unit"] == "house-steps/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["steps"] == 30
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
