@@ -175,7 +175,20 @@ def gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if distributed:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on STDOUT when the first communicator is created; the contract is ONE JSON line
+        # there, so stdout is pointed at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     w = WORKLOADS[args.workload]
     E = args.envs or w["envs"]
     N = w["houses"]
