@@ -211,3 +211,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_population_spec_mirrors_the_config_entries():
+    """MdrPopulationSpec (device-side population draw) carries exactly the entries utils.applyPropertyNoise reads."""
+    import pytest
+    cfg = mdr_b200.make_default_config()
+    cfg["noise_house_prop"]["noise_mode"] = "big_noise"
+    cfg["noise_hvac_prop"]["noise_mode"] = "big_noise"
+    cfg["default_hvac_prop"]["lockout_noise"] = 8
+    flat = mdr_b200.FlatConfig(cfg)
+    sp = mdr_b200.population_spec(flat)
+    nh = cfg["noise_house_prop"]["noise_parameters"]["big_noise"]
+    hd, vd = cfg["default_house_prop"], cfg["default_hvac_prop"]
+    assert (sp.std_start_temp, sp.std_target_temp) == (nh["std_start_temp"], nh["std_target_temp"])
+    assert (sp.factor_thermo_low, sp.factor_thermo_high) == (nh["factor_thermo_low"], nh["factor_thermo_high"])
+    assert (sp.ua, sp.cm, sp.ca, sp.hm) == (hd["Ua"], hd["Cm"], hd["Ca"], hd["Hm"])
+    caps = cfg["noise_hvac_prop"]["noise_parameters"]["big_noise"]["cooling_capacity_list"][vd["cooling_capacity"]]
+    assert sp.n_cap == len(caps) and [sp.cap_list[i] for i in range(sp.n_cap)] == [float(c) for c in caps]
+    assert (sp.lockout_duration, sp.lockout_noise) == (vd["lockout_duration"], 8)
+    assert sp.random_start == 1 and sp.interp_update_period == flat.interp_update_period
+    from mdr_b200.config_flatten import epoch_seconds
+    assert sp.start_epoch == epoch_seconds(flat.start_datetime)
+    cfg["default_hvac_prop"]["lockout_noise"] = vd["lockout_duration"] + 1   # HVAC.__init__ :438-461
+    with pytest.raises(ValueError):
+        mdr_b200.population_spec(mdr_b200.FlatConfig(cfg))
