@@ -254,8 +254,9 @@ int mdr_reset(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs
 int mdr_observe(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
                 const MdrStepInputs *in, const MdrOutputs *out, void *stream);
 
-/* MADemandResponseEnv.step (:174-210) for every env of the shard, `n_steps` times (n_steps > 1
-   requires on-device action/noise sources).  One kernel launch per step -- except that steps which need
+/* MADemandResponseEnv.step (:174-210) for every env of the shard, `n_steps` times.  n_steps > 1 is meant for
+   on-device action/noise sources; with MDR_ACT_ARRAY or replayed noise arrays the SAME arrays are applied at every
+   one of the n_steps steps.  One kernel launch per step -- except that steps which need
    nothing from the host between them (on-device action source, no replayed noise, individual_L2 penalty,
    out->obs == NULL, constant base power -- or interpolated base power with n_houses <= interp_nb_agents, no
    solar gain and a signal mode other than regular_steps) run as ONE fused launch with the house state in registers
