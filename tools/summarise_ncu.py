@@ -51,6 +51,8 @@ if key:
     tpath = os.path.join(os.path.dirname(out), "traffic.json")
     t = json.load(open(tpath)) if os.path.isfile(tpath) else {}
     t[key] = tr
-    t["source"] = "%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches of the step kernel)" % (os.path.basename(out), len(data))
+    t.pop("source", None)
+    t.setdefault("sources", {})[key] = ("%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches "
+                                        "of the step kernel)" % (os.path.basename(out), len(data)))
     json.dump(t, open(tpath, "w"), indent=1)
 print("wrote", out)
