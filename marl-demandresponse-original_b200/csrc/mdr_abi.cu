@@ -339,7 +339,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   k.rows_per_pass = g.rows_per_pass;
   k.div_magic = (unsigned)(4294967296ull / (unsigned)cfg->n_houses) + 1u;
   {
-    int L = 16;  // 2*nb_octaves + 1 = 11 Philox draws per env in production mode
+    int L = 16;  // nb_octaves + 1 items per env in production mode
     while (L > 1 && L * g.envs_per_cta > 32) L >>= 1;
     k.pro_lanes = L;
   }

@@ -131,6 +131,8 @@ __device__ __forceinline__ double solar_gain(const Calendar& c, double window_ar
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double perlin_fade(double t) { return t * t * t * (t * (t * 6.0 - 15.0) + 10.0); }
 
+__device__ __forceinline__ float perlin_fade_f(float t) { return t * t * t * (t * (t * 6.0f - 15.0f) + 10.0f); }
+
 // Lattice gradient g_o(i) in (-1, 1): a pure function of (lattice point, octave, env key).  A two-round
 // multiply-xorshift integer hash ("lowbias32" constants) instead of a Philox block: the prologue warp evaluates
 // 2 * nb_octaves of these per env and step on its critical path, and a noise texture needs decorrelation, not a
@@ -143,6 +145,21 @@ __device__ __forceinline__ float perlin_gradient(int lattice, int octave, uint64
   x *= 0x846ca68bu;
   x ^= x >> 16;
   return 2.0f * (((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f)) - 1.0f;
+}
+
+// One octave of utils.Perlin.calculate_noise (utils.py:1247-1253) at position x = t / period: both lattice corners
+// of PerlinNoise(octaves = 2^j * octaves_step), weighted 1 / 2^j (last octave: 1 / (2^nb - 1)).  One fp64 multiply and
+// floor per octave, the rest in fp32 (the value is a noise texture; the per-octave result is the unit both the
+// pipelined/generic prologue and the fused kernel's record warp sum in fp64, so they agree to the last bit or two).
+__device__ __forceinline__ float perlin_octave(double x, int j, int nb, int octaves_step, uint64_t key) {
+  const double xo = x * (double)((1 << j) * octaves_step);
+  const double fl = floor(xo);
+  const float d0 = (float)(xo - fl);  // distance to the left corner, [0, 1); to the right corner: d0 - 1
+  const int i0 = (int)fl;
+  const float v = perlin_fade_f(1.0f - d0) * perlin_gradient(i0, j, key) * d0 +
+                  perlin_fade_f(d0) * perlin_gradient(i0 + 1, j, key) * (d0 - 1.0f);
+  const float wgt = j == nb - 1 ? 1.0f / (float)((1 << nb) - 1) : 1.0f / (float)(1 << j);
+  return v * wgt;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -43,19 +43,8 @@ __device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32
     const int nb = p.perlin_nb_octaves;
     const double x = (double)cal.sod * p.inv_perlin_period;
     const uint64_t pkey = p.seed ^ (uint64_t)__double_as_longlong(p.perlin_seed[e2]);
-    // same association as the 16-lane butterfly of env_prologue is not reproducible with one lane; the
-    // terms are summed in draw order (difference ~1 ulp of a value that is replayed in parity tests)
-    for (int d = 0; d < 2 * nb; ++d) {
-      const int j = d >> 1, corner = d & 1;
-      const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
-      const double fl = floor(xo);
-      const double dist = xo - (fl + corner);
-      const float fd = 1.0f - fabsf((float)dist);
-      const float fade = fd * fd * fd * (fd * (fd * 6.0f - 15.0f) + 10.0f);
-      const float g = perlin_gradient((int)fl + corner, j, pkey);
-      const float wgt = j == nb - 1 ? 1.0f / (float)((1 << nb) - 1) : 1.0f / (float)(1 << j);
-      sig_noise += (double)(fade * g * wgt) * dist;
-    }
+    // (the 16-lane butterfly of env_prologue sums the same per-octave values in another order: ~1 ulp in fp64)
+    for (int j = 0; j < nb; ++j) sig_noise += (double)perlin_octave(x, j, nb, p.perlin_octaves_step, pkey);
   }
   const double od_noise =
       p.temp_std * normal_from(philox4x32((uint32_t)e2, (uint32_t)step_index, (uint32_t)(step_index >> 32), STREAM_OD, p.seed));

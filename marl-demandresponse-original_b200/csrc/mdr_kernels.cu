@@ -260,25 +260,17 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
   Calendar cal = calendar_time(t);
   if (p.solar || (p.state_flags & MDR_STATE_DAY)) calendar_date(cal);
   if (draw_od || draw_perlin) {  // warp-uniform
-    // utils.Perlin.calculate_noise (utils.py:1247-1253) with hashed lattice gradients: draw d < 2*nb is
-    // lattice corner (d & 1) of octave (d >> 1); the last draw is the outdoor-temperature normal
+    // utils.Perlin.calculate_noise (utils.py:1247-1253) with hashed lattice gradients: item d < nb is octave d
+    // (both lattice corners, see perlin_octave); the last item is the outdoor-temperature normal
     const int nb = p.perlin_nb_octaves;
-    const int n_perlin = draw_perlin ? 2 * nb : 0;
+    const int n_perlin = draw_perlin ? nb : 0;
     const int n_draws = n_perlin + (draw_od ? 1 : 0);
     const double x = (double)cal.sod * p.inv_perlin_period;  // time.mktime(...) % 86400 with TZ=UTC, :1297
     const uint64_t pkey = draw_perlin ? p.seed ^ (uint64_t)__double_as_longlong(p.perlin_seed[e2]) : 0;
     double terms = 0.0, normal = 0.0;
     for (int d = sub; d < n_draws; d += L) {
       if (d < n_perlin) {
-        const int j = d >> 1, corner = d & 1;
-        const double xo = x * (double)((1 << j) * p.perlin_octaves_step);
-        const double fl = floor(xo);
-        const double dist = xo - (fl + corner);
-        const float fd = 1.0f - fabsf((float)dist);
-        const float fade = fd * fd * fd * (fd * (fd * 6.0f - 15.0f) + 10.0f);
-        const float g = perlin_gradient((int)fl + corner, j, pkey);
-        const float wgt = j == nb - 1 ? 1.0f / (float)((1 << nb) - 1) : 1.0f / (float)(1 << j);
-        terms += (double)(fade * g * wgt) * dist;
+        terms += (double)perlin_octave(x, d, nb, p.perlin_octaves_step, pkey);
       } else {
         normal = normal_from(philox4x32((uint32_t)e2, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_OD,
                                         p.seed));

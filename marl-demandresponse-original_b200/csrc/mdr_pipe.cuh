@@ -112,7 +112,7 @@ __device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B
   const int ring_shift = 31 - __clz(ring);
   const int lane = threadIdx.x & 31;
   const int lanes_per_tile = 32 / B;
-  int L = 16;  // lanes cooperating on one env (2 * nb_octaves + 1 = 11 Philox draws per env)
+  int L = 16;  // lanes cooperating on one env (nb_octaves perlin octaves + 1 Philox normal per env)
   while (L > 1 && L * p.G > lanes_per_tile) L >>= 1;
   const int groups = lanes_per_tile / L;  // envs of a tile processed at once (>= 1: G * pro_batch <= 32)
   const int tlane = lane & (lanes_per_tile - 1);
