@@ -238,7 +238,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   __syncthreads();
   if (warp >= p.house_warps) {
     asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
-    const int B = p.pro_batch;
+    // tiles per pass: pro_batch, but not more than this launch gives a CTA (a small problem should spend its lanes
+    // on the envs of tiles that exist, not on absent ones)
+    int B = p.pro_batch;
+    while (B > 1 && (B >> 1) * (int)gridDim.x >= p.n_tiles) B >>= 1;
     for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
     return;
   }
