@@ -10,8 +10,10 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every device buffer is allocated by the caller (torch,
- *     cudaMalloc, ...) on `MdrConfig.device`; the library never allocates, frees or keeps
- *     global state, and it never synchronises the stream except in the *_host entry points;
+ *     cudaMalloc, ...) on `MdrConfig.device`; the library never allocates or frees device memory and never
+ *     synchronises the stream except in the *_host entry points.  The only process-wide state is a
+ *     mutex-protected cache of per-device launch attributes (occupancy, opt-in shared memory) and the
+ *     tuning environment variables MDR_TARGET_THREADS / MDR_PRO_BATCH, read once at first use;
  *   - every function returns an MdrStatus (0 = OK, negative = error) and never throws/prints;
  *   - "real" is float when MdrConfig.precision == MDR_F32 and double when == MDR_F64;
  *   - per-house arrays are [n_envs * n_houses], env-major (house h of env e at e*n_houses+h),
@@ -28,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MDR_ABI_VERSION 9
+#define MDR_ABI_VERSION 10
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
@@ -127,7 +129,18 @@ typedef struct MdrConfig {
   const void *l2_window_base;
   uint64_t l2_window_bytes;
   double l2_hit_ratio;
+  /* Launch options (0 = defaults): MDR_FLAG_* bitmask, and a cap on the CTAs of the persistent pipelined kernel
+     (0 = SMs x resident CTAs; tests use a small cap so that every CTA walks many tiles). */
+  int32_t flags;
+  int32_t max_ctas;
 } MdrConfig;
+
+/* MdrConfig.flags */
+enum {
+  MDR_FLAG_NO_PIPELINE = 1, /* never take the persistent pipelined kernel (generic kernel instead) */
+  MDR_FLAG_NO_FUSED = 2,    /* never take the fused multi-step kernel (one launch per step instead) */
+  MDR_FLAG_NO_PDL = 4       /* launch without programmatic dependent launch */
+};
 
 /* Per-house struct-of-arrays.  Packed vectors keep every access a coalesced 8/16-byte load. */
 typedef struct MdrHouses {

@@ -5,7 +5,7 @@ import os
 
 from . import build as _build
 
-MDR_ABI_VERSION = 9
+MDR_ABI_VERSION = 10
 MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
@@ -15,6 +15,7 @@ PEN = {"individual_L2": 0, "common_L2": 1, "common_max": 2, "mixture": 3}
 BASE = {"constant": 0, "interpolation": 1}
 SIG_FLAT, SIG_SINUSOIDALS, SIG_REGULAR_STEPS, SIG_PERLIN = 0, 1, 2, 3
 ACT = {"array": 0, "bangbang": 1, "random": 2, "greedy": 3}
+FLAG_NO_PIPELINE, FLAG_NO_FUSED, FLAG_NO_PDL = 1, 2, 4
 METRIC_NAMES = ("steps", "sum_mean_reward", "sum_mean_temp_offset", "sum_mean_temp_error", "sum_sq_temp_error",
                 "sum_sq_max_temp_error", "max_temp_error", "sum_od_temp", "sum_signal", "sum_consumption",
                 "sum_signal_offset", "sum_signal_error", "sum_sq_signal_error")
@@ -39,7 +40,8 @@ class MdrConfig(C.Structure):
         + [(n, _f64) for n in ("steps_amplitude_per_hvac", "steps_period", "perlin_amplitude", "perlin_period",
                                "comm_defect_prob")]
         + [("interp_dims", _i32 * INTERP_DIMS), ("interp_axes", (_f64 * INTERP_MAX_AXIS) * INTERP_DIMS),
-           ("seed", C.c_uint64), ("l2_window_base", _vp), ("l2_window_bytes", C.c_uint64), ("l2_hit_ratio", _f64)]
+           ("seed", C.c_uint64), ("l2_window_base", _vp), ("l2_window_bytes", C.c_uint64), ("l2_hit_ratio", _f64),
+           ("flags", _i32), ("max_ctas", _i32)]
     )
 
 
@@ -89,11 +91,18 @@ def load(build_if_missing: bool = True):
         return _lib
     path = os.environ.get("MDR_LIB_PATH") or _build.LIB_PATH  # override: A/B-testing a differently built library
     if path == _build.LIB_PATH and build_if_missing and _build.is_stale():
+        # build() serialises concurrent builders (torchrun ranks on a fresh clone) with a file lock and publishes
+        # the library with an atomic rename, so no rank can dlopen a half-written file
         try:
             _build.build()
-        except Exception as exc:  # no nvcc on this box: use the shipped .so if there is one
+        except _build.NvccMissing as exc:  # no compiler on this box: the shipped .so is all there is
             if not os.path.isfile(path):
                 raise MdrError("libmdr_b200.so is missing and could not be built: %s" % exc)
+            import warnings
+            warnings.warn("libmdr_b200.so is older than its sources and nvcc is not available to rebuild it; "
+                          "loading the existing library (the ABI version is still checked)", RuntimeWarning)
+        except Exception as exc:  # sources are newer and the build FAILED: never run a stale binary silently
+            raise MdrError("libmdr_b200.so is stale and rebuilding it failed: %s" % exc)
     if not os.path.isfile(path):
         raise MdrError("CUDA extension %s not found; run `python __graft_entry__.py` (build) first. "
                        "There is no CPU fallback." % path)

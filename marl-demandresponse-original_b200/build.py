@@ -1,4 +1,5 @@
 """Builds csrc/libmdr_b200.so for sm_100a with nvcc (in-tree, so the .so travels to the GPU box)."""
+import fcntl
 import os
 import shutil
 import subprocess
@@ -12,11 +13,15 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC"]
 
 
+class NvccMissing(RuntimeError):
+    pass
+
+
 def find_nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.isfile(cand):
             return cand
-    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+    raise NvccMissing("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
 def is_stale() -> bool:
@@ -27,15 +32,29 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles into a temporary file and renames it over LIB_PATH, under an exclusive file lock: concurrent
+    callers (one per torchrun rank) build once, and nobody can load a partially written library."""
     if not force and not is_stale():
         return LIB_PATH
-    extra = os.environ.get("MDR_NVCC_EXTRA", "").split()  # e.g. -DMDR_BLOCKS_256=4 for tuning experiments
-    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + list(SOURCES)
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
-    if verbose:
-        print(res.stderr)
+    nvcc = find_nvcc()
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while we waited for the lock
+                return LIB_PATH
+            extra = os.environ.get("MDR_NVCC_EXTRA", "").split()  # e.g. -DMDR_BLOCKS_256=4 for tuning experiments
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + list(SOURCES)
+            res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -1,6 +1,7 @@
 // C ABI of the step path (include/mdr_b200.h): argument validation, launch geometry, launches,
-// error mapping.  No allocation, no global mutable state besides a per-device "attribute set"
-// latch inside the launcher, no stream synchronisation except in mdr_step_host.
+// error mapping.  No device allocation; the only process-wide state is the launchers' mutex/atomic-protected
+// per-device attribute caches and two tuning environment variables read once; no stream synchronisation
+// except in the *_host entry points.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -83,8 +84,11 @@ static void fill_config(KernelParams& k, const MdrConfig* c);
 static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool need_met = false) {
   const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
   if (N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
-  const char* tt_env = getenv("MDR_TARGET_THREADS");  // tuning knob: house threads per CTA
-  const int target_threads = tt_env ? atoi(tt_env) : 224;  // + 32 for the prologue warp = 256
+  static const int target_threads = [] {  // tuning knob (house threads per CTA), read once
+    const char* s = getenv("MDR_TARGET_THREADS");
+    const int v = s ? atoi(s) : 0;
+    return v >= 32 && v <= 992 ? v : 224;  // + 32 for the prologue warp = 256
+  }();
   int gmax = target_threads / N;
   if (gmax < 1) gmax = 1;
   if (gmax > E) gmax = E;
@@ -132,6 +136,8 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
   g->l2_window_base = c->l2_window_base;
   g->l2_window_bytes = c->l2_window_base ? (size_t)c->l2_window_bytes : 0;
   g->l2_hit_ratio = (float)(c->l2_hit_ratio > 0.0 && c->l2_hit_ratio <= 1.0 ? c->l2_hit_ratio : 1.0);
+  g->max_ctas = c->max_ctas > 0 ? c->max_ctas : 0;
+  g->no_pdl = (c->flags & MDR_FLAG_NO_PDL) != 0;
   if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32) {
     g->pro_batch = mdr::pipe_pro_batch(G, has_obs);
     const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride, g->pro_batch);
@@ -152,8 +158,7 @@ extern "C" int mdr_launch_geometry(const MdrConfig* cfg, int has_obs, int32_t* e
   if (ctas) *ctas = g.ctas;
   KernelParams k;
   fill_config(k, cfg);
-  const char* no_pipe = getenv("MDR_NO_PIPELINE");
-  const bool pipe = !(no_pipe && no_pipe[0] == '1') && mdr::pipe_eligible(k, g, cfg->precision);
+  const bool pipe = !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::pipe_eligible(k, g, cfg->precision);
   if (smem_bytes) *smem_bytes = pipe ? g.pipe_smem_bytes : g.smem_bytes;
   if (pipelined) *pipelined = pipe ? 1 : 0;
   return MDR_OK;
@@ -355,8 +360,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
                         k.metrics != nullptr);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);
-  const char* no_pipe = getenv("MDR_NO_PIPELINE");
-  const bool pipe = !(no_pipe && no_pipe[0] == '1') && mdr::pipe_eligible(k, g, cfg->precision);
+  const bool pipe = !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::pipe_eligible(k, g, cfg->precision);
   if (pipe) {
     k.pro_batch = g.pro_batch;
     int L = 16;  // lanes per env within one tile's lane group
@@ -367,8 +371,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
                           cfg->base_power_mode == MDR_BASE_INTERPOLATION, out->obs != nullptr, cfg->n_comm, g.part_stride,
                           g.pro_batch);
   }
-  const char* no_fused = getenv("MDR_NO_FUSED");
-  if (!(no_fused && no_fused[0] == '1') && mdr::fused_eligible(k) && g.pro_warp >= g.house_warps &&
+  if (!(cfg->flags & MDR_FLAG_NO_FUSED) && mdr::fused_eligible(k) && g.pro_warp >= g.house_warps &&
       (n_steps > 1 || k.metrics != nullptr)) {
     err = mdr::launch_fused(k, g, cfg->precision, n_steps, stream);
     return err == cudaSuccess ? MDR_OK : cuda_fail(err);

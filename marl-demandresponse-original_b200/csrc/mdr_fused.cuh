@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? (kInterp && 
 
 template <typename R, int kMaxThreads, int kAct, bool kMetrics, bool kInterp>
 static cudaError_t launch_fused_k(const KernelParams& kp, const Geometry& g, size_t smem, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(run_fused_kernel<R, kMaxThreads, kAct, kMetrics, kInterp>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
+  static std::atomic<uint64_t> latch{0};
+  cudaError_t err = ensure_max_smem(run_fused_kernel<R, kMaxThreads, kAct, kMetrics, kInterp>, latch);
   if (err != cudaSuccess) return err;
   run_fused_kernel<R, kMaxThreads, kAct, kMetrics, kInterp><<<g.ctas, g.threads, smem, stream>>>(kp);
   return cudaGetLastError();

@@ -25,6 +25,10 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "mdr_device.cuh"
 
 #ifndef MDR_BLOCKS_256
@@ -900,17 +904,26 @@ static cudaError_t launch_precompute(const KernelParams& kp, cudaStream_t stream
   return cudaGetLastError();
 }
 
+// Opt-in to the full shared-memory carve-out, once per (kernel, device).  The latch is an atomic bit per device:
+// two host threads racing on the first launch both set the (idempotent) attribute.
+template <typename K>
+static cudaError_t ensure_max_smem(K kernel, std::atomic<uint64_t>& latch) {
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (dev < 64 && (latch.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+  err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
+  if (err != cudaSuccess) return err;
+  if (dev < 64) latch.fetch_or(bit, std::memory_order_release);
+  return cudaSuccess;
+}
+
 template <typename R, int kMaxThreads, bool kFast, int kC>
 static cudaError_t launch_step_t(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(step_kernel<R, kMaxThreads, kFast, kC>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    attr_set[dev] = true;
-  }
+  static std::atomic<uint64_t> latch{0};
+  cudaError_t err = ensure_max_smem(step_kernel<R, kMaxThreads, kFast, kC>, latch);
+  if (err != cudaSuccess) return err;
   step_kernel<R, kMaxThreads, kFast, kC><<<g.ctas, g.threads, g.smem_bytes, stream>>>(kp);
   return cudaGetLastError();
 }
@@ -932,41 +945,45 @@ static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cuda
   return fast ? launch_step_f<R, true, 0>(kp, g, stream) : launch_step_f<R, false, 0>(kp, g, stream);
 }
 
+// Resident CTAs per SM of one pipelined instantiation, cached per (device, threads, shared memory) under a mutex
+// (different geometries alternate freely; any host thread may launch).
+struct OccEntry { int dev, threads; size_t smem; int ctas_per_sm, sm_count; };
+
 template <int kC, int kAct, bool kObs>
 static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, cudaStream_t stream) {
-  static int ctas_per_sm[64] = {};
-  static int sm_count[64] = {};
-  static int cached_threads[64] = {};
-  static size_t cached_smem[64] = {};
+  static std::atomic<uint64_t> latch{0};
+  static std::mutex mu;
+  static std::vector<OccEntry> cache;
+  cudaError_t err = ensure_max_smem(step_pipe_kernel<kC, kAct, kObs>, latch);
+  if (err != cudaSuccess) return err;
   int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 64) return cudaErrorInvalidDevice;
-  if (sm_count[dev] == 0) {
-    cudaError_t err = cudaFuncSetAttribute(step_pipe_kernel<kC, kAct, kObs>, cudaFuncAttributeMaxDynamicSharedMemorySize, MDR_MAX_SMEM_BYTES);
-    if (err != cudaSuccess) return err;
-    err = cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-    if (err != cudaSuccess) return err;
-  }
-  if (cached_threads[dev] != g.threads || cached_smem[dev] != g.pipe_smem_bytes) {
-    int n = 0;
-    cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_pipe_kernel<kC, kAct, kObs>, g.threads, g.pipe_smem_bytes);
-    if (err != cudaSuccess) return err;
-    if (n < 1) return cudaErrorLaunchOutOfResources;
-    ctas_per_sm[dev] = n;
-    cached_threads[dev] = g.threads;
-    cached_smem[dev] = g.pipe_smem_bytes;
+  err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  int ctas_per_sm = 0, sm_count = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (const OccEntry& o : cache)
+      if (o.dev == dev && o.threads == g.threads && o.smem == g.pipe_smem_bytes) { ctas_per_sm = o.ctas_per_sm; sm_count = o.sm_count; }
+    if (ctas_per_sm == 0) {
+      err = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      if (err != cudaSuccess) return err;
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, step_pipe_kernel<kC, kAct, kObs>, g.threads, g.pipe_smem_bytes);
+      if (err != cudaSuccess) return err;
+      if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
+      cache.push_back(OccEntry{dev, g.threads, g.pipe_smem_bytes, ctas_per_sm, sm_count});
+    }
   }
   KernelParams kp = kp_in;
   kp.n_tiles = g.ctas;
-  int grid = sm_count[dev] * ctas_per_sm[dev];
+  int grid = sm_count * ctas_per_sm;
+  if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
   if (grid > g.ctas) grid = g.ctas;
   // Programmatic dependent launch: the CTAs of step t+1 may become resident (and set up their mbarriers and index
   // arithmetic) while the last CTAs of step t are still draining; they block in griddepcontrol.wait before touching
   // global memory, so the data dependency on the whole previous grid is unchanged.
   cudaLaunchAttribute attrs[2];
   int n_attrs = 0;
-  static const bool pdl = !(getenv("MDR_NO_PDL") && getenv("MDR_NO_PDL")[0] == '1');
-  if (pdl) {
+  if (!g.no_pdl) {
     attrs[n_attrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[n_attrs].val.programmaticStreamSerializationAllowed = 1;
     ++n_attrs;
@@ -1008,10 +1025,12 @@ cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t 
 // allow.  MDR_PRO_BATCH overrides the cap for tuning.
 int pipe_pro_batch(int envs_per_cta, bool has_obs) {
   int cap = has_obs ? 4 : 8;
-  if (const char* s = getenv("MDR_PRO_BATCH")) {
-    const int v = atoi(s);
-    if (v == 1 || v == 2 || v == 4 || v == 8) cap = v;
-  }
+  static const int tuned = [] {  // read once (thread-safe static initialisation)
+    const char* s = getenv("MDR_PRO_BATCH");
+    const int v = s ? atoi(s) : 0;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 0;
+  }();
+  if (tuned) cap = tuned;
   int b = 1;
   while (2 * b <= cap && 2 * b * envs_per_cta <= 32) b *= 2;
   return b;

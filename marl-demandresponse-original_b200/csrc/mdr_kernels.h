@@ -69,6 +69,8 @@ struct Geometry {
   const void* l2_window_base;  // optional persisting-L2 access policy window of the launch
   size_t l2_window_bytes;
   float l2_hit_ratio;
+  int max_ctas;  // cap on the persistent pipelined grid (0 = SMs x resident CTAs)
+  bool no_pdl;   // MDR_FLAG_NO_PDL
 };
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,

@@ -54,6 +54,7 @@ class VecDemandResponseEnv:
         # L2 residency of the per-house state (None = MDR_L2_PERSIST env var; default OFF: measured 2x slower on c4)
         self.l2_persist = (os.environ.get("MDR_L2_PERSIST", "0") == "1") if l2_persist is None else bool(l2_persist)
         self._l2_window = (0, 0, 1.0)
+        self._flags, self._max_ctas = 0, 0
         self.n_envs = int(len(np.atleast_1d(population["t_epoch"])))
         self.n_houses = self.flat.n_houses
         self.n_comm = self.flat.n_comm
@@ -170,6 +171,7 @@ class VecDemandResponseEnv:
             self._setup_l2_window()
         self.cfg.l2_window_base = C.c_void_p(self._l2_window[0]) if self._l2_window[1] else None
         self.cfg.l2_window_bytes, self.cfg.l2_hit_ratio = self._l2_window[1], self._l2_window[2]
+        self.cfg.flags, self.cfg.max_ctas = self._flags, self._max_ctas
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         h = _lib.MdrHouses()
         for k in ("ua", "cm", "ca", "hm", "cap", "target", "deadband"):
@@ -188,6 +190,17 @@ class VecDemandResponseEnv:
         self.out_s.obs, self.out_s.reward = p(self.obs), p(self.reward)
         self._refs = (C.byref(self.cfg), C.byref(self.houses_s), C.byref(self.envs_s), C.byref(self.in_s),
                       C.byref(self.out_s))
+
+    def set_launch_options(self, *, no_pipeline=None, no_fused=None, no_pdl=None, max_ctas=None):
+        """MdrConfig.flags / max_ctas: pin the kernel choice (tests compare the pipelined, generic and fused kernels
+        on the same inputs) and cap the persistent grid (so that every CTA walks many tiles in a small test)."""
+        for bit, v in ((_lib.FLAG_NO_PIPELINE, no_pipeline), (_lib.FLAG_NO_FUSED, no_fused), (_lib.FLAG_NO_PDL, no_pdl)):
+            if v is not None:
+                self._flags = (self._flags | bit) if v else (self._flags & ~bit)
+        if max_ctas is not None:
+            self._max_ctas = int(max_ctas)
+        self.cfg.flags, self.cfg.max_ctas = self._flags, self._max_ctas
+        return self
 
     def _setup_l2_window(self):
         """Persisting-L2 carve-out + access policy window over the state arena (B200: 126 MB L2)."""
@@ -288,6 +301,16 @@ class VecDemandResponseEnv:
             self.out_s.obs = out_obs
         self._keep.append(m)
         return self.observe_tensor() if self.obs is not None else None
+
+    def stagger_interp_clock(self, seed=0):
+        """Spreads PowerGrid.time_since_last_interp (:1155, 1250-1255) of the envs uniformly over one refresh period
+        (multiples of the time step), as it is in a rollout whose clusters were reset at different times: every step
+        then refreshes ~dt/period of the envs instead of all of them every period/dt steps."""
+        gen = torch.Generator(device=self.device).manual_seed(int(seed))
+        slots = max(1, self.flat.interp_update_period // self.flat.time_step)
+        k = torch.randint(0, slots, (self.n_envs,), generator=gen, device=self.device, dtype=torch.int32)
+        self.time_since_interp.copy_(k * self.flat.time_step)
+        return self.time_since_interp
 
     def observe_tensor(self, *, msg_keep=None, comm=None):
         """Observation of the current state; nothing advances."""

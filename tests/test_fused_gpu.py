@@ -34,12 +34,12 @@ def _env(cfg, n_envs, precision, action_source, seed=3):
 
 
 def _per_step(env, k):
-    os.environ["MDR_NO_FUSED"] = "1"
+    env.set_launch_options(no_fused=True)
     try:
         for _ in range(k):
             out = env.step_tensor(None)
     finally:
-        os.environ.pop("MDR_NO_FUSED", None)
+        env.set_launch_options(no_fused=False)
     return out
 
 

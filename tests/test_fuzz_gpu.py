@@ -132,12 +132,9 @@ def test_random_fused_run_equals_single_steps(case):
     if c["metrics"]:
         a.enable_metrics()
     _, rew_a, p_a, s_a = a.run(c["k"])
-    os.environ["MDR_NO_FUSED"] = "1"
-    try:
-        for _ in range(c["k"]):
-            _, rew_b, p_b, s_b = b.step_tensor(None)
-    finally:
-        os.environ.pop("MDR_NO_FUSED", None)
+    b.set_launch_options(no_fused=True)
+    for _ in range(c["k"]):
+        _, rew_b, p_b, s_b = b.step_tensor(None)
     torch.cuda.synchronize()
     assert torch.equal(a.hvac, b.hvac) and torch.equal(a.t_epoch, b.t_epoch) and torch.equal(p_a, p_b)
     assert torch.equal(a.time_since_interp, b.time_since_interp)

@@ -226,7 +226,7 @@ def test_checkpoint_and_deepcopy():
 def test_pipelined_kernel_matches_oracle(n_envs, n, interp, signal, nb_comm):
     """The persistent pipelined fp32 kernel (no message drops, default flags -> `pipelined` geometry) against the
     oracle, including steps on which the interpolation refresh is due (deferred post-pass), and against the generic
-    kernel on the same inputs (MDR_NO_PIPELINE=1): integer state bit-exact, reals within the fp32 tolerance."""
+    kernel on the same inputs (MDR_FLAG_NO_PIPELINE): integer state bit-exact, reals within the fp32 tolerance."""
     import os
     import mdr_b200
     steps = 160 if interp else 30
@@ -236,7 +236,9 @@ def test_pipelined_kernel_matches_oracle(n_envs, n, interp, signal, nb_comm):
     table = gu.synthetic_table() if interp else None
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
     twin = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
+    twin.set_launch_options(no_pipeline=True)
     assert env.launch_geometry()["kernel"].startswith("mdr::step_pipe_kernel")
+    assert twin.launch_geometry()["kernel"] == "mdr::step_kernel"
     oracle = orc.OracleEnv(cfg, {k: v for k, v in pop.items() if k != "perlin_seed"},
                            interp=orc.PowerInterp(table, gu.INTERP_GRID, gu.INTERP_KEYS) if interp else None)
     for e in range(n_envs):
@@ -251,11 +253,7 @@ def test_pipelined_kernel_matches_oracle(n_envs, n, interp, signal, nb_comm):
         refreshes += int((oracle.s["base_power"] != base_before).any())
         kw = dict(od_noise=d["od_noise"][t], signal_noise=d["sig_noise"][t], interp_ids=d["ids"][t])
         obs, rew, p, s = env.step_tensor(d["actions"][t], **kw)
-        os.environ["MDR_NO_PIPELINE"] = "1"
-        try:
-            g_obs, g_rew, g_p, g_s = twin.step_tensor(d["actions"][t], **kw)
-        finally:
-            os.environ.pop("MDR_NO_PIPELINE", None)
+        g_obs, g_rew, g_p, g_s = twin.step_tensor(d["actions"][t], **kw)
         assert np.array_equal(env.hvac.cpu().numpy(), twin.hvac.cpu().numpy()), t
         assert np.array_equal(env.hvac_on.cpu().numpy(), oracle.s["on"]), t
         assert np.array_equal(env.hvac_lockout.cpu().numpy(), oracle.s["lockout"]), t

@@ -30,7 +30,7 @@ for signal, interp in (("perlin", False), ("sinusoidals", False), ("flat", False
             env.run(K)
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (reps * K)
-        os.environ["MDR_NO_FUSED"] = "1"
+        env.set_launch_options(no_fused=True)
         if metrics:
             env.disable_metrics()
         for _ in range(20):
@@ -40,7 +40,7 @@ for signal, interp in (("perlin", False), ("sinusoidals", False), ("flat", False
         for _ in range(300):
             env.step_tensor(None)
         e1.record(); torch.cuda.synchronize()
-        os.environ.pop("MDR_NO_FUSED")
+        env.set_launch_options(no_fused=False)
         per_step = e0.elapsed_time(e1) * 1e3 / 300
         print("signal %-12s interp %-5s metrics %-5s: fused %.2f us per env step (%.3g house-steps/s); one launch per step %.2f us"
               % (signal, interp, metrics, us, E * N / us * 1e6, per_step))

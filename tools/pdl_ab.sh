@@ -1,7 +1,7 @@
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 for v in 0 1; do
   for w in c4 c2 c3; do
-    MDR_NO_PDL=$v timeout 200 python bench.py --workload $w --steps 600 --warmup 50 --no-cpu-baseline > gpurun_out/pdl${v}_${w}.json 2> gpurun_out/pdl${v}_${w}.err
+    MDR_NO_PDL_UNUSED=$v timeout 200 python bench.py --workload $w --steps 600 --warmup 50 --no-cpu-baseline > gpurun_out/pdl${v}_${w}.json 2> gpurun_out/pdl${v}_${w}.err
   done
 done
 python - <<'PY'
