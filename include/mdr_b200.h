@@ -34,7 +34,8 @@ extern "C" {
 #define MDR_MAX_SINUSOIDS 8
 #define MDR_INTERP_DIMS 10
 #define MDR_INTERP_MAX_AXIS 12
-#define MDR_MAX_HOUSES_PER_ENV 1024 /* one env lives in one CTA (thread per house) */
+#define MDR_MAX_HOUSES_PER_ENV 1024      /* largest env that lives in ONE CTA (thread per house) */
+#define MDR_MAX_HOUSES_PER_CLUSTER 16384 /* largest env split over one thread-block cluster (16 CTAs x 1024 houses) */
 
 typedef enum MdrStatus {
   MDR_OK = 0,
@@ -43,7 +44,7 @@ typedef enum MdrStatus {
   MDR_ERR_MODE = -3,        /* unknown enum value (reference raises ValueError) */
   MDR_ERR_ALIGN = -4,       /* a buffer is not 16-byte aligned */
   MDR_ERR_CUDA = -5,        /* a CUDA runtime call failed (see mdr_last_cuda_error) */
-  MDR_ERR_UNSUPPORTED = -6, /* valid in the reference but outside this build (e.g. N > 1024) */
+  MDR_ERR_UNSUPPORTED = -6, /* valid in the reference but outside this build (e.g. greedy controller with N > 1024) */
   MDR_ERR_VERSION = -7      /* MdrConfig.abi_version != MDR_ABI_VERSION */
 } MdrStatus;
 
@@ -139,7 +140,8 @@ typedef struct MdrConfig {
 enum {
   MDR_FLAG_NO_PIPELINE = 1, /* never take the persistent pipelined kernel (generic kernel instead) */
   MDR_FLAG_NO_FUSED = 2,    /* never take the fused multi-step kernel (one launch per step instead) */
-  MDR_FLAG_NO_PDL = 4       /* launch without programmatic dependent launch */
+  MDR_FLAG_NO_PDL = 4,      /* launch without programmatic dependent launch */
+  MDR_FLAG_NO_CLUSTER = 8   /* never split an env of 225..1024 houses over a thread-block cluster (one CTA per env) */
 };
 
 /* Per-house struct-of-arrays.  Packed vectors keep every access a coalesced 8/16-byte load. */
@@ -174,6 +176,7 @@ typedef struct MdrEnvs {
   int32_t *time_since_interp;/* PowerGrid.time_since_last_interp */
   const double *perlin_seed; /* seed of the device perlin (production mode only) */
   double *metrics;           /* optional [n_envs, MDR_N_METRICS] running accumulators (see MDR_M_*), or NULL */
+  void *workspace;           /* mdr_workspace_bytes() of device scratch, 16-byte aligned (0 bytes needed -> may be NULL) */
 } MdrEnvs;
 
 /* Per-env running accumulators of MdrEnvs.metrics ([n_envs, MDR_N_METRICS] doubles, += by every mdr_step call
@@ -241,15 +244,22 @@ const char *mdr_last_cuda_error(void);
 /* F of utils.normStateDict (utils.py:740-880) for these flags; negative MdrStatus on error. */
 int mdr_obs_width(const MdrConfig *cfg);
 
+/* Device scratch a step of this configuration needs in MdrEnvs.workspace: 0 unless an env is larger than a
+   thread-block cluster can hold (n_houses > MDR_MAX_HOUSES_PER_CLUSTER), where the cluster power, the penalties and
+   the per-env record cross the CTAs through global memory (three launches per step). */
+int mdr_workspace_bytes(const MdrConfig *cfg, size_t *bytes);
+
 /* Validates cfg (modes, shapes) the way the reference constructors raise ValueError
    (env/MA_DemandResponse.py:249,324,898,1169,1306). */
 int mdr_validate(const MdrConfig *cfg);
 
 /* Launch geometry the step kernel will use (for tests and the roofline report).  `ctas` counts the
    G-env tiles; `pipelined` is 1 when a plain production-mode step of this configuration runs the
-   persistent software-pipelined kernel (grid = SMs x resident CTAs, looping over the tiles). */
+   persistent software-pipelined kernel (grid = SMs x resident CTAs, looping over the tiles);
+   `cluster_size` > 1 when one env is split over the CTAs of a thread-block cluster (N > 224: cluster power and
+   penalties cross the CTAs through distributed shared memory, ClusterHouses.step :1005-1055 for any nb_agents). */
 int mdr_launch_geometry(const MdrConfig *cfg, int has_obs, int32_t *envs_per_cta, int32_t *threads,
-                        int32_t *ctas, size_t *smem_bytes, int32_t *pipelined);
+                        int32_t *ctas, size_t *smem_bytes, int32_t *pipelined, int32_t *cluster_size);
 
 /* Replaces the per-step recomputation of a,b,c,r1,r2,A3,A4,exp(r*dt) in
    SingleHouse.update_temperature (:704-735) and HVAC.get_Q/power_consumption (:494-523):

@@ -6,7 +6,7 @@ import os
 from . import build as _build
 
 MDR_ABI_VERSION = 10
-MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV = 8, 10, 12, 1024
+MAX_SINUSOIDS, INTERP_DIMS, INTERP_MAX_AXIS, MAX_HOUSES_PER_ENV, MAX_HOUSES_PER_CLUSTER = 8, 10, 12, 1024, 16384
 F32, F64 = 4, 8
 COMM_NEIGHBOURS, COMM_TABLE, COMM_TABLE_PER_ENV, COMM_NONE = 0, 1, 2, 3
 STATE_HOUR, STATE_DAY, STATE_SOLAR, STATE_THERMAL, STATE_HVAC = 1, 2, 4, 8, 16
@@ -15,7 +15,8 @@ PEN = {"individual_L2": 0, "common_L2": 1, "common_max": 2, "mixture": 3}
 BASE = {"constant": 0, "interpolation": 1}
 SIG_FLAT, SIG_SINUSOIDALS, SIG_REGULAR_STEPS, SIG_PERLIN = 0, 1, 2, 3
 ACT = {"array": 0, "bangbang": 1, "random": 2, "greedy": 3}
-FLAG_NO_PIPELINE, FLAG_NO_FUSED, FLAG_NO_PDL = 1, 2, 4
+FLAG_NO_PIPELINE, FLAG_NO_FUSED, FLAG_NO_PDL, FLAG_NO_CLUSTER = 1, 2, 4, 8
+HAS_CLUSTER_PATH = True
 METRIC_NAMES = ("steps", "sum_mean_reward", "sum_mean_temp_offset", "sum_mean_temp_error", "sum_sq_temp_error",
                 "sum_sq_max_temp_error", "max_temp_error", "sum_od_temp", "sum_signal", "sum_consumption",
                 "sum_signal_offset", "sum_signal_error", "sum_sq_signal_error")
@@ -53,7 +54,7 @@ class MdrHouses(C.Structure):
 class MdrEnvs(C.Structure):
     _fields_ = [(n, _vp) for n in ("t_epoch", "phase", "od_temp", "solar_gain", "artificial_ratio",
                                    "max_power", "base_power", "signal", "cluster_power", "time_since_interp",
-                                   "perlin_seed", "metrics")]
+                                   "perlin_seed", "metrics", "workspace")]
 
 
 class MdrStepInputs(C.Structure):
@@ -75,7 +76,7 @@ class MdrOutputs(C.Structure):
 
 EXPORTS = ("mdr_version", "mdr_strerror", "mdr_last_cuda_error", "mdr_obs_width", "mdr_validate",
            "mdr_launch_geometry", "mdr_precompute", "mdr_reset", "mdr_observe", "mdr_step", "mdr_step_host",
-           "mdr_l2_persist_limit", "mdr_populate")
+           "mdr_l2_persist_limit", "mdr_populate", "mdr_workspace_bytes")
 
 _lib = None
 
@@ -117,7 +118,8 @@ def load(build_if_missing: bool = True):
     P = C.POINTER
     lib.mdr_obs_width.argtypes = [P(MdrConfig)]
     lib.mdr_validate.argtypes = [P(MdrConfig)]
-    lib.mdr_launch_geometry.argtypes = [P(MdrConfig), C.c_int, P(_i32), P(_i32), P(_i32), P(C.c_size_t), P(_i32)]
+    lib.mdr_workspace_bytes.argtypes = [P(MdrConfig), P(C.c_size_t)]
+    lib.mdr_launch_geometry.argtypes = [P(MdrConfig), C.c_int, P(_i32), P(_i32), P(_i32), P(C.c_size_t), P(_i32), P(_i32)]
     lib.mdr_precompute.argtypes = [P(MdrConfig), P(MdrHouses), _vp]
     step_args = [P(MdrConfig), P(MdrHouses), P(MdrEnvs), P(MdrStepInputs), P(MdrOutputs)]
     lib.mdr_reset.argtypes = step_args + [_vp]

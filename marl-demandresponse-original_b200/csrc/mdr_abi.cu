@@ -67,7 +67,8 @@ extern "C" int mdr_validate(const MdrConfig* c) {
   if (c->action_source < MDR_ACT_ARRAY || c->action_source > MDR_ACT_GREEDY) return MDR_ERR_MODE;
   if (c->n_sinusoids < 0 || c->n_sinusoids > MDR_MAX_SINUSOIDS) return MDR_ERR_SHAPE;
   if (c->n_features != mdr_obs_width(c)) return MDR_ERR_SHAPE;
-  if (c->n_houses > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
+  /* the on-device greedy controller sorts an env inside one CTA */
+  if (c->n_houses > MDR_MAX_HOUSES_PER_ENV && c->action_source == MDR_ACT_GREEDY) return MDR_ERR_UNSUPPORTED;
   /* 32-bit house / observation indexing inside the kernel */
   if ((double)c->n_envs * c->n_houses * (c->n_features > 0 ? c->n_features : 1) >= 4294967296.0) return MDR_ERR_UNSUPPORTED;
   if (c->base_power_mode == MDR_BASE_INTERPOLATION) {
@@ -80,30 +81,72 @@ extern "C" int mdr_validate(const MdrConfig* c) {
 }
 
 static void fill_config(KernelParams& k, const MdrConfig* c);
+static bool split_geometry(const MdrConfig* c, int* slice, int* k);
 
-static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool need_met = false) {
+// envs beyond a thread-block cluster take the three-launch path through a global workspace (mdr_big.cuh)
+static bool needs_big_path(const MdrConfig* c) {
+  if (c->n_houses <= MDR_MAX_HOUSES_PER_ENV) return false;
+  int slice = 0, k = 0;
+  return c->n_houses > MDR_MAX_HOUSES_PER_CLUSTER || !split_geometry(c, &slice, &k);
+}
+
+extern "C" int mdr_workspace_bytes(const MdrConfig* cfg, size_t* bytes) {
+  if (!cfg || !bytes) return MDR_ERR_NULL;
+  int st = mdr_validate(cfg);
+  if (st != MDR_OK) return st;
+  *bytes = needs_big_path(cfg) ? mdr::big_workspace(cfg->n_envs, cfg->n_houses) : 0;
+  return MDR_OK;
+}
+
+// One env split over a thread-block cluster (N > 224): CTA capacity 224 / 480 / 992 houses with a dedicated prologue
+// warp, 1024 without; the smallest capacity that needs at most 8 (portable), else 16 CTAs.  The slice of rank 0 must
+// hold every sampled house of an interpolation refresh.
+static bool split_geometry(const MdrConfig* c, int* slice, int* k) {
+  const int N = c->n_houses;
+  const int need = c->base_power_mode == MDR_BASE_INTERPOLATION ? (N < c->interp_nb_agents ? N : c->interp_nb_agents) : 1;
+  const int caps[4] = {224, 480, 992, 1024};
+  for (int max_k = 8; max_k <= 16; max_k += 8)
+    for (int i = 0; i < 4; ++i) {
+      const int kk = (N + caps[i] - 1) / caps[i];
+      if (kk < 2 || kk > max_k) continue;
+      int S = (N + kk - 1) / kk;
+      S = (S + 3) & ~3;  // slices start on a multiple of 4 houses: 16-byte aligned observation rows whenever N % 4 == 0
+      if (S > caps[i] || N - (kk - 1) * S < 1 || S < need) continue;
+      *slice = S;
+      *k = kk;
+      return true;
+    }
+  return false;
+}
+
+static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool need_met = false, bool allow_split = false) {
   const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
-  if (N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
   static const int target_threads = [] {  // tuning knob (house threads per CTA), read once
     const char* s = getenv("MDR_TARGET_THREADS");
     const int v = s ? atoi(s) : 0;
     return v >= 32 && v <= 992 ? v : 224;  // + 32 for the prologue warp = 256
   }();
+  int slice = 0, ncl = 1;
+  const bool split = allow_split && N > 224 && !(c->flags & MDR_FLAG_NO_CLUSTER) && c->action_source != MDR_ACT_GREEDY &&
+                     split_geometry(c, &slice, &ncl);
+  if (!split && N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
   int gmax = target_threads / N;
   if (gmax < 1) gmax = 1;
   if (gmax > E) gmax = E;
   int G = gmax;
-  if (has_obs) {  // a CTA's first observation row should be 16-byte aligned for the bulk store
+  if (has_obs && !split) {  // a CTA's first observation row should be 16-byte aligned for the bulk store
     for (int k = gmax; k >= 1; --k)
       if (((size_t)k * N * F * rb) % 16 == 0) { G = k; break; }
   }
-  const int house_threads = ((G * N + 31) / 32) * 32;
+  if (split) G = 1;
+  const int house_threads = ((((split ? slice : G * N) + 31) / 32)) * 32;
   const int house_warps = house_threads / 32;
   // a dedicated prologue warp when the CTA has room for one, else warp 0 runs the prologue first
   const bool extra = house_threads + 32 <= 1024;
   const int threads = house_threads + (extra ? 32 : 0);
   const int nwarps = house_warps;  // staging tiles exist for the house warps only
   const int part_stride = (N + 31) / 32 + 1;
+  const int part_slots = split ? house_warps : part_stride;  // warp partials a CTA keeps per env
   const bool need_val = c->base_power_mode == MDR_BASE_INTERPOLATION || c->action_source == MDR_ACT_GREEDY;
   const bool need_pen = c->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2;
   int blocks_per_sm = 768 / threads;
@@ -112,12 +155,12 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
   int rpp = 0;
   size_t smem = 0;
   for (int r = 32; r >= 1; r >>= 1) {
-    smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride, need_met);
+    smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride, need_met, part_slots);
     if (smem <= budget) { rpp = r; break; }
   }
   if (rpp == 0) {
     for (int r = 32; r >= 1; r >>= 1) {
-      smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride, need_met);
+      smem = mdr::step_smem_layout(nullptr, rb, house_threads, G, nwarps, r, F, need_val, need_pen, has_obs, c->n_comm, part_stride, need_met, part_slots);
       if (smem <= (size_t)MDR_MAX_SMEM_BYTES) { rpp = r; break; }
     }
   }
@@ -128,7 +171,10 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
   g->house_warps = house_warps;
   g->pro_warp = extra ? house_warps : 0;
   g->part_stride = part_stride;
-  g->ctas = (E + G - 1) / G;
+  g->ctas = split ? E * ncl : (E + G - 1) / G;
+  g->cluster = split ? ncl : 1;
+  g->cluster_slice = split ? slice : 0;
+  g->part_slots = part_slots;
   g->rows_per_pass = rpp;
   g->smem_bytes = smem;
   g->pipe_smem_bytes = 0;
@@ -138,7 +184,7 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
   g->l2_hit_ratio = (float)(c->l2_hit_ratio > 0.0 && c->l2_hit_ratio <= 1.0 ? c->l2_hit_ratio : 1.0);
   g->max_ctas = c->max_ctas > 0 ? c->max_ctas : 0;
   g->no_pdl = (c->flags & MDR_FLAG_NO_PDL) != 0;
-  if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32) {
+  if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32 && !split) {
     g->pro_batch = mdr::pipe_pro_batch(G, has_obs);
     const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride, g->pro_batch);
     if (ps <= (size_t)MDR_MAX_SMEM_BYTES) g->pipe_smem_bytes = ps;
@@ -147,12 +193,23 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
 }
 
 extern "C" int mdr_launch_geometry(const MdrConfig* cfg, int has_obs, int32_t* envs_per_cta, int32_t* threads,
-                                   int32_t* ctas, size_t* smem_bytes, int32_t* pipelined) {
+                                   int32_t* ctas, size_t* smem_bytes, int32_t* pipelined, int32_t* cluster_size) {
   int st = mdr_validate(cfg);
   if (st != MDR_OK) return st;
   Geometry g;
-  st = choose_geometry(cfg, has_obs != 0, &g);
+  if (needs_big_path(cfg)) {
+    const int nparts = (cfg->n_houses + 255) / 256;
+    if (envs_per_cta) *envs_per_cta = 1;
+    if (threads) *threads = 256;
+    if (ctas) *ctas = cfg->n_envs * nparts;
+    if (smem_bytes) *smem_bytes = 0;
+    if (pipelined) *pipelined = 0;
+    if (cluster_size) *cluster_size = 0;  /* 0 = plain CTAs, three launches per step */
+    return MDR_OK;
+  }
+  st = choose_geometry(cfg, has_obs != 0, &g, false, true);
   if (st != MDR_OK) return st;
+  if (cluster_size) *cluster_size = g.cluster;
   if (envs_per_cta) *envs_per_cta = g.envs_per_cta;
   if (threads) *threads = g.threads;
   if (ctas) *ctas = g.ctas;
@@ -245,6 +302,7 @@ static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, cons
     return MDR_ERR_NULL;
   if (out->obs && !aligned16(out->obs)) return MDR_ERR_ALIGN;
   k.metrics = e->metrics;
+  k.workspace = e->workspace;
   k.t_epoch = e->t_epoch; k.phase = e->phase; k.od_temp = e->od_temp; k.solar_gain = e->solar_gain;
   k.artificial_ratio = e->artificial_ratio; k.max_power = e->max_power;
   k.base_power = e->base_power; k.signal = e->signal; k.cluster_power = e->cluster_power;
@@ -336,9 +394,33 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   if (st != MDR_OK) return st;
   st = fill_step(k, cfg, envs, in, out, is_reset);
   if (st != MDR_OK) return st;
+  if (needs_big_path(cfg)) {
+    if (!k.workspace) return MDR_ERR_NULL;          // mdr_workspace_bytes() of device memory in MdrEnvs.workspace
+    if (k.metrics) return MDR_ERR_UNSUPPORTED;      // accumulate from the returned tensors instead
+    if (!aligned16(k.workspace)) return MDR_ERR_ALIGN;
+    cudaError_t err = cudaSetDevice(cfg->device);
+    if (err != cudaSuccess) return cuda_fail(err);
+    for (int i = 0; i < n_steps; ++i) {
+      err = mdr::launch_big(k, cfg->precision, k.workspace, stream);
+      if (err != cudaSuccess) return cuda_fail(err);
+      k.step_index += 1;
+    }
+    return MDR_OK;
+  }
+  // Geometry: whole envs per CTA (N <= 1024) is what the fused multi-step kernel needs; otherwise an env of more
+  // than 224 houses is split over a thread-block cluster.
   Geometry g;
-  st = choose_geometry(cfg, out->obs != nullptr, &g, k.metrics != nullptr);
-  if (st != MDR_OK) return st;
+  bool fused = false;
+  if (cfg->n_houses <= MDR_MAX_HOUSES_PER_ENV) {
+    st = choose_geometry(cfg, out->obs != nullptr, &g, k.metrics != nullptr, false);
+    if (st != MDR_OK) return st;
+    fused = !(cfg->flags & MDR_FLAG_NO_FUSED) && mdr::fused_eligible(k) && g.pro_warp >= g.house_warps &&
+            (n_steps > 1 || k.metrics != nullptr);
+  }
+  if (!fused) {
+    st = choose_geometry(cfg, out->obs != nullptr, &g, k.metrics != nullptr, true);
+    if (st != MDR_OK) return st;
+  }
   k.G = g.envs_per_cta;
   k.hmax = g.hmax;
   k.rows_per_pass = g.rows_per_pass;
@@ -354,10 +436,12 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   k.in_stride = g.hmax * 52;
   k.pro_warp = g.pro_warp;
   k.part_stride = g.part_stride;
+  k.cl = g.cluster;
+  k.cl_slice = g.cluster_slice;
   mdr::step_smem_layout(&k, cfg->precision, g.hmax, g.envs_per_cta, g.house_warps, g.rows_per_pass, cfg->n_features,
                         cfg->base_power_mode == MDR_BASE_INTERPOLATION || cfg->action_source == MDR_ACT_GREEDY,
                         cfg->temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2, out->obs != nullptr, cfg->n_comm, g.part_stride,
-                        k.metrics != nullptr);
+                        k.metrics != nullptr, g.part_slots);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);
   const bool pipe = !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::pipe_eligible(k, g, cfg->precision);
@@ -371,8 +455,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
                           cfg->base_power_mode == MDR_BASE_INTERPOLATION, out->obs != nullptr, cfg->n_comm, g.part_stride,
                           g.pro_batch);
   }
-  if (!(cfg->flags & MDR_FLAG_NO_FUSED) && mdr::fused_eligible(k) && g.pro_warp >= g.house_warps &&
-      (n_steps > 1 || k.metrics != nullptr)) {
+  if (fused) {
     err = mdr::launch_fused(k, g, cfg->precision, n_steps, stream);
     return err == cudaSuccess ? MDR_OK : cuda_fail(err);
   }

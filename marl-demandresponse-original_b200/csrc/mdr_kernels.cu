@@ -65,20 +65,24 @@ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // shared-memory carve-up (must match between host sizing and the kernel)
 struct SmemLayout {
-  size_t off_msg, off_pw, off_val, off_pen, off_env, off_met, off_stage, total;
+  size_t off_msg, off_pw, off_val, off_pen, off_env, off_met, off_cl, off_stage, total;
 };
 
 // hmax = threads per CTA (>= G*N); the message window holds G*(N+C) entries (wrap-around halos)
+// part_slots: warp-partial slots per env (part_stride, or -- env split over a cluster -- the warps of one CTA)
 inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarps, int rows_per_pass, int n_features,
-                              bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met) {
+                              bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met,
+                              int part_slots) {
   SmemLayout L;
   size_t o = 0;
+  if (part_slots <= 0) part_slots = part_stride;
   L.off_msg = o; o += align16((size_t)(hmax + genvs_max * n_comm) * 4 * real_bytes);
-  L.off_pw = o;  o += align16((size_t)genvs_max * part_stride * sizeof(double));
+  L.off_pw = o;  o += align16((size_t)genvs_max * part_slots * sizeof(double));
   L.off_val = o; o += need_val ? align16((size_t)hmax * 3 * sizeof(double)) : 0;  // interpolation values / greedy sort scratch
   L.off_pen = o; o += need_pen ? align16((size_t)hmax * sizeof(double)) : 0;
   L.off_env = o; o += align16((size_t)genvs_max * sizeof(EnvScratch));
-  L.off_met = o; o += need_met ? align16((size_t)genvs_max * part_stride * 5 * sizeof(double)) : 0;
+  L.off_met = o; o += need_met ? align16((size_t)genvs_max * part_slots * 5 * sizeof(double)) : 0;
+  L.off_cl = o;  o += 128;  // ClusterTot
   L.off_stage = o;
   o += has_obs ? align16((size_t)nwarps * rows_per_pass * n_features * real_bytes) : 0;
   L.total = o;
@@ -378,6 +382,28 @@ __device__ __forceinline__ int cta_or(int pred) {
   return r;
 }
 
+// Thread-block-cluster rendezvous (one env split over the CTAs of a cluster, N > 224): every thread of every CTA of
+// the cluster arrives and waits; release/acquire at cluster scope, so shared AND global writes made before it are
+// visible to the peers after it.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// generic address of `local` (a shared-memory address of this CTA) in the CTA of rank `rank` of the cluster (DSMEM)
+template <typename T>
+__device__ __forceinline__ const T* dsmem_peer(const T* local, int rank) {
+  return reinterpret_cast<const T*>(__cluster_map_shared_rank(const_cast<T*>(local), (unsigned)rank));
+}
+// per-CTA totals exchanged through DSMEM when an env is split over a cluster
+struct ClusterTot {
+  double P, pen_sum, pen_max, pad;
+  double met[8];  // metric partials (reward, offset, |error|, error^2 sums; max |error|)
+};
+
+// first env of this CTA's tile and whether the env is split over a cluster
+__device__ __forceinline__ int tile_env0(const KernelParams& p) {
+  return p.cl > 1 ? (int)(blockIdx.x / (unsigned)p.cl) : (int)blockIdx.x * p.G;
+}
+
 // Body of the dedicated prologue warp (and, when the CTA has no spare warp, of warp 0 before it
 // turns to its houses).  Kept out of line so that none of its register pressure or call-saved
 // state leaks into the house warps' code path.
@@ -385,8 +411,9 @@ __device__ __noinline__ int prologue_warp_main(const KernelParams& p, bool reset
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EnvScratch* s_env = reinterpret_cast<EnvScratch*>(smem_raw + p.off_env);
   const int lane = threadIdx.x & 31;
-  const int env0 = blockIdx.x * p.G;
-  const int genvs = min(p.G, p.E - env0);
+  const bool split = p.cl > 1;  // every CTA of the cluster evaluates the env's prologue for itself (same inputs, same result)
+  const int env0 = tile_env0(p);
+  const int genvs = split ? 1 : min(p.G, p.E - env0);
   const int L = p.pro_lanes, groups = 32 / L;
   const int sub = lane & (L - 1), grp = lane / L;
   int my_due = 0;
@@ -401,8 +428,18 @@ __device__ __noinline__ int prologue_warp_main(const KernelParams& p, bool reset
   // barrier sequence of the house warps (see step_kernel)
   if (p.solar) cta_sync();
   const int due = p.base_power_mode == MDR_BASE_INTERPOLATION ? cta_or(my_due) : (cta_sync(), 0);
-  if (p.temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2) cta_sync();
-  if (due) { cta_sync(); cta_sync(); }
+  if (split) { cluster_sync_all(); cta_sync(); }
+  else if (p.temp_penalty_mode != MDR_PEN_INDIVIDUAL_L2) cta_sync();
+  if (due) {
+    cta_sync();
+    if (split) cluster_sync_all();
+    cta_sync();
+  }
+  if (split) {
+    // no thread of the cluster exits before every peer is done reading this CTA's shared memory
+    if (p.metrics != nullptr && !reset) cluster_sync_all();
+    cluster_sync_all();
+  }
   return 0;
 }
 
@@ -417,6 +454,91 @@ __device__ __forceinline__ R segmented_sum(R v, int key, int lane) {
     if (lane + o < 32 && tk == key) v += tv;
   }
   return v;
+}
+
+// ----------------------------------------------------------------------------------------
+// One observation row in utils.normStateDict order (utils.py:774-880) for ANY flag / neighbour mode;
+// `msg_at(j)` returns the message (dT/5, sso, P/7500, Pmax/7500) of house j of the same env.
+// ----------------------------------------------------------------------------------------
+template <typename R>
+struct HouseRow {
+  R t_air, t_mass, target, deadband, p_on, inv_lock;
+  int on, lock, sso, e, li;
+  unsigned h;
+  double P;
+};
+
+template <typename R, typename MsgAt>
+__device__ __forceinline__ void generic_row(const KernelParams& p, R* row, const HouseRow<R>& hr, const EnvScratch& es,
+                                            int state_flags, int msg_flags, int comm_mode, bool has_keep, bool has_defect,
+                                            int C, MsgAt msg_at) {
+  const int N = p.N, half = C >> 1, li = hr.li, e = hr.e;
+  const unsigned h = hr.h;
+  const R inv_lock = hr.inv_lock;
+  // own features, utils.normStateDict order (utils.py:774-840)
+  row[0] = (hr.t_air - 20) * (R)0.2;
+  row[1] = (hr.t_mass - 20) * (R)0.2;
+  row[2] = (hr.target - 20) * (R)0.2;
+  int c = 3;
+  if (state_flags & MDR_STATE_THERMAL) row[c++] = (R)es.f_od;
+  row[c++] = hr.deadband;
+  if (state_flags & MDR_STATE_DAY) { row[c++] = (R)es.f_sin_day; row[c++] = (R)es.f_cos_day; }
+  if (state_flags & MDR_STATE_HOUR) { row[c++] = (R)es.f_sin_hr; row[c++] = (R)es.f_cos_hr; }
+  if (state_flags & MDR_STATE_SOLAR) row[c++] = (R)es.f_solar;
+  row[c++] = hr.p_on * (R)p.cop_over_def_cap;
+  if (state_flags & MDR_STATE_THERMAL) {
+    row[c++] = (R)(p.ua[h] / p.def_ua);
+    row[c++] = (R)(p.cm[h] / p.def_cm);
+    row[c++] = (R)(p.ca[h] / p.def_ca);
+    row[c++] = (R)(p.hm[h] / p.def_hm);
+  }
+  if (state_flags & MDR_STATE_HVAC) {
+    row[c++] = (R)(p.hvac_cop / p.def_cop);
+    row[c++] = (R)(p.hvac_latent / p.def_latent);
+  }
+  row[c++] = (R)hr.on;
+  row[c++] = (R)hr.lock;
+  row[c++] = (R)hr.sso * inv_lock;
+  row[c++] = (R)1;
+  row[c++] = (R)es.f_sig;
+  row[c++] = (R)(hr.P * p.inv_norm_sig_agents);
+  // messages, SingleHouse.message :624-662 normalised as utils.py:842-868
+  R* mrow = row + c;
+  const size_t tbase = comm_mode == MDR_COMM_TABLE_PER_ENV ? (size_t)e * N * C : 0;
+  for (int k = 0; k < C; ++k) {
+    int j;
+    if (comm_mode == MDR_COMM_NEIGHBOURS) {
+      j = k < half ? li - half + k : li + 1 + (k - half);
+      if (j < 0) j += N;
+      if (j >= N) j -= N;
+    } else {
+      j = p.comm_table[tbase + (size_t)li * C + k];
+    }
+    const auto m = msg_at(j);
+    bool keep = true;
+    if (has_keep) keep = p.msg_keep[(size_t)h * C + k] != 0;
+    else if (has_defect) {
+      const uint4 r = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+                                 STREAM_MSG + 16 * (uint32_t)k, p.seed);
+      keep = u01(r.x, r.y) > p.comm_defect_prob;
+    }
+    const R kf = keep ? (R)1 : (R)0;
+    mrow[0] = m.x * kf; mrow[1] = m.y * inv_lock * kf; mrow[2] = m.z * kf; mrow[3] = m.w * kf;
+    mrow += 4;
+    if (msg_flags) {
+      const size_t hj = (size_t)e * N + j;
+      if (msg_flags & MDR_MSG_THERMAL) {
+        mrow[0] = (R)(p.ua[hj] / p.def_ua) * kf; mrow[1] = (R)(p.cm[hj] / p.def_cm) * kf;
+        mrow[2] = (R)(p.ca[hj] / p.def_ca) * kf; mrow[3] = (R)(p.hm[hj] / p.def_hm) * kf;
+        mrow += 4;
+      }
+      if (msg_flags & MDR_MSG_HVAC) {
+        mrow[0] = (R)(p.hvac_cop / p.def_cop) * kf; mrow[1] = (R)(p.hvac_latent / p.def_latent) * kf;
+        mrow[2] = (R)(p.cap[hj] / p.def_cap) * kf;
+        mrow += 3;
+      }
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -456,16 +578,25 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   if (warp == p.pro_warp) my_due = prologue_warp_main(p, reset, observe_only, false);
 
   const int N = p.N, C = kC > 0 ? kC : p.C;
-  const int env0 = blockIdx.x * p.G;
-  const int genvs = min(p.G, p.E - env0);
-  const int H = genvs * N;
+  // Large clusters (N > 224): ONE env is split over the p.cl CTAs of a thread-block cluster; CTA `rank` owns the
+  // houses [rank * cl_slice, ...) of env blockIdx.x / cl.  Cluster power / penalties cross the CTAs as per-CTA totals
+  // through distributed shared memory, neighbour messages are read from the owning CTA's window.
+  const int ncl = p.cl;
+  const bool split = ncl > 1;
+  const int rank = split ? (int)(blockIdx.x % (unsigned)ncl) : 0;
+  const int slice_lo = rank * p.cl_slice;  // first house (index within the env) of this CTA
+  const int env0 = tile_env0(p);
+  const int genvs = split ? 1 : min(p.G, p.E - env0);
+  const int H = split ? min(p.cl_slice, N - slice_lo) : genvs * N;
   const bool in_tile = tid < H;
-  const int le = in_tile ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
-  const int li = tid - le * N;
+  const int le = (in_tile && !split) ? (N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
+  const int li = split ? slice_lo + tid : tid - le * N;  // index of the house within its env
+  const int wl = split ? tid : li;                        // ... within this CTA's message window
   const int e = env0 + le;
   // env mask (mdr_reset of a subset of the envs): houses of unselected envs are inactive
   const bool active = in_tile && (p.env_mask == nullptr || p.env_mask[e] != 0);
-  const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)tid;
+  const bool env_head = active && (split ? (rank == 0 && tid == 0) : li == 0);  // writes the per-env outputs
+  const unsigned h = (unsigned)env0 * (unsigned)N + (unsigned)(split ? slice_lo : 0) + (unsigned)tid;
   const bool interp_mode = p.base_power_mode == MDR_BASE_INTERPOLATION;
   const bool need_pen = pen_mode != MDR_PEN_INDIVIDUAL_L2;
 
@@ -576,9 +707,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
     const R inv_norm = (R)p.inv_norm_reg_sig;
     const T4 m = make4((tt.x - target) * (R)0.2, (R)sso, pw * inv_norm, p_on * inv_norm);
     T4* win = s_msg + le * ns;
-    win[half + li] = m;
-    if (li < C - half) win[half + N + li] = m;        // wrap-around halo after the last house
-    if (li >= N - half) win[li - (N - half)] = m;     // ... and before the first one
+    win[half + wl] = m;
+    if (!split) {
+      if (li < C - half) win[half + N + li] = m;        // wrap-around halo after the last house
+      if (li >= N - half) win[li - (N - half)] = m;     // ... and before the first one
+    }
     // utils.deadbandL2, utils.py:1266-1274
     const R hi = target + deadband / 2, lo = target - deadband / 2;
     if (hi < tt.x) pen = (tt.x - hi) * (tt.x - hi);
@@ -598,17 +731,59 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   // Fast path with a dedicated prologue warp: the house warps first meet on their own barrier (1),
   // sum the power and assemble their observation rows, and only then join the prologue warp on
   // barrier 0 -- its fp64 latency is hidden behind the row assembly.
-  const bool deferred = kFast && p.pro_warp >= p.house_warps && p.obs != nullptr;
+  const bool deferred = kFast && !split && p.pro_warp >= p.house_warps && p.obs != nullptr;
   int any_due = 0;
   if (deferred) house_sync(p.house_warps * 32);
   else any_due = interp_mode ? cta_or(my_due) : (cta_sync(), 0);
 
   // every thread now knows its env's power: sum the warp partials in warp order
   double P = 0.0;
-  if (active) {
+  if (split) {
+    // per-CTA totals (power; sum and max of the penalties) -> cluster barrier -> warp 0 adds the peers' totals in
+    // rank order (deterministic) -> one more CTA barrier publishes them to the house threads
+    ClusterTot* s_tot = reinterpret_cast<ClusterTot*>(smem_raw + p.off_cl);
+    if (warp == 0) {
+      const int nw = (H + 31) >> 5;
+      double ps = 0.0, pn = 0.0, pm = 0.0;
+      for (int w = lane; w < nw; w += 32) ps += s_part[w];
+      if (need_pen)
+        for (int i = lane; i < H; i += 32) {
+          const double v = s_pen[i];
+          pn += v / N;
+          pm = fmax(pm, v);
+        }
+      ps = warp_sum(ps); pn = warp_sum(pn); pm = warp_max(pm);
+      if (lane == 0) { s_tot->P = ps; s_tot->pen_sum = pn; s_tot->pen_max = pm; }
+    }
+    cluster_sync_all();
+    if (warp == 0) {
+      double tp = 0.0, tn = 0.0, tm = 0.0;
+      if (lane < ncl) {
+        const ClusterTot* peer = dsmem_peer(s_tot, lane);
+        tp = peer->P; tn = peer->pen_sum; tm = peer->pen_max;
+      }
+      double sp = 0.0, sn = 0.0, sm = 0.0;
+      for (int r = 0; r < ncl; ++r) {
+        sp += __shfl_sync(0xffffffffu, tp, r);
+        sn += __shfl_sync(0xffffffffu, tn, r);
+        sm = fmax(sm, __shfl_sync(0xffffffffu, tm, r));
+      }
+      if (lane == 0) { s_env[0].P = sp; s_env[0].pen_mean = sn; s_env[0].pen_max = sm; }
+    }
+    cta_sync();
+    P = s_env[0].P;
+  } else if (active) {
     const int first_warp = (le * N) >> 5, last_warp = (le * N + N - 1) >> 5;
     for (int w = 0; w <= last_warp - first_warp; ++w) P += s_part[le * p.part_stride + w];
   }
+  // message of house j (index within the env) of this thread's env: local window, or the owning CTA's (DSMEM)
+  auto msg_at = [&](int j) -> T4 {
+    if (!split) return s_msg[le * ns + half + j];
+    const int rj = j / p.cl_slice;
+    const T4* src = s_msg + half + (j - rj * p.cl_slice);
+    if (rj != rank) src = dsmem_peer(src, rj);
+    return *src;
+  };
 
   const int F = p.F;
   const int rpp = p.rows_per_pass;
@@ -633,7 +808,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
     R* mrow = row + 11;
 #pragma unroll
     for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
-      const T4 m = win[k + (k >= half ? 1 : 0)];
+      T4 m;
+      if (!split) m = win[k + (k >= half ? 1 : 0)];
+      else {
+        int j = li - half + k + (k >= half ? 1 : 0);
+        if (j < 0) j += N;
+        if (j >= N) j -= N;
+        m = msg_at(j);
+      }
       mrow[4 * k + 0] = m.x;
       mrow[4 * k + 1] = m.y * inv_lock;
       mrow[4 * k + 2] = m.z;
@@ -646,7 +828,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   }
 
   // ---------------- phase B (generic penalty modes only): mean / max of the penalties --------
-  if (need_pen) {
+  if (need_pen && !split) {
     const int nwarps = p.house_warps;
     for (int le2 = warp; le2 < genvs; le2 += nwarps) {
       double pmean = 0.0, pmax = 0.0;
@@ -666,7 +848,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   }
 
   // per-env state written back by the env's first house thread
-  if (active && li == 0 && !observe_only) {
+  if (env_head && !observe_only) {
     const EnvScratch& es = s_env[le];
     p.cluster_power[e] = P;
     if (!reset) {
@@ -685,7 +867,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   if (any_due) {
     const int nb = p.interp_nb_agents;
     const int nsamp = N <= nb ? N : nb;
-    if (active && s_env[le].due && li < nsamp) {
+    // split env: the CTA of rank 0 evaluates all samples (the peers' new temperatures are visible in global memory
+    // since the cluster barrier) and hands the new signal to the peers
+    if (active && s_env[le].due && li < nsamp && rank == 0) {
       int src = li;
       if (N > nb) {
         if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
@@ -703,7 +887,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
                                   es.date);
     }
     cta_sync();
-    if (active && li == 0 && s_env[le].due) {
+    if (env_head && s_env[le].due) {
       EnvScratch& es = s_env[le];
       double base = 0.0;
       for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);  // id order, :1218-1232
@@ -714,6 +898,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
       p.signal[e] = sig;
       es.f_sig = sig * p.inv_norm_sig_agents;
       es.sig_new = sig;
+    }
+    if (split) {
+      cluster_sync_all();
+      if (rank != 0 && tid == 0 && s_env[0].due) {
+        const EnvScratch* lead = dsmem_peer(s_env, 0);
+        s_env[0].f_sig = lead->f_sig;
+        s_env[0].sig_new = lead->sig_new;
+      }
     }
     cta_sync();
   }
@@ -759,13 +951,38 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
       d[0] = v0; d[1] = v1; d[2] = v2; d[3] = v3; d[4] = v4;
     }
     house_sync(p.house_warps * 32);
-    if (active && li == 0) {
-      const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
+    if (split) {
+      // per-CTA totals in warp order -> cluster barrier -> the env's first thread adds them in rank order
+      ClusterTot* s_tot = reinterpret_cast<ClusterTot*>(smem_raw + p.off_cl);
+      if (tid == 0) {
+        const int nw = (H + 31) >> 5;
+        double t[4] = {0.0, 0.0, 0.0, 0.0}, mx = 0.0;
+        for (int w = 0; w < nw; ++w) {
+          const double* d = s_met + (size_t)w * 5;
+          for (int k = 0; k < 4; ++k) t[k] += d[k];
+          mx = fmax(mx, d[4]);
+        }
+        for (int k = 0; k < 4; ++k) s_tot->met[k] = t[k];
+        s_tot->met[4] = mx;
+      }
+      cluster_sync_all();
+    }
+    if (env_head) {
       double t[4] = {0.0, 0.0, 0.0, 0.0}, mx = 0.0;
-      for (int w = 0; w < nparts; ++w) {
-        const double* d = s_met + (size_t)(le * p.part_stride + w) * 5;
-        for (int k = 0; k < 4; ++k) t[k] += d[k];
-        mx = fmax(mx, d[4]);
+      if (split) {
+        const ClusterTot* s_tot = reinterpret_cast<const ClusterTot*>(smem_raw + p.off_cl);
+        for (int r = 0; r < ncl; ++r) {
+          const ClusterTot* peer = dsmem_peer(s_tot, r);
+          for (int k = 0; k < 4; ++k) t[k] += peer->met[k];
+          mx = fmax(mx, peer->met[4]);
+        }
+      } else {
+        const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
+        for (int w = 0; w < nparts; ++w) {
+          const double* d = s_met + (size_t)(le * p.part_stride + w) * 5;
+          for (int k = 0; k < 4; ++k) t[k] += d[k];
+          mx = fmax(mx, d[4]);
+        }
       }
       const EnvScratch& es = s_env[le];
       const double dsp = es.sig_new - P;  // NEW signal (after a refresh, if one was due) minus this step's consumption
@@ -786,8 +1003,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
     }
   }
 
-  if (p.obs == nullptr) return;
-  R* gobs = reinterpret_cast<R*>(p.obs) + (size_t)((unsigned)env0 * (unsigned)N + (unsigned)wrow0) * F;
+  if (p.obs != nullptr) {
+  R* gobs = reinterpret_cast<R*>(p.obs) + (size_t)((unsigned)env0 * (unsigned)N + (unsigned)(split ? slice_lo : 0) + (unsigned)wrow0) * F;
   bool issued = false;
   for (int pass0 = 0; pass0 < nrows_w; pass0 += rpp) {
     const int nr = min(rpp, nrows_w - pass0);
@@ -798,74 +1015,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
         row[9] = (R)s_env[le].f_sig;
       }
     } else if (lane >= pass0 && lane < pass0 + nr) {
-      const EnvScratch& es = s_env[le];
-      R* row = stage + (lane - pass0) * F;
-      // own features, utils.normStateDict order (utils.py:774-840)
-      row[0] = (tt.x - 20) * (R)0.2;
-      row[1] = (tt.y - 20) * (R)0.2;
-      row[2] = (target - 20) * (R)0.2;
-      int c = 3;
-      if (state_flags & MDR_STATE_THERMAL) row[c++] = (R)es.f_od;
-      row[c++] = deadband;
-      if (state_flags & MDR_STATE_DAY) { row[c++] = (R)es.f_sin_day; row[c++] = (R)es.f_cos_day; }
-      if (state_flags & MDR_STATE_HOUR) { row[c++] = (R)es.f_sin_hr; row[c++] = (R)es.f_cos_hr; }
-      if (state_flags & MDR_STATE_SOLAR) row[c++] = (R)es.f_solar;
-      row[c++] = p_on * (R)p.cop_over_def_cap;
-      if (state_flags & MDR_STATE_THERMAL) {
-        row[c++] = (R)(p.ua[h] / p.def_ua);
-        row[c++] = (R)(p.cm[h] / p.def_cm);
-        row[c++] = (R)(p.ca[h] / p.def_ca);
-        row[c++] = (R)(p.hm[h] / p.def_hm);
-      }
-      if (state_flags & MDR_STATE_HVAC) {
-        row[c++] = (R)(p.hvac_cop / p.def_cop);
-        row[c++] = (R)(p.hvac_latent / p.def_latent);
-      }
-      row[c++] = (R)on;
-      row[c++] = (R)lock;
-      row[c++] = (R)sso * inv_lock;
-      row[c++] = (R)1;
-      row[c++] = (R)es.f_sig;
-      row[c++] = (R)(P * p.inv_norm_sig_agents);
-      // messages, SingleHouse.message :624-662 normalised as utils.py:842-868
-      R* mrow = row + c;
-      {
-        const size_t tbase = comm_mode == MDR_COMM_TABLE_PER_ENV ? (size_t)e * N * C : 0;
-        for (int k = 0; k < C; ++k) {
-          int j;
-          if (comm_mode == MDR_COMM_NEIGHBOURS) {
-            j = k < half ? li - half + k : li + 1 + (k - half);
-            if (j < 0) j += N;
-            if (j >= N) j -= N;
-          } else {
-            j = p.comm_table[tbase + (size_t)li * C + k];
-          }
-          const T4 m = s_msg[le * ns + half + j];
-          bool keep = true;
-          if (has_keep) keep = p.msg_keep[(size_t)h * C + k] != 0;
-          else if (has_defect) {
-            const uint4 r = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
-                                       STREAM_MSG + 16 * (uint32_t)k, p.seed);
-            keep = u01(r.x, r.y) > p.comm_defect_prob;
-          }
-          const R kf = keep ? (R)1 : (R)0;
-          mrow[0] = m.x * kf; mrow[1] = m.y * inv_lock * kf; mrow[2] = m.z * kf; mrow[3] = m.w * kf;
-          mrow += 4;
-          if (msg_flags) {
-            const size_t hj = (size_t)e * N + j;
-            if (msg_flags & MDR_MSG_THERMAL) {
-              mrow[0] = (R)(p.ua[hj] / p.def_ua) * kf; mrow[1] = (R)(p.cm[hj] / p.def_cm) * kf;
-              mrow[2] = (R)(p.ca[hj] / p.def_ca) * kf; mrow[3] = (R)(p.hm[hj] / p.def_hm) * kf;
-              mrow += 4;
-            }
-            if (msg_flags & MDR_MSG_HVAC) {
-              mrow[0] = (R)(p.hvac_cop / p.def_cop) * kf; mrow[1] = (R)(p.hvac_latent / p.def_latent) * kf;
-              mrow[2] = (R)(p.cap[hj] / p.def_cap) * kf;
-              mrow += 3;
-            }
-          }
-        }
-      }
+      HouseRow<R> hr;
+      hr.t_air = tt.x; hr.t_mass = tt.y; hr.target = target; hr.deadband = deadband; hr.p_on = p_on; hr.inv_lock = inv_lock;
+      hr.on = on; hr.lock = lock; hr.sso = sso; hr.P = P; hr.h = h; hr.e = e; hr.li = li;
+      generic_row<R>(p, stage + (lane - pass0) * F, hr, s_env[le], state_flags, msg_flags, comm_mode, has_keep, has_defect, C, msg_at);
     }
     R* dst = gobs + (size_t)pass0 * F;
     const uint32_t bytes = (uint32_t)(nr * F * sizeof(R));
@@ -886,11 +1039,15 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
     }
   }
   if (issued && lane == 0) bulk_wait_read_all();
+  }
+  // no CTA of the cluster may exit while a peer still reads its shared memory
+  if (split) cluster_sync_all();
 }
 
 #include "mdr_pipe.cuh"
 #include "mdr_fused.cuh"
 #include "mdr_populate.cuh"
+#include "mdr_big.cuh"
 
 // ----------------------------------------------------------------------------------------
 // host-side launch helpers
@@ -924,6 +1081,33 @@ static cudaError_t launch_step_t(const KernelParams& kp, const Geometry& g, cuda
   static std::atomic<uint64_t> latch{0};
   cudaError_t err = ensure_max_smem(step_kernel<R, kMaxThreads, kFast, kC>, latch);
   if (err != cudaSuccess) return err;
+  if (g.cluster > 1) {
+    // one env per thread-block cluster (clusters larger than 8 CTAs are "non-portable": opt in once per device)
+    if (g.cluster > 8) {
+      static std::atomic<uint64_t> np_latch{0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      const uint64_t bit = 1ull << (dev & 63);
+      if (!(np_latch.load(std::memory_order_acquire) & bit)) {
+        err = cudaFuncSetAttribute(step_kernel<R, kMaxThreads, kFast, kC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (err != cudaSuccess) return err;
+        np_latch.fetch_or(bit, std::memory_order_release);
+      }
+    }
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)g.cluster;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)g.ctas);
+    lc.blockDim = dim3((unsigned)g.threads);
+    lc.dynamicSmemBytes = g.smem_bytes;
+    lc.stream = stream;
+    lc.attrs = &attr;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, step_kernel<R, kMaxThreads, kFast, kC>, kp);
+  }
   step_kernel<R, kMaxThreads, kFast, kC><<<g.ctas, g.threads, g.smem_bytes, stream>>>(kp);
   return cudaGetLastError();
 }
@@ -1071,13 +1255,14 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
 }
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
-                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met) {
+                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met,
+                        int part_slots) {
   const SmemLayout L = smem_layout(real_bytes, hmax, genvs, nwarps, rows_per_pass, n_features, need_val, need_pen, has_obs,
-                                   n_comm, part_stride, need_met);
+                                   n_comm, part_stride, need_met, part_slots);
   if (kp) {
     kp->off_msg = (int)L.off_msg; kp->off_pw = (int)L.off_pw; kp->off_val = (int)L.off_val;
     kp->off_pen = (int)L.off_pen; kp->off_env = (int)L.off_env; kp->off_stage = (int)L.off_stage;
-    kp->off_met = (int)L.off_met;
+    kp->off_met = (int)L.off_met; kp->off_cl = (int)L.off_cl;
   }
   return L.total;
 }

@@ -22,6 +22,7 @@ struct KernelParams {
   int precision;                                              // MDR_F32 / MDR_F64 (kernels that are not templated on it)
   int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
+  int cl, cl_slice, off_cl;                                   // env split over a cluster of `cl` CTAs, `cl_slice` houses each; ClusterTot offset
   unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)
   int is_reset, comm_mode, state_flags, msg_flags, temp_penalty_mode, solar, base_power_mode, signal_mode;
   int n_sinusoids, interp_update_period, interp_nb_agents, perlin_nb_octaves, perlin_octaves_step, action_source;
@@ -50,6 +51,7 @@ struct KernelParams {
   const void* interp_table;
   void *obs, *reward;
   double* metrics;  // [E, MDR_N_METRICS] running accumulators (fused multi-step kernel), or nullptr
+  void* workspace;  // mdr_workspace_bytes() of scratch (envs beyond a thread-block cluster), or nullptr
   uint64_t step_index, seed;
   // scalars
   double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
@@ -64,17 +66,19 @@ struct KernelParams {
 };
 
 struct Geometry {
-  int envs_per_cta, threads, ctas, rows_per_pass, hmax, house_warps, pro_warp, part_stride, pro_batch;
+  int envs_per_cta, threads, ctas, rows_per_pass, hmax, house_warps, pro_warp, part_stride, part_slots, pro_batch;
   size_t smem_bytes, pipe_smem_bytes;
   const void* l2_window_base;  // optional persisting-L2 access policy window of the launch
   size_t l2_window_bytes;
   float l2_hit_ratio;
+  int cluster, cluster_slice;  // one env split over `cluster` CTAs (thread-block cluster) of `cluster_slice` houses; 1 = whole envs per CTA
   int max_ctas;  // cap on the persistent pipelined grid (0 = SMs x resident CTAs)
   bool no_pdl;   // MDR_FLAG_NO_PDL
 };
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
-                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met);
+                        int n_features, bool need_val, bool need_pen, bool has_obs, int n_comm, int part_stride, bool need_met,
+                        int part_slots = 0);
 size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int n_features, bool need_val, bool has_obs,
                         int n_comm, int part_stride, int pro_batch);
 int pipe_pro_batch(int envs_per_cta, bool has_obs);
@@ -84,6 +88,8 @@ cudaError_t launch_populate(const KernelParams& kp, const MdrPopulationSpec& spe
                             double* ca, double* hm, double* cap, double* target, double* deadband, int32_t* lockout_dur,
                             int precision, uint64_t draw_index, cudaStream_t stream);
 bool fused_eligible(const KernelParams& kp);
+cudaError_t launch_big(const KernelParams& kp, int precision, void* workspace, cudaStream_t stream);
+size_t big_workspace(int n_envs, int n_houses);
 cudaError_t launch_fused(const KernelParams& kp, const Geometry& g, int precision, int n_steps, cudaStream_t stream);
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);
 cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream);

@@ -184,6 +184,11 @@ class VecDemandResponseEnv:
         for k in self.env:
             setattr(e, k, p(self.env[k]))
         e.metrics = p(self.metrics)
+        need = C.c_size_t()
+        _lib.check(self.lib.mdr_workspace_bytes(C.byref(self.cfg), C.byref(need)), "mdr_workspace_bytes")
+        if need.value and (getattr(self, "_workspace", None) is None or self._workspace.numel() < need.value):
+            self._workspace = torch.zeros(need.value, dtype=torch.uint8, device=self.device)
+        e.workspace = p(getattr(self, "_workspace", None))
         self.envs_s = e
         self.in_s = _lib.MdrStepInputs()
         self.out_s = _lib.MdrOutputs()
@@ -191,10 +196,11 @@ class VecDemandResponseEnv:
         self._refs = (C.byref(self.cfg), C.byref(self.houses_s), C.byref(self.envs_s), C.byref(self.in_s),
                       C.byref(self.out_s))
 
-    def set_launch_options(self, *, no_pipeline=None, no_fused=None, no_pdl=None, max_ctas=None):
+    def set_launch_options(self, *, no_pipeline=None, no_fused=None, no_pdl=None, no_cluster=None, max_ctas=None):
         """MdrConfig.flags / max_ctas: pin the kernel choice (tests compare the pipelined, generic and fused kernels
         on the same inputs) and cap the persistent grid (so that every CTA walks many tiles in a small test)."""
-        for bit, v in ((_lib.FLAG_NO_PIPELINE, no_pipeline), (_lib.FLAG_NO_FUSED, no_fused), (_lib.FLAG_NO_PDL, no_pdl)):
+        for bit, v in ((_lib.FLAG_NO_PIPELINE, no_pipeline), (_lib.FLAG_NO_FUSED, no_fused), (_lib.FLAG_NO_PDL, no_pdl),
+                       (_lib.FLAG_NO_CLUSTER, no_cluster)):
             if v is not None:
                 self._flags = (self._flags | bit) if v else (self._flags & ~bit)
         if max_ctas is not None:
@@ -456,11 +462,12 @@ class VecDemandResponseEnv:
         return self.hvac >> 2
 
     def launch_geometry(self):
-        g, t, c, s, pl = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t(), C.c_int32()
+        g, t, c, s, pl, cl = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t(), C.c_int32(), C.c_int32()
         _lib.check(self.lib.mdr_launch_geometry(self._refs[0], int(self.with_obs), C.byref(g), C.byref(t), C.byref(c),
-                                                C.byref(s), C.byref(pl)), "mdr_launch_geometry")
-        return dict(envs_per_cta=g.value, threads=t.value, tiles=c.value, smem_bytes=s.value,
-                    kernel="mdr::step_pipe_kernel (persistent, software-pipelined)" if pl.value else "mdr::step_kernel")
+                                                C.byref(s), C.byref(pl), C.byref(cl)), "mdr_launch_geometry")
+        return dict(envs_per_cta=g.value, threads=t.value, tiles=c.value, smem_bytes=s.value, cluster_size=cl.value,
+                    kernel="mdr::step_pipe_kernel (persistent, software-pipelined)" if pl.value else
+                    ("mdr::big_update/env/finish_kernel (three launches)" if cl.value == 0 else "mdr::step_kernel"))
 
     # ------------------------------------------------------------------ checkpoint / copy
     _STATE = ("coef_a", "coef_b", "coef_c", "interp_key", "temps", "hvac", "lockout_dur", "t_epoch",
@@ -499,7 +506,7 @@ class VecDemandResponseEnv:
     def __deepcopy__(self, memo):
         new = object.__new__(type(self))
         memo[id(self)] = new
-        skip = {"lib", "cfg", "houses_s", "envs_s", "in_s", "out_s", "_refs", "_keep", "_pinned", "_arena", "coef_a",
+        skip = {"lib", "cfg", "houses_s", "envs_s", "in_s", "out_s", "_refs", "_keep", "_pinned", "_arena", "_workspace", "coef_a",
                 "coef_b", "coef_c", "temps", "hvac", "actions"}
         for k, v in self.__dict__.items():
             if k in skip:

@@ -79,23 +79,29 @@ def test_launch_geometry():
         for prec in (_lib.F32, _lib.F64):
             s = flat.to_struct(e, prec, 0)
             g, t, c, sm = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_size_t()
-            pl = ctypes.c_int32()
+            pl, cl = ctypes.c_int32(), ctypes.c_int32()
             assert lib.mdr_launch_geometry(ctypes.byref(s), 1, ctypes.byref(g), ctypes.byref(t), ctypes.byref(c),
-                                           ctypes.byref(sm), ctypes.byref(pl)) == 0
+                                           ctypes.byref(sm), ctypes.byref(pl), ctypes.byref(cl)) == 0
             assert pl.value == 0  # solar gain is on in the shipped default -> classic kernel
             cfg2 = __import__('copy').deepcopy(cfg)
             cfg2['default_house_prop']['solar_gain_bool'] = False
             s2 = mdr_b200.FlatConfig(cfg2).to_struct(e, prec, 0)
-            assert lib.mdr_launch_geometry(ctypes.byref(s2), 1, None, None, None, None, ctypes.byref(pl)) == 0
+            assert lib.mdr_launch_geometry(ctypes.byref(s2), 1, None, None, None, None, ctypes.byref(pl), None) == 0
             assert pl.value == (1 if (prec == _lib.F32 and n <= 100) else 0)  # persistent pipelined kernel
-            assert g.value * n <= t.value <= 1024 and t.value % 32 == 0
-            assert c.value == -(-e // g.value)
+            assert t.value <= 1024 and t.value % 32 == 0
+            if n <= 224:
+                assert cl.value == 1 and g.value * n <= t.value and c.value == -(-e // g.value)
+            else:  # one env split over a thread-block cluster: 1000 -> 5 CTAs x 200 houses, 1024 -> 5 x 208
+                assert g.value == 1 and 2 <= cl.value <= 8 and c.value == e * cl.value
+                assert (cl.value - 1) * (t.value - 32) < n <= cl.value * (t.value - 32)
             assert sm.value <= 227 * 1024
             out[(n, prec)] = (g.value, t.value, c.value, sm.value)
     assert out[(50, 4)][0] == 4 and out[(100, 4)][0] == 2  # CTA start rows 16-byte aligned for the bulk store
     cfg["default_env_prop"]["cluster_prop"]["nb_agents"] = 2000
     s = mdr_b200.FlatConfig(cfg).to_struct(1, _lib.F32, 0)
-    assert lib.mdr_validate(ctypes.byref(s)) == -6  # N > 1024 is outside this build
+    assert lib.mdr_validate(ctypes.byref(s)) == 0   # N > 1024: one env over a thread-block cluster
+    s = mdr_b200.FlatConfig(cfg).to_struct(1, _lib.F32, 0, action_source="greedy")
+    assert lib.mdr_validate(ctypes.byref(s)) == -6  # the on-device greedy controller sorts inside one CTA
 
 
 def test_bad_modes_raise_like_the_reference():
