@@ -210,6 +210,8 @@ typedef struct MdrStepInputs {
   const int32_t *comm_table;  /* MDR_COMM_TABLE(_PER_ENV) neighbour ids */
   const void *interp_table;   /* real[prod(interp_dims)], C order (mergedGridSearchResultFinal.npy) */
   uint64_t step_index;        /* counter for the Philox streams */
+  const uint64_t *step_counter; /* optional DEVICE counter added to step_index by the kernels: a CUDA graph that captured
+                                   a rollout advances it on the device, so replays do not repeat their draws */
   const uint8_t *env_mask;    /* mdr_reset only: [E], nonzero = reset this env; NULL = all.  Needs out->obs == NULL
                                  (follow with mdr_observe, which has no side effects) */
 } MdrStepInputs;
@@ -296,6 +298,14 @@ int mdr_step(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
    selected are not touched.  Follow with mdr_precompute and mdr_reset (same mask). */
 int mdr_populate(const MdrConfig *cfg, const MdrPopulationSpec *spec, const MdrHouses *houses, const MdrEnvs *envs,
                  const uint8_t *env_mask, uint64_t draw_index, void *stream);
+
+/* Rollout collection: the per-agent, per-step `Categorical(action_prob).sample()` of the reference's
+   learners (agents/ppo.py:68-75) for a whole batch in one launch.  probs = float [n_rows, n_actions] (un-normalised is
+   fine: Categorical divides by the row sum), actions = uint8 [n_rows] (what mdr_step reads), chosen_prob = float [n_rows]
+   or NULL: probs[row, action], the `a_log_prob` entry of agents/ppo.py:92-107.  Draws are Philox uniforms keyed by
+   (seed, row, draw_index + *draw_counter); draw_counter is an optional device counter (see MdrStepInputs.step_counter). */
+int mdr_sample_actions(const float *probs, int64_t n_rows, int32_t n_actions, uint64_t seed, uint64_t draw_index,
+                       const uint64_t *draw_counter, uint8_t *actions, float *chosen_prob, void *stream);
 
 /* Sets the device's persisting-L2 carve-out (cudaLimitPersistingL2CacheSize) to min(bytes, device maximum);
    bytes = 0 resets it and drops persisting lines.  Reports the granted carve-out and the largest access

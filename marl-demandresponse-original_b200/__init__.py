@@ -23,9 +23,9 @@ def __getattr__(name):
     if name == "MADemandResponseEnv":
         from .env import MADemandResponseEnv
         return MADemandResponseEnv
-    if name == "DeviceRolloutCollector":
-        from .rollout import DeviceRolloutCollector
-        return DeviceRolloutCollector
+    if name in ("DeviceRolloutCollector", "ActorMLP"):
+        from . import rollout
+        return getattr(rollout, name)
     if name in ("regenerate_table", "regenerate_entries"):
         from . import montecarlo
         return getattr(montecarlo, name)

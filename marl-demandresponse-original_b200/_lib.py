@@ -59,7 +59,7 @@ class MdrEnvs(C.Structure):
 
 class MdrStepInputs(C.Structure):
     _fields_ = [(n, _vp) for n in ("actions", "od_noise", "signal_noise", "interp_ids", "msg_keep", "comm_table",
-                                   "interp_table")] + [("step_index", C.c_uint64), ("env_mask", _vp)]
+                                   "interp_table")] + [("step_index", C.c_uint64), ("step_counter", _vp), ("env_mask", _vp)]
 
 
 class MdrPopulationSpec(C.Structure):
@@ -76,7 +76,7 @@ class MdrOutputs(C.Structure):
 
 EXPORTS = ("mdr_version", "mdr_strerror", "mdr_last_cuda_error", "mdr_obs_width", "mdr_validate",
            "mdr_launch_geometry", "mdr_precompute", "mdr_reset", "mdr_observe", "mdr_step", "mdr_step_host",
-           "mdr_l2_persist_limit", "mdr_populate", "mdr_workspace_bytes")
+           "mdr_l2_persist_limit", "mdr_populate", "mdr_workspace_bytes", "mdr_sample_actions")
 
 _lib = None
 
@@ -119,6 +119,7 @@ def load(build_if_missing: bool = True):
     lib.mdr_obs_width.argtypes = [P(MdrConfig)]
     lib.mdr_validate.argtypes = [P(MdrConfig)]
     lib.mdr_workspace_bytes.argtypes = [P(MdrConfig), P(C.c_size_t)]
+    lib.mdr_sample_actions.argtypes = [_vp, C.c_int64, _i32, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]
     lib.mdr_launch_geometry.argtypes = [P(MdrConfig), C.c_int, P(_i32), P(_i32), P(_i32), P(C.c_size_t), P(_i32), P(_i32)]
     lib.mdr_precompute.argtypes = [P(MdrConfig), P(MdrHouses), _vp]
     step_args = [P(MdrConfig), P(MdrHouses), P(MdrEnvs), P(MdrStepInputs), P(MdrOutputs)]

@@ -126,9 +126,13 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
     const int v = s ? atoi(s) : 0;
     return v >= 32 && v <= 992 ? v : 224;  // + 32 for the prologue warp = 256
   }();
+  // Splitting pays when whole-env CTAs would leave SMs idle (fewer envs than SMs) -- each CTA of this non-persistent
+  // kernel is latency-bound (~7 us), so with many envs more, smaller CTAs only add waves (measured: 1000 x 1000 houses
+  // 47 us as 1000 CTAs of 1024 threads, 87 us as 5000 CTAs of 256) -- and it is mandatory above 1024 houses.
   int slice = 0, ncl = 1;
-  const bool split = allow_split && N > 224 && !(c->flags & MDR_FLAG_NO_CLUSTER) && c->action_source != MDR_ACT_GREEDY &&
-                     split_geometry(c, &slice, &ncl);
+  const bool want_split = N > MDR_MAX_HOUSES_PER_ENV || (N > 224 && E < 148);
+  const bool split = allow_split && want_split && !(c->flags & MDR_FLAG_NO_CLUSTER && N <= MDR_MAX_HOUSES_PER_ENV) &&
+                     c->action_source != MDR_ACT_GREEDY && split_geometry(c, &slice, &ncl);
   if (!split && N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
   int gmax = target_threads / N;
   if (gmax < 1) gmax = 1;
@@ -313,7 +317,7 @@ static int fill_step(KernelParams& k, const MdrConfig* c, const MdrEnvs* e, cons
     if (is_reset != 1 || out->obs) return MDR_ERR_UNSUPPORTED;  // masked reset only, observation via mdr_observe
     k.env_mask = in->env_mask;
   }
-  k.interp_table = in->interp_table; k.step_index = in->step_index;
+  k.interp_table = in->interp_table; k.step_index = in->step_index; k.step_counter = in->step_counter;
   k.obs = out->obs; k.reward = out->reward;
   k.is_reset = is_reset;
   return MDR_OK;
@@ -465,6 +469,16 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     k.step_index += 1;
   }
   return MDR_OK;
+}
+
+extern "C" int mdr_sample_actions(const float* probs, int64_t n_rows, int32_t n_actions, uint64_t seed, uint64_t draw_index,
+                                  const uint64_t* draw_counter, uint8_t* actions, float* chosen_prob, void* stream) {
+  if (!probs || !actions) return MDR_ERR_NULL;
+  if (n_rows < 0 || n_actions < 1 || n_actions > 256) return MDR_ERR_SHAPE;
+  if (n_rows == 0) return MDR_OK;
+  cudaError_t err = mdr::launch_sample_actions(probs, (long long)n_rows, n_actions, seed, draw_index, draw_counter, actions,
+                                               chosen_prob, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? MDR_OK : cuda_fail(err);
 }
 
 extern "C" int mdr_reset(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs, const MdrStepInputs* in,

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kBigThreads) big_update_kernel(const __grid_co
       int cmd;
       if (p.action_source == MDR_ACT_ARRAY) cmd = p.actions[h] != 0;
       else if (p.action_source == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
-      else cmd = philox4x32((uint32_t)h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
+      else cmd = philox4x32((uint32_t)h, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt, lockdur = (int)cc.y;
       if (!on) sso += dt;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) big_env_kernel(const __grid_constant__ Ke
       if (N > nb) {
         if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + i];
         else {
-          const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+          const uint4 r = philox4x32((uint32_t)e, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
                                      STREAM_IDS + 16 * (uint32_t)i, p.seed);
           src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
         }

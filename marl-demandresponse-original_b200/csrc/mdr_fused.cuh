@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? (kInterp && 
       const int e2 = env0 + le2;
       const uint32_t t0 = (uint32_t)p.t_epoch[e2];
       if (j < K) {
-        const StepRec rec = env_record(p, e2, t0 + (uint32_t)(j + 1) * (uint32_t)dt, p.step_index + (uint64_t)j, kInterp);
+        const StepRec rec = env_record(p, e2, t0 + (uint32_t)(j + 1) * (uint32_t)dt, step_now(p) + (uint64_t)j, kInterp);
         s_rec[((b & 1) * G + le2) * 32 + lane] = make4((R)rec.od_new, (R)rec.sig_new, (R)rec.gain, (R)0);
         if (j == K - 1) {
           p.od_temp[e2] = rec.od_new;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? (kInterp && 
         int cmd;
         if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
         else {
-          const uint64_t si = p.step_index + (uint64_t)j;
+          const uint64_t si = step_now(p) + (uint64_t)j;
           cmd = philox4x32(h, (uint32_t)si, (uint32_t)(si >> 32), STREAM_ACT, p.seed).x & 1;
         }
         // HVAC.step, :475-492

@@ -38,6 +38,12 @@
 namespace mdr {
 
 
+// Step index of the Philox streams: the host's counter plus an optional device-resident one (CUDA-graph replays of a
+// captured rollout must not repeat their draws: the graph advances the device counter, the baked-in host value stays).
+__device__ __forceinline__ uint64_t step_now(const KernelParams& p) {
+  return p.step_counter != nullptr ? p.step_index + *p.step_counter : p.step_index;
+}
+
 // ----------------------------------------------------------------------------------------
 struct EnvScratch {
   double P, od_new, rew_sig, pen_mean, pen_max, hour_s, date, s_old, sig_new, sig_noise, base;
@@ -57,7 +63,10 @@ struct PipeEnv {
   float f_sig;       // normalised new signal = observation feature 9 (rewritten by a refresh)
   int due;           // interpolation refresh due for this env
   int time_sec;
-  double pad[3];
+  double sig_new;    // grid signal after this step (metric accumulators; not final when `due`)
+  float gain;        // solar gain of this step (0 with solar gain off), utils.py:1277-1350
+  int pad0;
+  double pad1;
 };
 static_assert(sizeof(PipeEnv) == 64, "PipeEnv must stay 64 bytes");
 
@@ -280,7 +289,7 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
       if (d < n_perlin) {
         terms += (double)perlin_octave(x, d, nb, p.perlin_octaves_step, pkey);
       } else {
-        normal = normal_from(philox4x32((uint32_t)e2, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_OD,
+        normal = normal_from(philox4x32((uint32_t)e2, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_OD,
                                         p.seed));
       }
     }
@@ -325,6 +334,9 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
       pe.f_sig = (float)(sig * p.inv_norm_sig_agents);
       pe.due = due;
       pe.time_sec = time_sec;
+      pe.sig_new = sig;
+      pe.gain = (float)gain;
+      if (p.solar) p.solar_gain[e2] = gain;
       p.t_epoch[e2] = (int64_t)t;
       p.od_temp[e2] = od_new;  // the house threads take the OLD value from the record
       if (!due) {
@@ -460,6 +472,16 @@ __device__ __forceinline__ R segmented_sum(R v, int key, int lane) {
 // One observation row in utils.normStateDict order (utils.py:774-880) for ANY flag / neighbour mode;
 // `msg_at(j)` returns the message (dT/5, sso, P/7500, Pmax/7500) of house j of the same env.
 // ----------------------------------------------------------------------------------------
+// Message drop of the production mode (np.random.rand() > comm_defect_prob, :992): one Philox block serves four
+// messages of a house; message k takes word k % 4 of block k / 4 as a 32-bit uniform.
+__device__ __forceinline__ uint4 drop_block(const KernelParams& p, unsigned h, int k4) {
+  return philox4x32(h, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_MSG + 16 * (uint32_t)k4, p.seed);
+}
+__device__ __forceinline__ bool drop_keep(const KernelParams& p, const uint4& r, int k) {
+  const uint32_t w = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
+  return ((double)w + 0.5) * (1.0 / 4294967296.0) > p.comm_defect_prob;
+}
+
 template <typename R>
 struct HouseRow {
   R t_air, t_mass, target, deadband, p_on, inv_lock;
@@ -505,6 +527,7 @@ __device__ __forceinline__ void generic_row(const KernelParams& p, R* row, const
   // messages, SingleHouse.message :624-662 normalised as utils.py:842-868
   R* mrow = row + c;
   const size_t tbase = comm_mode == MDR_COMM_TABLE_PER_ENV ? (size_t)e * N * C : 0;
+  uint4 dr = make_uint4(0, 0, 0, 0);
   for (int k = 0; k < C; ++k) {
     int j;
     if (comm_mode == MDR_COMM_NEIGHBOURS) {
@@ -518,9 +541,8 @@ __device__ __forceinline__ void generic_row(const KernelParams& p, R* row, const
     bool keep = true;
     if (has_keep) keep = p.msg_keep[(size_t)h * C + k] != 0;
     else if (has_defect) {
-      const uint4 r = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
-                                 STREAM_MSG + 16 * (uint32_t)k, p.seed);
-      keep = u01(r.x, r.y) > p.comm_defect_prob;
+      if ((k & 3) == 0) dr = drop_block(p, h, k >> 2);
+      keep = drop_keep(p, dr, k);
     }
     const R kf = keep ? (R)1 : (R)0;
     mrow[0] = m.x * kf; mrow[1] = m.y * inv_lock * kf; mrow[2] = m.z * kf; mrow[3] = m.w * kf;
@@ -682,7 +704,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
       if (p.action_source == MDR_ACT_ARRAY) cmd = cmd != 0;
       else if (p.action_source == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
       else if (p.action_source == MDR_ACT_GREEDY) cmd = greedy_cmd;
-      else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
+      else cmd = philox4x32(h, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
       const int lockdur = (int)lockdur_r;
@@ -874,7 +896,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
       if (N > nb) {
         if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
         else {
-          const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+          const uint4 r = philox4x32((uint32_t)e, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
                                      STREAM_IDS + 16 * (uint32_t)li, p.seed);
           src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
         }
@@ -1048,6 +1070,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
 #include "mdr_fused.cuh"
 #include "mdr_populate.cuh"
 #include "mdr_big.cuh"
+#include "mdr_rollout.cuh"
 
 // ----------------------------------------------------------------------------------------
 // host-side launch helpers
@@ -1133,12 +1156,12 @@ static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cuda
 // (different geometries alternate freely; any host thread may launch).
 struct OccEntry { int dev, threads; size_t smem; int ctas_per_sm, sm_count; };
 
-template <int kC, int kAct, bool kObs>
+template <int kC, int kAct, bool kObs, int kVar>
 static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, cudaStream_t stream) {
   static std::atomic<uint64_t> latch{0};
   static std::mutex mu;
   static std::vector<OccEntry> cache;
-  cudaError_t err = ensure_max_smem(step_pipe_kernel<kC, kAct, kObs>, latch);
+  cudaError_t err = ensure_max_smem(step_pipe_kernel<kC, kAct, kObs, kVar>, latch);
   if (err != cudaSuccess) return err;
   int dev = 0;
   err = cudaGetDevice(&dev);
@@ -1151,7 +1174,7 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
     if (ctas_per_sm == 0) {
       err = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
       if (err != cudaSuccess) return err;
-      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, step_pipe_kernel<kC, kAct, kObs>, g.threads, g.pipe_smem_bytes);
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, step_pipe_kernel<kC, kAct, kObs, kVar>, g.threads, g.pipe_smem_bytes);
       if (err != cudaSuccess) return err;
       if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
       cache.push_back(OccEntry{dev, g.threads, g.pipe_smem_bytes, ctas_per_sm, sm_count});
@@ -1189,19 +1212,28 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   lc.stream = stream;
   lc.attrs = attrs;
   lc.numAttrs = n_attrs;
-  return cudaLaunchKernelEx(&lc, step_pipe_kernel<kC, kAct, kObs>, kp);
+  return cudaLaunchKernelEx(&lc, step_pipe_kernel<kC, kAct, kObs, kVar>, kp);
+}
+
+template <int kC, bool kObs, int kVar>
+static cudaError_t launch_pipe_c(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, kObs, kVar>(kp, g, stream);
+  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, kObs, kVar>(kp, g, stream);
+  return launch_pipe_t<kC, MDR_ACT_RANDOM, kObs, kVar>(kp, g, stream);
 }
 
 template <int kC, bool kObs>
-static cudaError_t launch_pipe_c(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, kObs>(kp, g, stream);
-  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, kObs>(kp, g, stream);
-  return launch_pipe_t<kC, MDR_ACT_RANDOM, kObs>(kp, g, stream);
+static cudaError_t launch_pipe_v(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
+  // variant bits: 1 = metric accumulators, 2 = message drops (only meaningful with an observation)
+  const bool drops = kObs && (kp.msg_keep != nullptr || kp.comm_defect_prob > 0.0);
+  const bool metrics = kp.metrics != nullptr;
+  if (kObs && drops) return metrics ? launch_pipe_c<kC, kObs, (kObs ? 3 : 1)>(kp, g, stream) : launch_pipe_c<kC, kObs, (kObs ? 2 : 0)>(kp, g, stream);
+  return metrics ? launch_pipe_c<kC, kObs, 1>(kp, g, stream) : launch_pipe_c<kC, kObs, 0>(kp, g, stream);
 }
 
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  if (kp.obs != nullptr) return kp.C == 10 ? launch_pipe_c<10, true>(kp, g, stream) : launch_pipe_c<0, true>(kp, g, stream);
-  return kp.C == 10 ? launch_pipe_c<10, false>(kp, g, stream) : launch_pipe_c<0, false>(kp, g, stream);
+  if (kp.obs != nullptr) return kp.C == 10 ? launch_pipe_v<10, true>(kp, g, stream) : launch_pipe_v<0, true>(kp, g, stream);
+  return kp.C == 10 ? launch_pipe_v<10, false>(kp, g, stream) : launch_pipe_v<0, false>(kp, g, stream);
 }
 
 // tiles per prologue pass (power of two): as deep as the lanes (one per env at least), the ring
@@ -1220,11 +1252,14 @@ int pipe_pro_batch(int envs_per_cta, bool has_obs) {
   return b;
 }
 
+// The pipelined kernel takes the default observation layout (implicit `neighbours` messages, no optional feature
+// blocks), the individual_L2 penalty and whole envs of <= 224 houses per tile; solar gain, message drops (replayed or
+// Philox) and the metric accumulators are variants of it (runtime / template), so none of them changes the kernel.
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision) {
   return precision == MDR_F32 && kp.is_reset == 0 && kp.comm_mode == MDR_COMM_NEIGHBOURS && kp.state_flags == 0 &&
-         kp.msg_flags == 0 && kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && kp.msg_keep == nullptr &&
-         !(kp.comm_defect_prob > 0.0) && !kp.solar && g.pro_warp >= g.house_warps && g.threads <= 256 &&
-         g.rows_per_pass == 32 && g.pipe_smem_bytes > 0 && kp.action_source != MDR_ACT_GREEDY && kp.metrics == nullptr;
+         kp.msg_flags == 0 && kp.temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && g.pro_warp >= g.house_warps &&
+         g.threads <= 256 && g.rows_per_pass == 32 && g.pipe_smem_bytes > 0 && g.cluster <= 1 &&
+         kp.action_source != MDR_ACT_GREEDY;
 }
 
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream) {
@@ -1242,6 +1277,7 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   size_t o = 0;
   const size_t off_msg = o;   o += align16((size_t)2 * genvs * (n_houses + n_comm) * 4 * sizeof(float));
   const size_t off_pw = o;    o += align16((size_t)2 * genvs * part_stride * sizeof(double));
+  const size_t off_met = o;   o += align16((size_t)2 * genvs * part_stride * 5 * sizeof(float));  // metric partials
   const size_t off_val = o;   o += need_val ? align16((size_t)hmax * sizeof(double)) : 0;
   const size_t off_env = o;   o += align16((size_t)2 * pro_batch * genvs * sizeof(PipeEnv));
   const size_t off_ctl = o;   o += align16(sizeof(PipeCtl));
@@ -1250,6 +1286,7 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   if (kp) {
     kp->off_msg = (int)off_msg; kp->off_pw = (int)off_pw; kp->off_val = (int)off_val; kp->off_pen = 0;
     kp->off_env = (int)off_env; kp->off_stage = (int)off_stage; kp->off_in = (int)off_in; kp->off_ctl = (int)off_ctl;
+    kp->off_met = (int)off_met;
   }
   return o;
 }

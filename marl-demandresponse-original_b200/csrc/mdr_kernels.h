@@ -53,6 +53,7 @@ struct KernelParams {
   double* metrics;  // [E, MDR_N_METRICS] running accumulators (fused multi-step kernel), or nullptr
   void* workspace;  // mdr_workspace_bytes() of scratch (envs beyond a thread-block cluster), or nullptr
   uint64_t step_index, seed;
+  const uint64_t* step_counter;  // optional device-resident addend of step_index (CUDA-graph replay)
   // scalars
   double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
   double inv_norm_reg_sig, inv_norm_sig_agents, cop_over_def_cap, inv_perlin_period, inv_n, k_temp, k_sig, od_amplitude, od_bias, two_pi_over_24;
@@ -90,6 +91,8 @@ cudaError_t launch_populate(const KernelParams& kp, const MdrPopulationSpec& spe
 bool fused_eligible(const KernelParams& kp);
 cudaError_t launch_big(const KernelParams& kp, int precision, void* workspace, cudaStream_t stream);
 size_t big_workspace(int n_envs, int n_houses);
+cudaError_t launch_sample_actions(const float* probs, long long n_rows, int n_actions, uint64_t seed, uint64_t draw_index,
+                                  const uint64_t* draw_counter, uint8_t* actions, float* chosen_prob, cudaStream_t stream);
 cudaError_t launch_fused(const KernelParams& kp, const Geometry& g, int precision, int n_steps, cudaStream_t stream);
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);
 cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream);

@@ -158,6 +158,15 @@ __device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B
 // env like any other (the prologue parks its perlin value and marks it), and this pass -- after the
 // loop, same launch, same CTA, same tile order -- evaluates the table on the houses' NEW state,
 // re-evaluates the signal and patches observation feature 9 (the only output that depends on it).
+// signal-dependent metric accumulators of one env and step (MDR_M_SUM_SIGNAL ..., main-deploy.py:140-149)
+__device__ __forceinline__ void metrics_signal_terms(double* m, double sig, double P) {
+  const double d = sig - P;
+  m[MDR_M_SUM_SIGNAL] += sig;
+  m[MDR_M_SUM_SIGNAL_OFFSET] += d;
+  m[MDR_M_SUM_SIGNAL_ERROR] += fabs(d);
+  m[MDR_M_SUM_SQ_SIGNAL_ERROR] += d * d;
+}
+
 __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
@@ -182,14 +191,22 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
                  : "r"((int)due), "r"(T)
                  : "memory");
     if (!any) continue;
-    double od_new = 0.0;
-    if (due) od_new = p.od_temp[e];
+    double od_new = 0.0, hour_s = 0.0, date = 0.0;
+    if (due) {
+      od_new = p.od_temp[e];
+      if (p.solar) {  // interpolatePower point :1198-1207: seconds since midnight and tm_yday, 0 with solar gain off
+        Calendar cal = calendar_time((uint32_t)p.t_epoch[e]);
+        calendar_date(cal);
+        hour_s = (double)cal.sod;
+        date = (double)cal.yday;
+      }
+    }
     if (due && li < nsamp) {
       int src = li;
       if (N > nb) {
         if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
         else {
-          const uint4 r = philox4x32((uint32_t)e, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32),
+          const uint4 r = philox4x32((uint32_t)e, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
                                      STREAM_IDS + 16 * (uint32_t)li, p.seed);
           src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
         }
@@ -197,7 +214,7 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       const size_t hs = (size_t)e * N + src;
       const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
       const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-      s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, 0.0, 0.0);
+      s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
     }
     house_sync(T);
     if (due && li == 0) {
@@ -212,6 +229,8 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       p.time_since_interp[e] = 0;
       p.signal[e] = sig;
       s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
+      // the tile loop left the signal-dependent accumulators of a due env to this pass (its signal was not final)
+      if (p.metrics != nullptr) metrics_signal_terms(p.metrics + (size_t)e * MDR_N_METRICS, sig, p.cluster_power[e]);
     }
     house_sync(T);
     if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
@@ -219,8 +238,12 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
   }
 }
 
-template <int kC, int kAct, bool kObs>
+// kVar: bit 0 = metric accumulators (MDR_M_*) as an epilogue of the tile; bit 1 = message drops
+// (replayed msg_keep, or Philox against comm_defect_prob) in the observation rows.
+template <int kC, int kAct, bool kObs, int kVar>
 __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
+  constexpr bool kMetrics = (kVar & 1) != 0;
+  constexpr bool kDrops = kObs && (kVar & 2) != 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -263,6 +286,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   // warp-partial power sums: [2][G][part_stride]
   float* const part0 = reinterpret_cast<float*>(smem_raw + p.off_pw) + le * p.part_stride;
   const int part_buf = G * p.part_stride;
+  float* const met0 = reinterpret_cast<float*>(smem_raw + p.off_met) + le * p.part_stride * 5;  // [2][G][part_stride][5]
   const int first_warp = (le * N) >> 5;
   const int my_part = warp - first_warp;
   const int nparts = ((le * N + N - 1) >> 5) - first_warp + 1;
@@ -327,12 +351,13 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const PipeEnv* const env_buf = s_env + slot * G;
     mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);
     const float od_old = env_buf[le].od_old;
+    const float gain = env_buf[le].gain;  // 0 with solar gain off
     MDR_STAMP(1);
     cp_async_wait<1>();  // this thread's copies of the current tile have landed
     MDR_STAMP(2);
 
     // ---------------- phase A: per house ---------------------------------------------------
-    float t_air = 0, t_mass = 0, target = 0, p_on = 0, deadband = 0, inv_lock = 1, pen = 0, pw = 0;
+    float t_air = 0, t_mass = 0, target = 0, p_on = 0, deadband = 0, inv_lock = 1, pen = 0, pw = 0, terr = 0;
     int on = 0, lock = 0, sso = 0;
     float4* const msg = msg0 + sbuf * msg_buf;
     if (active) {
@@ -347,7 +372,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       on = hv & 1; sso = hv >> 2;
       if (kAct == MDR_ACT_ARRAY) cmd = cmd != 0;
       else if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
-      else cmd = philox4x32(h, (uint32_t)p.step_index, (uint32_t)(p.step_index >> 32), STREAM_ACT, p.seed).x & 1;
+      else cmd = philox4x32(h, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
       const int lockdur = (int)cc.y;
@@ -358,7 +383,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       if (!lock && !new_on && sso + dt < lockdur) lock = 1;
       on = new_on;
       // SingleHouse.update_temperature, :681-738, with the OLD outdoor temperature
-      const float qa = on ? cb.y : 0.0f;
+      const float qa = (on ? cb.y : 0.0f) + gain;  // this step's solar gain (new datetime, :694)
       const float tss = od_old + qa * cb.x;
       const float x = tt.x - tss, y = tt.y - tss;
       t_air = tt.x + (ca4.x * x + ca4.y * y);
@@ -375,14 +400,34 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       const float hi = target + deadband * 0.5f, lo = target - deadband * 0.5f;
       if (hi < t_air) pen = (t_air - hi) * (t_air - hi);
       else if (lo > t_air) pen = (lo - t_air) * (lo - t_air);
+      terr = t_air - target;
     }
     float* const part = part0 + sbuf * part_buf;
     {
       const int key = active ? le : -1;
-      // fp32 partial sums are exact here: integer-valued watts, at most 224 houses (< 2^24 W)
+      // fp32 partial sums: exact for integer-valued watts (every shipped capacity / COP; at most 224 houses < 2^24 W),
+      // within fp32 rounding otherwise
       const float psum = segmented_sum<float>(pw, key, lane);
       const int prev_key = __shfl_up_sync(0xffffffffu, key, 1);
-      if (active && (lane == 0 || prev_key != key)) part[my_part] = psum;
+      const bool head = active && (lane == 0 || prev_key != key);
+      if (head) part[my_part] = psum;
+      if (kMetrics) {
+        // per-house terms of main-deploy.py:124-139 / metrics.py:22-25; the reward sum follows from the penalty sum
+        // (r_k = -(k_T pen_k + k_S dn^2), the second term is the same for every house of the env)
+        const float s0 = segmented_sum<float>(pen, key, lane), s1 = segmented_sum<float>(terr, key, lane);
+        const float s2 = segmented_sum<float>(fabsf(terr), key, lane), s3 = segmented_sum<float>(terr * terr, key, lane);
+        float s4 = fabsf(terr);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float tv = __shfl_down_sync(0xffffffffu, s4, o);
+          const int tk = __shfl_down_sync(0xffffffffu, key, o);
+          if (lane + o < 32 && tk == key) s4 = fmaxf(s4, tv);
+        }
+        if (head) {
+          float* d = met0 + (sbuf * part_buf + my_part) * 5;
+          d[0] = s0; d[1] = s1; d[2] = s2; d[3] = s3; d[4] = s4;
+        }
+      }
     }
     MDR_STAMP(3);
     // the staging rows of this warp may still be read by the previous tile's bulk store (waited for
@@ -405,6 +450,31 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         if (w < nparts) P += part[w];
       if (li == 0) p.cluster_power[e] = (double)P;
     }
+    if (kMetrics && active && li == 0) {
+      double t[4] = {0.0, 0.0, 0.0, 0.0};
+      float mxf = 0.0f;
+      const float* d = met0 + sbuf * part_buf * 5;
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if (w < nparts) {
+          t[0] += (double)d[w * 5 + 0]; t[1] += (double)d[w * 5 + 1]; t[2] += (double)d[w * 5 + 2]; t[3] += (double)d[w * 5 + 3];
+          mxf = fmaxf(mxf, d[w * 5 + 4]);
+        }
+      const PipeEnv& pe = env_buf[le];
+      const double mx = (double)mxf, Pd = (double)P;
+      const double dn = (Pd - pe.s_old) * p.inv_n;
+      double* m = p.metrics + (size_t)e * MDR_N_METRICS;
+      m[MDR_M_STEPS] += 1.0;
+      m[MDR_M_SUM_MEAN_REWARD] += -(t[0] * p.inv_n * p.k_temp + dn * dn * p.k_sig);
+      m[MDR_M_SUM_MEAN_TEMP_OFFSET] += t[1] * p.inv_n;
+      m[MDR_M_SUM_MEAN_TEMP_ERROR] += t[2] * p.inv_n;
+      m[MDR_M_SUM_SQ_TEMP_ERROR] += t[3];
+      m[MDR_M_SUM_SQ_MAX_TEMP_ERROR] += mx * mx;
+      m[MDR_M_MAX_TEMP_ERROR] = fmax(m[MDR_M_MAX_TEMP_ERROR], mx);
+      m[MDR_M_SUM_OD_TEMP] += pe.od_new;
+      m[MDR_M_SUM_CONSUMPTION] += Pd;
+      if (!pe.due) metrics_signal_terms(m, pe.sig_new, Pd);  // a due env: after its refresh (pipe_refresh_pass)
+    }
     if (kObs && active) {
       // fast-path row: [T_air, T_mass, target, deadband, cap, on, lockout, sso, 1, signal, power | C x 4 messages]
       row[0] = (t_air - 20.0f) * 0.2f;
@@ -420,13 +490,24 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       // neighbours (:816-828) = the C window entries around this house, skipping itself
       const float4* win = msg - half;
       float* mrow = row + 11;
+      uint4 dr = make_uint4(0, 0, 0, 0);
 #pragma unroll
       for (int k = 0; k < (kC > 0 ? kC : C); ++k) {
         const float4 m = win[k + (k >= half ? 1 : 0)];
-        mrow[4 * k + 0] = m.x;
-        mrow[4 * k + 1] = m.y * inv_lock;
-        mrow[4 * k + 2] = m.z;
-        mrow[4 * k + 3] = m.w;
+        float kf = 1.0f;
+        if (kDrops) {  // np.random.rand() > comm_defect_prob (:992): replayed, or one Philox block per four messages
+          bool keep;
+          if (p.msg_keep != nullptr) keep = p.msg_keep[(size_t)h * C + k] != 0;
+          else {
+            if ((k & 3) == 0) dr = drop_block(p, h, k >> 2);
+            keep = drop_keep(p, dr, k);
+          }
+          kf = keep ? 1.0f : 0.0f;
+        }
+        mrow[4 * k + 0] = m.x * kf;
+        mrow[4 * k + 1] = m.y * inv_lock * kf;
+        mrow[4 * k + 2] = m.z * kf;
+        mrow[4 * k + 3] = m.w * kf;
       }
     }
     MDR_STAMP(6);

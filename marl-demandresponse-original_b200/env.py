@@ -188,6 +188,11 @@ class MADemandResponseEnv:
             if comm_rows:
                 comm = np.asarray(comm_rows, dtype=np.int32)[None]
                 self._comm_host = comm[0]
+        elif c > 0:
+            # the reference calls np.random.rand() once per message at every observation (:992) even when nothing can be
+            # dropped: consume the same N*C uniforms so that learners sharing the global numpy stream
+            # (agents/network.py:161,172, agents/ddpg.py:268) see the reference's sequence under the same seed
+            np.random.rand(n * c)
         return comm, keep
 
     _ENV_SCALARS = ("od_temp", "signal", "cluster_power", "base_power", "solar_gain")

@@ -259,6 +259,7 @@ class VecDemandResponseEnv:
         s.actions, s.od_noise, s.signal_noise, s.interp_ids = p(act), p(od), p(sn), p(ids)
         s.msg_keep, s.comm_table, s.interp_table = p(mk), p(cm), p(self._table)
         s.step_index = self.step_index
+        s.step_counter = None
 
     # ------------------------------------------------------------------ API
     def precompute(self):
@@ -328,13 +329,15 @@ class VecDemandResponseEnv:
         return self.obs
 
     def step_tensor(self, actions=None, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None,
-                    comm=None, n_steps=1, obs_out=None, reward_out=None):
+                    comm=None, n_steps=1, obs_out=None, reward_out=None, step_counter=None):
         """One env step for every cluster.  `actions` [E, N] (nonzero = ON) unless the env was
         built with an on-device action source.  Replay arguments feed host-drawn randomness
         (parity mode); when omitted the kernel draws from Philox / evaluates its own perlin."""
         if not self._precomputed:
             self.precompute()
         self._set_inputs(actions, od_noise, signal_noise, interp_ids, msg_keep, comm)
+        # optional device-resident addend of the Philox step index (int64 [1]): CUDA-graph replays advance it on the device
+        self.in_s.step_counter = C.c_void_p(step_counter.data_ptr()) if step_counter is not None else None
         obs, reward = self.obs, self.reward
         if obs_out is not None or reward_out is not None:
             # zero-copy: the kernel writes straight into the caller's rollout storage

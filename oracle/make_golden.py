@@ -272,6 +272,52 @@ def _c1(cfg):
                 check=[0, 1, 2, 9, 19, 39, 59, 74, 75, 79], obs_steps=[0, 75])
 
 
+class DeployAccumulators:
+    """The reference's own deploy-loop accumulators (main-deploy.py:85-97 initialisation, :124-149 per-step update,
+    with `opt.start_stats_from = 0`) and its training `Metrics` class (metrics.py:13-30), EXECUTED from the reference's
+    source on the reference's obs / reward dicts -- the fixture for the on-device accumulators (MDR_M_*).
+    The source lines are located by their text, compiled and run unmodified."""
+
+    FIRST_INIT, LAST_INIT = "cumul_temp_offset = 0", "cumul_squared_max_error_temp = 0"
+    FIRST_STEP, LAST_STEP = "    max_temp_error_houses = 0", "        cumul_squared_error_sig += signal_error**2"
+
+    def __init__(self, env):
+        import textwrap
+        import types
+        lines = open(os.path.join(ref_stubs.REFERENCE_ROOT, "main-deploy.py"), encoding="utf-8").read().split("\n")
+        i0, i1 = lines.index(self.FIRST_INIT), lines.index(self.LAST_INIT)
+        s0 = next(k for k, l in enumerate(lines) if l.rstrip() == self.FIRST_STEP)
+        s1 = next(k for k, l in enumerate(lines) if l.rstrip() == self.LAST_STEP)
+        assert i0 < i1 < s0 < s1
+        self.ns = {"np": np, "env": env, "opt": types.SimpleNamespace(start_stats_from=0)}
+        exec(compile("\n".join(lines[i0:i1 + 1]), "main-deploy.py:init", "exec"), self.ns)
+        self.step_code = compile(textwrap.dedent("\n".join(lines[s0:s1 + 1])), "main-deploy.py:step", "exec")
+        sys.path.insert(0, ref_stubs.REFERENCE_ROOT)
+        from metrics import Metrics  # the reference's class
+        self.metrics, self.env, self.steps = Metrics(), env, 0
+
+    def update(self, i, obs_dict, rewards_dict):
+        self.ns.update(i=i, obs_dict=obs_dict)
+        exec(self.step_code, self.ns)
+        for k in obs_dict.keys():
+            self.metrics.update(k, obs_dict, rewards_dict, self.env)
+        self.steps += 1
+
+    def arrays(self):
+        ns, m = self.ns, self.metrics
+        deploy = [ns[k] for k in ("cumul_temp_offset", "cumul_temp_error", "max_temp_error", "cumul_signal_offset",
+                                  "cumul_signal_error", "cumul_OD_temp", "cumul_signal", "cumul_cons",
+                                  "cumul_squared_error_sig", "cumul_squared_error_temp", "cumul_squared_max_error_temp")]
+        train = [m.cumul_avg_reward, m.cumul_temp_offset, m.cumul_temp_error, m.cumul_signal_offset, m.cumul_signal_error]
+        return np.array(deploy, np.float64), np.array(train, np.float64)
+
+
+DEPLOY_KEYS = ("cumul_temp_offset", "cumul_temp_error", "max_temp_error", "cumul_signal_offset", "cumul_signal_error",
+               "cumul_OD_temp", "cumul_signal", "cumul_cons", "cumul_squared_error_sig", "cumul_squared_error_temp",
+               "cumul_squared_max_error_temp")
+TRAIN_KEYS = ("cumul_avg_reward", "cumul_temp_offset", "cumul_temp_error", "cumul_signal_offset", "cumul_signal_error")
+
+
 def run_case(name, Env, norm, cfg, perlin_cls):
     spec = CASES[name](cfg)
     c = spec["config"]
@@ -331,6 +377,7 @@ def run_case(name, Env, norm, cfg, perlin_cls):
         out = {k: [] for k in ("t_air", "t_mass", "on", "lockout", "sso", "reward")}
         power, signal, od_temp, solar = np.zeros(steps), np.zeros(steps), np.zeros(steps), np.zeros(steps)
         obs_rec = []
+        acc = DeployAccumulators(env)
         for t in range(steps):
             if spec["policy"] == "bangbang":
                 act = {i: bool(obs[i]["house_temp"] > obs[i]["house_target_temp"]) for i in env.agent_ids}
@@ -351,6 +398,7 @@ def run_case(name, Env, norm, cfg, perlin_cls):
                 msg_keep[t] = (np.array(rands) > defect).astype(np.uint8).reshape(n, C)
             if samples:
                 comm_t[t] = np.array(samples, dtype=np.int32).reshape(n, C)
+            acc.update(t, obs, rew)
             power[t] = info["cluster_hvac_power"]
             signal[t] = env.power_grid.current_signal
             od_temp[t] = env.cluster.current_OD_temp
@@ -385,6 +433,7 @@ def run_case(name, Env, norm, cfg, perlin_cls):
         on=np.array(out["on"], np.uint8), lockout=np.array(out["lockout"], np.uint8),
         sso=np.array(out["sso"], np.int32), reward=np.array(out["reward"]),
     )
+    data["deploy_acc"], data["train_acc"] = acc.arrays()  # order: DEPLOY_KEYS / TRAIN_KEYS
     if comm0 is not None:
         data["comm"] = comm0
     if comm_t is not None:

@@ -107,10 +107,11 @@ def deadband_l2(target, deadband, value):
 
 class ScalarEnv:
     """One cluster.  `snap` is a single-env snapshot (see oracle/mdr_oracle.py), `config` the
-    reference config dict.  Supports: `neighbours` messages, individual_L2 penalty, constant base
-    power, flat / sinusoidals / perlin (replayed noise) signal, solar gain off."""
+    reference config dict.  Supports: `neighbours` messages, individual_L2 penalty, constant or interpolated base
+    power (`interp` = oracle.mdr_oracle.PowerInterp; env/MA_DemandResponse.py:1195-1255), flat / sinusoidals /
+    perlin (replayed noise) signal, solar gain off."""
 
-    def __init__(self, config, snap):
+    def __init__(self, config, snap, interp=None):
         ep = config["default_env_prop"]
         self.config = config
         self.dt = int(ep["time_step"])
@@ -138,6 +139,27 @@ class ScalarEnv:
         self.gp = ep["power_grid_prop"]
         self.rp = ep["reward_prop"]
         self.house_def = config["default_house_prop"]
+        self.interp = interp
+        self.base_power = float(snap["base_power"]) if "base_power" in snap else 0.0
+        self.time_since_interp = int(snap["time_since_interp"]) if "time_since_interp" in snap else 0
+
+    def _interpolate_power(self, ids):
+        """PowerGrid.interpolatePower :1195-1234 (solar gain off: hour = date = 0); `ids` replays random.choices."""
+        ip = self.gp["base_power_parameters"]["interpolation"]
+        hd = self.house_def
+        if self.n <= ip["interp_nb_agents"]:
+            ids, factor = list(range(self.n)), 1
+        else:
+            factor = float(self.n) / ip["interp_nb_agents"]
+        base = 0
+        for i in ids:
+            house = self.houses[int(i)]
+            point = {"date": 0.0, "hour": 0.0, "Ua_ratio": house.ua / hd["Ua"], "Cm_ratio": house.cm / hd["Cm"],
+                     "Ca_ratio": house.ca / hd["Ca"], "Hm_ratio": house.hm / hd["Hm"],
+                     "air_temp": house.t_air - house.target, "mass_temp": house.t_mass - house.target,
+                     "OD_temp": self.od_temp - house.target, "HVAC_power": house.hvac.cap}
+            base += self.interp.fast(self.interp.clip(point))
+        return base * factor
 
     def _obs_dict(self):
         obs = {}
@@ -156,7 +178,7 @@ class ScalarEnv:
             obs[i] = d
         return obs
 
-    def step(self, action_dict, od_noise, sig_noise=0.0):
+    def step(self, action_dict, od_noise, sig_noise=0.0, interp_ids=None):
         self.datetime += _dt.timedelta(seconds=self.dt)
         for i, house in self.houses.items():
             house.hvac.step(action_dict[i])
@@ -178,7 +200,14 @@ class ScalarEnv:
             pen = deadband_l2(house.target, house.deadband, house.t_air)
             rewards[i] = -1 * (self.rp["alpha_temp"] * pen / norm_temp + self.rp["alpha_sig"] * sig_pen / norm_sig)
         # power grid
-        base = self.gp["base_power_parameters"]["constant"]["avg_power_per_hvac"] * self.n
+        if self.gp["base_power_mode"] == "interpolation":      # PowerGrid.step :1250-1255
+            self.time_since_interp += self.dt
+            if self.time_since_interp >= self.gp["base_power_parameters"]["interpolation"]["interp_update_period"]:
+                self.base_power = self._interpolate_power(interp_ids)
+                self.time_since_interp = 0
+            base = self.base_power
+        else:
+            base = self.gp["base_power_parameters"]["constant"]["avg_power_per_hvac"] * self.n
         mode = self.gp["signal_mode"]
         params = self.gp["signal_parameters"][mode]
         if mode == "flat":
@@ -210,23 +239,26 @@ class ScalarEnv:
         return out
 
 
-def timed_rollout(config, snap, steps, seed=0):
+def timed_rollout(config, snap, steps, seed=0, interp=None, normalise=True):
     """Steps one cluster `steps` times with a bang-bang policy (agents/bangbang_controllers.py:41-61)
     and normalises every agent's observation, like a learner's rollout loop (train_ppo.py:62-116).
+    `interp` (PowerInterp) enables the interpolated base power with its refresh every interp_update_period.
     Returns (house_steps, seconds)."""
     import random
     import time
 
     rng = random.Random(seed)
-    env = ScalarEnv(config, snap)
+    env = ScalarEnv(config, snap, interp)
+    nb = config["default_env_prop"]["power_grid_prop"]["base_power_parameters"]["interpolation"]["interp_nb_agents"]
     obs = env._obs_dict()
     for d in obs.values():
         d["reg_signal"], d["cluster_hvac_power"] = env.signal, env.cluster_power
     t0 = time.perf_counter()
     for _ in range(steps):
         act = {i: obs[i]["house_temp"] > obs[i]["house_target_temp"] for i in obs}
-        obs, rew, _, _ = env.step(act, rng.gauss(0, 0.5), rng.uniform(-0.3, 0.3))
-        vecs = [env.norm_state(obs[i]) for i in obs]
+        ids = rng.choices(range(env.n), k=nb) if (interp is not None and env.n > nb) else None
+        obs, rew, _, _ = env.step(act, rng.gauss(0, 0.5), rng.uniform(-0.3, 0.3), ids)
+        vecs = [env.norm_state(obs[i]) for i in obs] if normalise else [None] * env.n
     dt = time.perf_counter() - t0
     assert len(vecs) == env.n
     return env.n * steps, dt

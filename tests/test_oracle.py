@@ -204,15 +204,18 @@ def test_oracle_initial_grid_step(name):
     assert env.s["base_power"][0] == pytest.approx(float(g.snap["base_power"]), rel=1e-14)
 
 
-@pytest.mark.parametrize("name", ["c0_bangbang_50", "tiny_3_comm_clipped"])
+@pytest.mark.parametrize("name", ["c0_bangbang_50", "tiny_3_comm_clipped", "interp_40_perlin", "c1_1000_fp64"])
 def test_scalar_port_matches_reference_trace(name):
-    """The per-object python port used as the CPU baseline walks the reference trajectory."""
+    """The per-object python port used as the CPU baseline walks the reference trajectory (incl. the interpolated base
+    power with sampled houses)."""
     from oracle import mdr_oracle_scalar as sc
     g = gu.Golden(name)
-    env = sc.ScalarEnv(g.config, g.snap)
+    interp = orc.PowerInterp(gu.synthetic_table(), gu.INTERP_GRID, gu.INTERP_KEYS) if g.uses_interp else None
+    env = sc.ScalarEnv(g.config, g.snap, interp)
     ci = oi = 0
     for t in range(g.steps):
-        obs, rew, done, info = env.step({i: bool(g.actions[t][i]) for i in range(g.n)}, g.od_noise[t], g.sig_noise[t])
+        ids = g.interp_ids[t] if g.interp_ids[t][0] >= 0 else None
+        obs, rew, done, info = env.step({i: bool(g.actions[t][i]) for i in range(g.n)}, g.od_noise[t], g.sig_noise[t], ids)
         assert info["cluster_hvac_power"] == g.power[t]
         assert env.signal == pytest.approx(g.signal[t], rel=1e-13)
         if t in g.check_steps:

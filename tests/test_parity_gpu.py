@@ -269,3 +269,47 @@ def test_pipelined_kernel_matches_oracle(n_envs, n, interp, signal, nb_comm):
     assert np.array_equal(env.t_epoch.cpu().numpy(), oracle.s["t_epoch"])
     if interp:
         assert refreshes >= 2  # the deferred refresh pass ran at least twice
+
+
+# order of golden `deploy_acc` (oracle/make_golden.py DEPLOY_KEYS, main-deploy.py:85-97) -> MDR_M_* column
+_DEPLOY_TO_M = ("sum_mean_temp_offset", "sum_mean_temp_error", "max_temp_error", "sum_signal_offset", "sum_signal_error",
+                "sum_od_temp", "sum_signal", "sum_consumption", "sum_sq_signal_error", "sum_sq_temp_error",
+                "sum_sq_max_temp_error")
+
+
+def check_metrics_against_reference(g, m, precision):
+    """`m` = one env's MDR_M_* accumulators after the golden trace; golden `deploy_acc` / `train_acc` are the values the
+    reference's own code produced on its own trace (main-deploy.py:124-149 executed from source, metrics.Metrics.update)."""
+    from mdr_b200 import _lib
+    col = {k: float(m[i]) for i, k in enumerate(_lib.METRIC_NAMES)}
+    tol = dict(rtol=1e-9, atol=1e-9) if precision == "fp64" else dict(rtol=2e-4, atol=1e-3)
+    assert col["steps"] == g.steps
+    for ref, key in zip(g.deploy_acc, _DEPLOY_TO_M):
+        np.testing.assert_allclose(col[key], ref, err_msg=key, **tol)
+    n = g.n
+    train = g.train_acc  # Metrics: cumul_avg_reward, temp_offset, temp_error, signal_offset, signal_error (metrics.py:22-30)
+    np.testing.assert_allclose(col["sum_mean_reward"], train[0], err_msg="cumul_avg_reward", **tol)
+    np.testing.assert_allclose(col["sum_mean_temp_offset"], train[1], **tol)
+    np.testing.assert_allclose(col["sum_mean_temp_error"], train[2], **tol)
+    np.testing.assert_allclose(col["sum_signal_offset"] / n, train[3], **tol)
+    np.testing.assert_allclose(col["sum_signal_error"] / n, train[4], **tol)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", gu.names())
+def test_device_metrics_match_reference_accumulators(name, precision):
+    """the on-device accumulators after replaying a reference trace == the reference's own deploy-loop
+    accumulators and training Metrics on that trace.  fp32 configurations that the pipelined kernel takes keep it with
+    metrics enabled (accumulators are an epilogue of that kernel too)."""
+    g = gu.Golden(name)
+    env = _env_from_golden(g, precision)
+    plain = env.launch_geometry()["kernel"]
+    env.enable_metrics()
+    assert env.launch_geometry()["kernel"] == plain   # metrics do not change which kernel runs
+    env.observe_tensor(msg_keep=g.init_keep[None])
+    for t in range(g.steps):
+        ids = g.interp_ids[t][None] if g.interp_ids[t][0] >= 0 else None
+        comm = None if g.comm_t is None else g.comm_t[t][None]
+        env.step_tensor(g.actions[t][None], od_noise=g.od_noise[t:t + 1], signal_noise=g.sig_noise[t:t + 1],
+                        interp_ids=ids, msg_keep=g.msg_keep[t][None], comm=comm)
+    check_metrics_against_reference(g, env.metrics[0].cpu().numpy(), precision)
