@@ -344,6 +344,9 @@ def gpu_arm(args):
     # ---- end-to-end: host-buffer C-ABI call, pinned H2D of the actions + D2H of obs/reward/power/signal
     k_e2e = max(3, min(args.steps, args.e2e_steps))
     host_actions = [r.cpu().numpy() for r in ring[:4]]
+    if not args.serial_e2e:
+        ncpu = len(os.sched_getaffinity(0))
+        env.host_pipeline(True, n_threads=max(1, min(24, ncpu if not distributed else ncpu // max(1, world // 2))))
     for i in range(2):
         env.step_host(host_actions[i & 3])
     if distributed:
@@ -402,7 +405,8 @@ def gpu_arm(args):
             "config": config, "launch": geom, "env_steps_per_launch": fused, "numa_node": numa,
             "clocks": clocks, "gpu_launches": args.steps // fused * (2 if rollout else 1),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": k_e2e, "api": "VecDemandResponseEnv.step_host -> mdr_step_host (pinned host buffers)"},
+                    "steps": k_e2e, "api": "VecDemandResponseEnv.step_host -> mdr_step_host (pinned host buffers)",
+                    "pipeline": env.host_pipeline_info()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_house_step": algo,
                          "kernel": geom["kernel"], "launch_us": launch_s * 1e6 * fused, "fused_k": fused,
@@ -488,6 +492,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3000,
                     help="env steps per CPU-baseline process (default: ~3 s per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial-e2e", action="store_true", help="e2e leg without the MdrHostCtx pipeline (one H2D, one launch, four D2H)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

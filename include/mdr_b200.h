@@ -10,8 +10,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every device buffer is allocated by the caller (torch,
- *     cudaMalloc, ...) on `MdrConfig.device`; the library never allocates or frees device memory and never
- *     synchronises the stream except in the *_host entry points.  The only process-wide state is a
+ *     cudaMalloc, ...) on `MdrConfig.device`; the library never allocates or frees device memory (except the staging
+ *     buffers of an explicitly created MdrHostCtx) and never synchronises the stream except in mdr_step_host.  The only process-wide state is a
  *     mutex-protected cache of per-device launch attributes (occupancy, opt-in shared memory) and the
  *     tuning environment variables MDR_TARGET_THREADS / MDR_PRO_BATCH, read once at first use;
  *   - every function returns an MdrStatus (0 = OK, negative = error) and never throws/prints;
@@ -312,13 +312,29 @@ int mdr_sample_actions(const float *probs, int64_t n_rows, int32_t n_actions, ui
    policy window of the device.  Device-global setting: call once per process and device. */
 int mdr_l2_persist_limit(int device, size_t bytes, size_t *granted_bytes, size_t *max_window_bytes);
 
-/* Same step with HOST buffers: copies `host_actions` to `in->actions` (device staging), runs
-   the step, copies obs / reward / per-env (power, signal) back into the host pointers and
-   synchronises the stream.  This is the call the dict API and the e2e benchmark use. */
+/* Resources of the pipelined host-buffer path (two internal streams, events, a device + a pinned host staging buffer
+   of n_envs * n_houses * 16 reals, `n_threads` worker threads; 0 = the calling thread's CPU affinity count, at most 24;
+   n_slices 0 = 8).  The ONE place where the library allocates; the pinned staging is first touched by the creating
+   thread, so pin the process to the GPU's NUMA node before creating it.  One context per shard; not thread-safe. */
+typedef struct MdrHostCtx MdrHostCtx;
+int mdr_host_ctx_create(const MdrConfig *cfg, int32_t n_threads, int32_t n_slices, MdrHostCtx **ctx);
+int mdr_host_ctx_destroy(MdrHostCtx *ctx);
+int mdr_host_ctx_info(const MdrHostCtx *ctx, int32_t *n_threads, int32_t *n_slices, size_t *compact_bytes);
+
+/* Same step with HOST buffers: copies `host_actions` to `in->actions` (device staging), runs the step, brings
+   obs / reward / per-env (power, signal) back into the host pointers and synchronises the stream.  This is the call
+   the dict API and the e2e benchmark use.
+   ctx == NULL: one H2D, one launch, four D2H on `stream` (the full [E, N, F] observation crosses PCIe).
+   ctx != NULL and the default observation layout (implicit `neighbours` messages, no optional feature blocks, no
+   message drops): the env axis is cut into slices alternating between the context's two streams, so uploads, kernels
+   and downloads of different slices overlap; per house only a 16-real record crosses PCIe (own 11 features, its
+   4-real message, 1 / lockout_duration -- utils.py:842-868: 4*C of the F features of a row are copies of other
+   houses' messages) and the context's threads expand the rows into `host_obs`.  The host buffers are bit-identical to
+   the ctx == NULL path; `out->obs` (device) is NOT written on this path.  Other layouts fall back to the serial path. */
 int mdr_step_host(const MdrConfig *cfg, const MdrHouses *houses, const MdrEnvs *envs,
                   const MdrStepInputs *in, const MdrOutputs *out, const uint8_t *host_actions,
                   void *host_obs, void *host_reward, double *host_power, double *host_signal,
-                  void *stream);
+                  MdrHostCtx *ctx, void *stream);
 
 #ifdef __cplusplus
 }

@@ -76,7 +76,8 @@ class MdrOutputs(C.Structure):
 
 EXPORTS = ("mdr_version", "mdr_strerror", "mdr_last_cuda_error", "mdr_obs_width", "mdr_validate",
            "mdr_launch_geometry", "mdr_precompute", "mdr_reset", "mdr_observe", "mdr_step", "mdr_step_host",
-           "mdr_l2_persist_limit", "mdr_populate", "mdr_workspace_bytes", "mdr_sample_actions")
+           "mdr_l2_persist_limit", "mdr_populate", "mdr_workspace_bytes", "mdr_sample_actions",
+           "mdr_host_ctx_create", "mdr_host_ctx_destroy", "mdr_host_ctx_info")
 
 _lib = None
 
@@ -126,7 +127,10 @@ def load(build_if_missing: bool = True):
     lib.mdr_reset.argtypes = step_args + [_vp]
     lib.mdr_observe.argtypes = step_args + [_vp]
     lib.mdr_step.argtypes = step_args + [_i32, _vp]
-    lib.mdr_step_host.argtypes = step_args + [_vp, _vp, _vp, _vp, _vp, _vp]
+    lib.mdr_step_host.argtypes = step_args + [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.mdr_host_ctx_create.argtypes = [P(MdrConfig), _i32, _i32, P(_vp)]
+    lib.mdr_host_ctx_destroy.argtypes = [_vp]
+    lib.mdr_host_ctx_info.argtypes = [_vp, P(_i32), P(_i32), P(C.c_size_t)]
     lib.mdr_l2_persist_limit.argtypes = [C.c_int, C.c_size_t, P(C.c_size_t), P(C.c_size_t)]
     lib.mdr_populate.argtypes = [P(MdrConfig), P(MdrPopulationSpec), P(MdrHouses), P(MdrEnvs), _vp, C.c_uint64, _vp]
     if lib.mdr_version() != MDR_ABI_VERSION:

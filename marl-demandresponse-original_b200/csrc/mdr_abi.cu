@@ -104,6 +104,21 @@ extern "C" int mdr_workspace_bytes(const MdrConfig* cfg, size_t* bytes) {
 static bool split_geometry(const MdrConfig* c, int* slice, int* k) {
   const int N = c->n_houses;
   const int need = c->base_power_mode == MDR_BASE_INTERPOLATION ? (N < c->interp_nb_agents ? N : c->interp_nb_agents) : 1;
+  // A handful of envs (config 1: ONE cluster of 1000 houses) is latency-bound: the shorter the slice a CTA owns, the
+  // shorter its row assembly -- up to 8 CTAs of >= 96 houses (>= the sampled houses of a refresh).
+  if (c->n_envs * 8 <= 148) {
+    const int floor_s = need > 96 ? need : 96;
+    int kk = N / floor_s;
+    if (kk > 8) kk = 8;
+    if (kk >= 2) {
+      int S = ((N + kk - 1) / kk + 3) & ~3;
+      if (S <= 992 && N - (kk - 1) * S >= 1 && S >= need) {
+        *slice = S;
+        *k = kk;
+        return true;
+      }
+    }
+  }
   const int caps[4] = {224, 480, 992, 1024};
   for (int max_k = 8; max_k <= 16; max_k += 8)
     for (int i = 0; i < 4; ++i) {
@@ -388,12 +403,14 @@ extern "C" int mdr_precompute(const MdrConfig* cfg, const MdrHouses* houses, voi
 }
 
 static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs, const MdrStepInputs* in,
-                     const MdrOutputs* out, int n_steps, int is_reset, cudaStream_t stream) {
+                     const MdrOutputs* out, int n_steps, int is_reset, cudaStream_t stream, int env_base = 0) {
   int st = mdr_validate(cfg);
   if (st != MDR_OK) return st;
   if (n_steps < 1) return MDR_ERR_SHAPE;
   KernelParams k;
   fill_config(k, cfg);
+  k.env_base = env_base;
+  k.house_base = (unsigned)env_base * (unsigned)cfg->n_houses;
   st = fill_houses(k, cfg, houses, true);
   if (st != MDR_OK) return st;
   st = fill_step(k, cfg, envs, in, out, is_reset);
@@ -496,15 +513,39 @@ extern "C" int mdr_step(const MdrConfig* cfg, const MdrHouses* houses, const Mdr
   return run_steps(cfg, houses, envs, in, out, n_steps, 0, static_cast<cudaStream_t>(stream));
 }
 
+namespace mdr {
+// entry points of the host-buffer pipeline (mdr_host.cu): one step / the compact observation record of a slice of the
+// env axis (`env_base` keeps the Philox keys those of the whole shard)
+int run_steps_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, const MdrStepInputs* in, const MdrOutputs* out,
+                    int env_base, cudaStream_t stream) {
+  return run_steps(cfg, h, e, in, out, 1, 0, stream, env_base);
+}
+int compact_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, void* out, cudaStream_t stream) {
+  KernelParams k;
+  fill_config(k, cfg);
+  k.temps = h->temps; k.hvac = h->hvac; k.coef_b = h->coef_b; k.coef_c = h->coef_c;
+  k.signal = e->signal; k.cluster_power = e->cluster_power;
+  cudaError_t err = launch_compact_obs(k, cfg->precision, out, stream);
+  return err == cudaSuccess ? MDR_OK : cuda_fail(err);
+}
+}  // namespace mdr
+
 extern "C" int mdr_step_host(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs,
                              const MdrStepInputs* in, const MdrOutputs* out, const uint8_t* host_actions,
                              void* host_obs, void* host_reward, double* host_power, double* host_signal,
-                             void* stream_v) {
-  if (!cfg || !in || !out || !envs) return MDR_ERR_NULL;
+                             MdrHostCtx* ctx, void* stream_v) {
+  if (!cfg || !in || !out || !envs || !houses) return MDR_ERR_NULL;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);
   const size_t houses_total = (size_t)cfg->n_envs * cfg->n_houses;
+  // pipelined path: slices of the env axis over two streams, compact observation records expanded on the host
+  if (ctx != nullptr && host_obs != nullptr && mdr::host_compact_eligible(cfg, in, out) && !needs_big_path(cfg)) {
+    int st = mdr_validate(cfg);
+    if (st != MDR_OK) return st;
+    return mdr::host_pipeline_step(ctx, cfg, houses, envs, in, out, host_actions, host_obs, host_reward, host_power,
+                                   host_signal, stream, cuda_fail);
+  }
   if (host_actions) {
     if (!in->actions) return MDR_ERR_NULL;
     err = cudaMemcpyAsync(const_cast<uint8_t*>(in->actions), host_actions, houses_total, cudaMemcpyHostToDevice, stream);

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kBigThreads) big_finish_kernel(const __grid_co
     return make4((tj.x - cj.w) * (R)0.2, (R)(hvj >> 2), ((hvj & 1) ? cj.z : (R)0) * inv_norm, cj.z * inv_norm);
   };
   HouseRow<R> hr;
-  hr.t_air = tt.x; hr.t_mass = tt.y; hr.target = target; hr.deadband = deadband; hr.p_on = cb.z; hr.inv_lock = (R)1 / cc.y;
+  hr.t_air = tt.x; hr.t_mass = tt.y; hr.target = target; hr.deadband = deadband; hr.p_on = cb.z; hr.inv_lock = inv_real(cc.y);
   hr.on = hv & 1; hr.lock = (hv >> 1) & 1; hr.sso = hv >> 2; hr.P = P; hr.h = (unsigned)h; hr.e = e; hr.li = li;
   generic_row<R>(p, reinterpret_cast<R*>(p.obs) + h * p.F, hr, s_es, p.state_flags, p.msg_flags, p.comm_mode,
                  p.msg_keep != nullptr, p.comm_defect_prob > 0.0, p.C, msg_at);

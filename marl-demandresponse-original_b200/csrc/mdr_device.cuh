@@ -17,6 +17,11 @@ __device__ __forceinline__ double2 make2(double a, double b) { return make_doubl
 __device__ __forceinline__ float4 make4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
 __device__ __forceinline__ double4 make4(double a, double b, double c, double d) { return make_double4(a, b, c, d); }
 
+// 1 / lockout_duration as every kernel (and the compact host transfer) computes it: the same bits everywhere, so the
+// observation a step kernel assembles and the one expanded on the host from the compact record are identical
+__device__ __forceinline__ float inv_real(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double inv_real(double x) { return 1.0 / x; }
+
 // Non-contracted arithmetic: the interpolation and the grid signal are evaluated in the
 // reference's operation order (scipy/_rgi.py:520-549, env/MA_DemandResponse.py:1295-1314) so
 // that fp64 results agree to the last bit with numpy given identical inputs.

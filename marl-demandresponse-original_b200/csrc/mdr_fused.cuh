@@ -47,7 +47,7 @@ __device__ __noinline__ StepRec env_record(const KernelParams& p, int e2, uint32
     for (int j = 0; j < nb; ++j) sig_noise += (double)perlin_octave(x, j, nb, p.perlin_octaves_step, pkey);
   }
   const double od_noise =
-      p.temp_std * normal_from(philox4x32((uint32_t)e2, (uint32_t)step_index, (uint32_t)(step_index >> 32), STREAM_OD, p.seed));
+      p.temp_std * normal_from(philox4x32((uint32_t)(e2 + p.env_base), (uint32_t)step_index, (uint32_t)(step_index >> 32), STREAM_OD, p.seed));
   // ClusterHouses.compute_OD_temp, :1070-1081
   const double time_day = cal.hour + cal.minute * (1.0 / 60.0);
   StepRec rec;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? (kInterp && 
         if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
         else {
           const uint64_t si = step_now(p) + (uint64_t)j;
-          cmd = philox4x32(h, (uint32_t)si, (uint32_t)(si >> 32), STREAM_ACT, p.seed).x & 1;
+          cmd = philox4x32(h + p.house_base, (uint32_t)si, (uint32_t)(si >> 32), STREAM_ACT, p.seed).x & 1;
         }
         // HVAC.step, :475-492
         if (!on) sso += dt;

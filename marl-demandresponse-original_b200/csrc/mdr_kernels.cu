@@ -289,7 +289,7 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
       if (d < n_perlin) {
         terms += (double)perlin_octave(x, d, nb, p.perlin_octaves_step, pkey);
       } else {
-        normal = normal_from(philox4x32((uint32_t)e2, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_OD,
+        normal = normal_from(philox4x32((uint32_t)(e2 + p.env_base), (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_OD,
                                         p.seed));
       }
     }
@@ -475,7 +475,7 @@ __device__ __forceinline__ R segmented_sum(R v, int key, int lane) {
 // Message drop of the production mode (np.random.rand() > comm_defect_prob, :992): one Philox block serves four
 // messages of a house; message k takes word k % 4 of block k / 4 as a 32-bit uniform.
 __device__ __forceinline__ uint4 drop_block(const KernelParams& p, unsigned h, int k4) {
-  return philox4x32(h, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_MSG + 16 * (uint32_t)k4, p.seed);
+  return philox4x32(h + p.house_base, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_MSG + 16 * (uint32_t)k4, p.seed);
 }
 __device__ __forceinline__ bool drop_keep(const KernelParams& p, const uint4& r, int k) {
   const uint32_t w = (k & 3) == 0 ? r.x : (k & 3) == 1 ? r.y : (k & 3) == 2 ? r.z : r.w;
@@ -584,6 +584,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  // Programmatic dependent launch: the next step's CTAs may be scheduled while this grid runs (launch latency is what
+  // bounds a 1 x 1000-house cluster); they block here until everything the previous grid wrote is visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // the fast instantiation is only launched for plain steps (never for reset / observe)
   const bool reset = kFast ? false : p.is_reset != 0;  // 1 = reset (grid step + obs), 2 = observe only
   const bool observe_only = kFast ? false : p.is_reset == 2;
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
       if (p.action_source == MDR_ACT_ARRAY) cmd = cmd != 0;
       else if (p.action_source == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
       else if (p.action_source == MDR_ACT_GREEDY) cmd = greedy_cmd;
-      else cmd = philox4x32(h, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_ACT, p.seed).x & 1;
+      else cmd = philox4x32(h + p.house_base, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
       const int lockdur = (int)lockdur_r;
@@ -812,7 +816,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
   R* stage = s_stage + warp * rpp * F;
   const int wrow0 = warp * 32;
   const int nrows_w = max(0, min(32, H - wrow0));
-  const R inv_lock = (R)1 / lockdur_r;
+  const R inv_lock = inv_real(lockdur_r);
   // fast-path row: [T_air, T_mass, target, deadband, cap, on, lockout, sso, 1, signal, power | C x 4 messages]
   auto fast_row = [&](R* row) {
     row[0] = (tt.x - 20) * (R)0.2;
@@ -896,7 +900,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
       if (N > nb) {
         if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
         else {
-          const uint4 r = philox4x32((uint32_t)e, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
+          const uint4 r = philox4x32((uint32_t)(e + p.env_base), (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
                                      STREAM_IDS + 16 * (uint32_t)li, p.seed);
           src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
         }
@@ -1071,6 +1075,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
 #include "mdr_populate.cuh"
 #include "mdr_big.cuh"
 #include "mdr_rollout.cuh"
+#include "mdr_compact.cuh"
 
 // ----------------------------------------------------------------------------------------
 // host-side launch helpers
@@ -1104,35 +1109,39 @@ static cudaError_t launch_step_t(const KernelParams& kp, const Geometry& g, cuda
   static std::atomic<uint64_t> latch{0};
   cudaError_t err = ensure_max_smem(step_kernel<R, kMaxThreads, kFast, kC>, latch);
   if (err != cudaSuccess) return err;
-  if (g.cluster > 1) {
-    // one env per thread-block cluster (clusters larger than 8 CTAs are "non-portable": opt in once per device)
-    if (g.cluster > 8) {
-      static std::atomic<uint64_t> np_latch{0};
-      int dev = 0;
-      cudaGetDevice(&dev);
-      const uint64_t bit = 1ull << (dev & 63);
-      if (!(np_latch.load(std::memory_order_acquire) & bit)) {
-        err = cudaFuncSetAttribute(step_kernel<R, kMaxThreads, kFast, kC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (err != cudaSuccess) return err;
-        np_latch.fetch_or(bit, std::memory_order_release);
-      }
+  if (g.cluster > 8) {  // clusters larger than 8 CTAs are "non-portable": opt in once per device
+    static std::atomic<uint64_t> np_latch{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(np_latch.load(std::memory_order_acquire) & bit)) {
+      err = cudaFuncSetAttribute(step_kernel<R, kMaxThreads, kFast, kC>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (err != cudaSuccess) return err;
+      np_latch.fetch_or(bit, std::memory_order_release);
     }
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = (unsigned)g.cluster;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3((unsigned)g.ctas);
-    lc.blockDim = dim3((unsigned)g.threads);
-    lc.dynamicSmemBytes = g.smem_bytes;
-    lc.stream = stream;
-    lc.attrs = &attr;
-    lc.numAttrs = 1;
-    return cudaLaunchKernelEx(&lc, step_kernel<R, kMaxThreads, kFast, kC>, kp);
   }
-  step_kernel<R, kMaxThreads, kFast, kC><<<g.ctas, g.threads, g.smem_bytes, stream>>>(kp);
-  return cudaGetLastError();
+  cudaLaunchAttribute attrs[2];
+  int n_attrs = 0;
+  if (g.cluster > 1) {  // one env per thread-block cluster
+    attrs[n_attrs].id = cudaLaunchAttributeClusterDimension;
+    attrs[n_attrs].val.clusterDim.x = (unsigned)g.cluster;
+    attrs[n_attrs].val.clusterDim.y = 1;
+    attrs[n_attrs].val.clusterDim.z = 1;
+    ++n_attrs;
+  }
+  if (!g.no_pdl) {
+    attrs[n_attrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[n_attrs].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attrs;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)g.ctas);
+  lc.blockDim = dim3((unsigned)g.threads);
+  lc.dynamicSmemBytes = g.smem_bytes;
+  lc.stream = stream;
+  lc.attrs = attrs;
+  lc.numAttrs = n_attrs;
+  return cudaLaunchKernelEx(&lc, step_kernel<R, kMaxThreads, kFast, kC>, kp);
 }
 
 template <typename R, bool kFast, int kC>

@@ -53,6 +53,8 @@ struct KernelParams {
   double* metrics;  // [E, MDR_N_METRICS] running accumulators (fused multi-step kernel), or nullptr
   void* workspace;  // mdr_workspace_bytes() of scratch (envs beyond a thread-block cluster), or nullptr
   uint64_t step_index, seed;
+  int env_base;          // index of this call's first env in the shard (host-buffer pipeline steps slices of the env axis)
+  unsigned house_base;   // env_base * N
   const uint64_t* step_counter;  // optional device-resident addend of step_index (CUDA-graph replay)
   // scalars
   double alpha_temp, alpha_sig, norm_temp_penalty, norm_sig_penalty, mix_alpha_ind, mix_alpha_common, mix_alpha_max;
@@ -91,10 +93,20 @@ cudaError_t launch_populate(const KernelParams& kp, const MdrPopulationSpec& spe
 bool fused_eligible(const KernelParams& kp);
 cudaError_t launch_big(const KernelParams& kp, int precision, void* workspace, cudaStream_t stream);
 size_t big_workspace(int n_envs, int n_houses);
+cudaError_t launch_compact_obs(const KernelParams& kp, int precision, void* out, cudaStream_t stream);
 cudaError_t launch_sample_actions(const float* probs, long long n_rows, int n_actions, uint64_t seed, uint64_t draw_index,
                                   const uint64_t* draw_counter, uint8_t* actions, float* chosen_prob, cudaStream_t stream);
 cudaError_t launch_fused(const KernelParams& kp, const Geometry& g, int precision, int n_steps, cudaStream_t stream);
 cudaError_t launch_precompute_any(const KernelParams& kp, int precision, cudaStream_t stream);
 cudaError_t launch_step_any(const KernelParams& kp, const Geometry& g, int precision, cudaStream_t stream);
+
+// host-buffer pipeline (mdr_host.cu <-> mdr_abi.cu)
+bool host_compact_eligible(const MdrConfig* c, const MdrStepInputs* in, const MdrOutputs* out);
+int host_pipeline_step(MdrHostCtx* ctx, const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, const MdrStepInputs* in,
+                       const MdrOutputs* out, const uint8_t* host_actions, void* host_obs, void* host_reward,
+                       double* host_power, double* host_signal, cudaStream_t user_stream, int (*fail)(cudaError_t));
+int run_steps_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, const MdrStepInputs* in, const MdrOutputs* out,
+                    int env_base, cudaStream_t stream);
+int compact_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, void* out, cudaStream_t stream);
 
 }  // namespace mdr

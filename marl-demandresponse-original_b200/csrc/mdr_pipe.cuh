@@ -93,10 +93,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
 // shared-memory control block of the pipelined kernel (at off_ctl).  The PipeEnv ring has
 // ring = 2 * pro_batch <= kMaxRing slots; slot = it % ring for the it-th tile of this CTA.
 constexpr int kMaxRing = 16;
+constexpr int kMaxDue = 60;
 struct PipeCtl {
   uint64_t full[kMaxRing];   // prologue -> house warps: slot is ready            (count 1)
   uint64_t empty[kMaxRing];  // house warps -> prologue: slot may be overwritten   (count house_warps)
   int tile_due[kMaxRing];    // any env of the tile has an interpolation refresh due
+  // tiles of this CTA with a refresh due in this launch: with staggered refresh clocks (rollouts restart clusters at
+  // different times) a few percent of the tiles are due at EVERY step, and the deferred pass must only visit those
+  int due_n;
+  int due_list[kMaxDue];
 };
 
 // The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
@@ -179,7 +184,13 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
   // the bulk stores of this warp's rows must have landed before feature 9 is patched
   if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __syncwarp();
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  house_sync(T);  // the due-tile list written by thread 0 during the tile loop
+  const int n_due = ctl.due_n;
+  const bool listed = n_due <= kMaxDue;  // (overflow: walk every tile of this CTA)
+  const int n_visit = listed ? n_due : (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  for (int v = 0; v < n_visit; ++v) {
+    const int tile = listed ? ctl.due_list[v] : (int)blockIdx.x + v * (int)gridDim.x;
     const int H = min(GN, (p.E - tile * G) * N);
     const bool active = tid < H;
     const int e = tile * G + le;
@@ -206,7 +217,7 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       if (N > nb) {
         if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
         else {
-          const uint4 r = philox4x32((uint32_t)e, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
+          const uint4 r = philox4x32((uint32_t)(e + p.env_base), (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
                                      STREAM_IDS + 16 * (uint32_t)li, p.seed);
           src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
         }
@@ -252,6 +263,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   const int ring_shift = 31 - __clz(ring_mask + 1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
   if (tid == 0) {
+    ctl.due_n = 0;
     for (int i = 0; i <= ring_mask; ++i) {
       mbar_init(&ctl.full[i], 1);
       mbar_init(&ctl.empty[i], p.house_warps);
@@ -368,11 +380,11 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       const float2 cc = *reinterpret_cast<const float2*>(in_t + so + T * 8);
       const int hv = *reinterpret_cast<const int*>(in_h + so);
       target = cb.w; p_on = cb.z; deadband = cc.x;
-      inv_lock = __fdividef(1.0f, cc.y);
+      inv_lock = inv_real(cc.y);
       on = hv & 1; sso = hv >> 2;
       if (kAct == MDR_ACT_ARRAY) cmd = cmd != 0;
       else if (kAct == MDR_ACT_BANGBANG) cmd = tt.x > target;  // agents/bangbang_controllers.py:50-61
-      else cmd = philox4x32(h, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_ACT, p.seed).x & 1;
+      else cmd = philox4x32(h + p.house_base, (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32), STREAM_ACT, p.seed).x & 1;
       // HVAC.step, :475-492
       const int dt = p.dt;
       const int lockdur = (int)cc.y;
@@ -486,7 +498,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       row[6] = (float)lock;
       row[7] = (float)sso * inv_lock;
       row[8] = 1.0f;
-      row[10] = P * p.f_inv_norm_sig_agents;
+      row[10] = (float)((double)P * p.inv_norm_sig_agents);  // same bits as the generic kernel and the compact record
       // neighbours (:816-828) = the C window entries around this house, skipping itself
       const float4* win = msg - half;
       float* mrow = row + 11;
@@ -511,7 +523,14 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       }
     }
     MDR_STAMP(6);
-    any_due |= ctl.tile_due[slot];
+    if (ctl.tile_due[slot]) {
+      any_due = 1;
+      if (tid == 0) {
+        const int k = ctl.due_n;
+        if (k < kMaxDue) ctl.due_list[k] = tile;
+        ctl.due_n = k + 1;
+      }
+    }
     if (active) {
       // reg_signal_penalty :244-247 with the OLD signal; weighting :364-372
       const float dn = (float)((double)P - env_buf[le].s_old) * p.f_inv_n;

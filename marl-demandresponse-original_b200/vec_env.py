@@ -410,11 +410,51 @@ class VecDemandResponseEnv:
             "rmse_signal_per_agent": torch.sqrt(col["sum_sq_signal_error"] / steps) / n,
         }
 
+    def host_pipeline(self, enable=True, n_threads=0, n_slices=0):
+        """Creates (or drops) the MdrHostCtx of the pipelined host-buffer path: env-axis slices over two streams and,
+        with the default observation layout, a compact 16-real record per house over PCIe expanded by `n_threads`
+        host threads (0 = this process's CPU affinity count, at most 24).  Pin the process to the GPU's NUMA node first."""
+        if getattr(self, "_host_ctx", None):
+            _lib.check(self.lib.mdr_host_ctx_destroy(self._host_ctx), "mdr_host_ctx_destroy")
+            self._host_ctx = None
+        if enable:
+            ctx = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.mdr_host_ctx_create(C.byref(self.cfg), int(n_threads), int(n_slices), C.byref(ctx)),
+                           "mdr_host_ctx_create")
+            self._host_ctx = ctx
+        return self
+
+    def host_pipeline_info(self):
+        if not getattr(self, "_host_ctx", None):
+            return None
+        t, s, b = C.c_int32(), C.c_int32(), C.c_size_t()
+        _lib.check(self.lib.mdr_host_ctx_info(self._host_ctx, C.byref(t), C.byref(s), C.byref(b)), "mdr_host_ctx_info")
+        return dict(threads=t.value, slices=s.value, compact_bytes=b.value)
+
+    def host_transfer_bytes(self):
+        """Device-to-host bytes of one step_host() call (observation + reward + per-env power and signal)."""
+        e, n = self.n_envs, self.n_houses
+        rb = 4 if self.dtype == torch.float32 else 8
+        f = self.flat
+        compact = bool(getattr(self, "_host_ctx", None)) and self.with_obs and f.comm_mode_name == "neighbours" \
+            and f.state_flags == 0 and f.msg_flags == 0 and f.comm_defect_prob == 0 and n <= _lib.MAX_HOUSES_PER_CLUSTER
+        per_house = (16 if compact else self.n_features) * rb if self.with_obs else 0
+        return e * n * (per_house + rb) + 16 * e
+
+    def __del__(self):
+        try:
+            if getattr(self, "_host_ctx", None):
+                self.lib.mdr_host_ctx_destroy(self._host_ctx)
+        except Exception:
+            pass
+
     def step_host(self, host_actions, *, od_noise=None, signal_noise=None, interp_ids=None, msg_keep=None, comm=None,
                   want_obs=True):
         """End-to-end step with HOST buffers (what the dict API and the e2e benchmark call):
         H2D of the uint8 actions, the fused step, D2H of obs / reward / power / signal into pinned
-        host memory, stream synchronised.  Returns numpy views of the pinned buffers."""
+        host memory, stream synchronised.  Returns numpy views of the pinned buffers.  With host_pipeline() enabled
+        the transfers are sliced and overlapped and the observation travels as compact records (mdr_step_host)."""
         if not self._precomputed:
             self.precompute()
         e, n = self.n_envs, self.n_houses
@@ -434,7 +474,8 @@ class VecDemandResponseEnv:
         try:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.mdr_step_host(*self._refs, p(pb["actions"]), None if skip_obs else p(pb["obs"]),
-                                                  p(pb["reward"]), p(pb["power"]), p(pb["signal"]), self._stream()),
+                                                  p(pb["reward"]), p(pb["power"]), p(pb["signal"]),
+                                                  getattr(self, "_host_ctx", None), self._stream()),
                            "mdr_step_host")
         finally:
             if skip_obs:
@@ -509,7 +550,8 @@ class VecDemandResponseEnv:
     def __deepcopy__(self, memo):
         new = object.__new__(type(self))
         memo[id(self)] = new
-        skip = {"lib", "cfg", "houses_s", "envs_s", "in_s", "out_s", "_refs", "_keep", "_pinned", "_arena", "_workspace", "coef_a",
+        skip = {"lib", "cfg", "houses_s", "envs_s", "in_s", "out_s", "_refs", "_keep", "_pinned", "_arena", "_workspace",
+                "_host_ctx", "coef_a",
                 "coef_b", "coef_c", "temps", "hvac", "actions"}
         for k, v in self.__dict__.items():
             if k in skip:

@@ -108,7 +108,7 @@ def test_split_equals_single_cta_bitwise():
     a = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp64", interp_table=table, seed=3)
     b = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp64", interp_table=table, seed=3)
     b.set_launch_options(no_cluster=True)
-    assert a.launch_geometry()["cluster_size"] == 4 and b.launch_geometry()["cluster_size"] == 1
+    assert a.launch_geometry()["cluster_size"] >= 2 and b.launch_geometry()["cluster_size"] == 1
     a.reset_tensor()
     b.reset_tensor()
     g = torch.Generator(device="cuda").manual_seed(4)

@@ -192,6 +192,35 @@ def test_host_buffer_entry_point_matches_tensor_path():
         assert np.array_equal(p.cpu().numpy(), h_p) and np.array_equal(s.cpu().numpy(), h_s)
 
 
+@pytest.mark.parametrize("n_envs,n,interp,precision,threads", [
+    (700, 50, False, "fp32", 4), (333, 100, True, "fp32", 3), (40, 300, True, "fp64", 2), (5, 1000, True, "fp32", 1),
+    (100, 12, False, "fp64", 5)])
+def test_pipelined_host_path_is_bit_identical(n_envs, n, interp, precision, threads):
+    """mdr_step_host with an MdrHostCtx (env-axis slices over two streams, compact 16-real records over PCIe, rows
+    expanded by host threads) returns exactly the bytes of the serial path and of the device tensors (utils.py:842-868)."""
+    import mdr_b200
+    cfg, flat, pop, d = _random_case(n_envs, n, 50 + n, interp, False, 6, signal="perlin")
+    table = gu.synthetic_table() if interp else None
+    mk = lambda: mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, interp_table=table, seed=11)
+    a, b, c = mk(), mk(), mk()
+    c.host_pipeline(True, n_threads=threads, n_slices=5)
+    assert c.host_pipeline_info()["threads"] == threads
+    for x in (a, b, c):
+        x.reset_tensor()
+        if interp:
+            x.stagger_interp_clock(seed=4)
+    assert c.host_transfer_bytes() < b.host_transfer_bytes()
+    for t in range(6):
+        obs, rew, p, s = a.step_tensor(d["actions"][t])            # device Philox noise: keys must not depend on slicing
+        s_obs, s_rew, s_p, s_s = [x.copy() for x in b.step_host(d["actions"][t])]
+        h_obs, h_rew, h_p, h_s = c.step_host(d["actions"][t])
+        assert np.array_equal(obs.cpu().numpy(), s_obs) and np.array_equal(rew.cpu().numpy(), s_rew)
+        assert np.array_equal(h_obs, s_obs), t
+        assert np.array_equal(h_rew, s_rew) and np.array_equal(h_p, s_p) and np.array_equal(h_s, s_s), t
+        assert np.array_equal(c.hvac.cpu().numpy(), a.hvac.cpu().numpy()) and np.array_equal(c.temps.cpu().numpy(), a.temps.cpu().numpy())
+    c.host_pipeline(False)
+
+
 def test_checkpoint_and_deepcopy():
     import mdr_b200
     cfg, flat, pop, d = _random_case(3, 40, 21, False, False, 8)
@@ -306,7 +335,7 @@ def test_device_metrics_match_reference_accumulators(name, precision):
     plain = env.launch_geometry()["kernel"]
     env.enable_metrics()
     assert env.launch_geometry()["kernel"] == plain   # metrics do not change which kernel runs
-    env.observe_tensor(msg_keep=g.init_keep[None])
+    env.precompute()
     for t in range(g.steps):
         ids = g.interp_ids[t][None] if g.interp_ids[t][0] >= 0 else None
         comm = None if g.comm_t is None else g.comm_t[t][None]
