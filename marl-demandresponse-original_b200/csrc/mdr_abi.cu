@@ -134,6 +134,13 @@ static bool split_geometry(const MdrConfig* c, int* slice, int* k) {
   return false;
 }
 
+// what the config alone says about the pipelined kernels' layout conditions (replayed message drops are a run-time
+// input: they send a split env to the generic cluster kernel)
+static bool pipe_layout_config(const MdrConfig* c) {
+  return c->precision == MDR_F32 && c->comm_mode == MDR_COMM_NEIGHBOURS && c->state_flags == 0 && c->msg_flags == 0 &&
+         c->temp_penalty_mode == MDR_PEN_INDIVIDUAL_L2 && c->action_source != MDR_ACT_GREEDY && !(c->flags & MDR_FLAG_NO_PIPELINE);
+}
+
 static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool need_met = false, bool allow_split = false) {
   const int N = c->n_houses, E = c->n_envs, F = c->n_features, rb = c->precision;
   static const int target_threads = [] {  // tuning knob (house threads per CTA), read once
@@ -145,7 +152,10 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
   // kernel is latency-bound (~7 us), so with many envs more, smaller CTAs only add waves (measured: 1000 x 1000 houses
   // 47 us as 1000 CTAs of 1024 threads, 87 us as 5000 CTAs of 256) -- and it is mandatory above 1024 houses.
   int slice = 0, ncl = 1;
-  const bool want_split = N > MDR_MAX_HOUSES_PER_ENV || (N > 224 && E < 148);
+  // ... unless the persistent pipelined split kernel takes the env (fp32, default layout, <= 8 x 224 houses, no drops): its
+  // CTAs loop over tiles with everything prefetched, so more, smaller tiles cost nothing.
+  const bool pipe_split_cfg = pipe_layout_config(c) && !(c->comm_defect_prob > 0.0) && N > 224 && N <= 8 * 224;
+  const bool want_split = N > MDR_MAX_HOUSES_PER_ENV || (N > 224 && E < 148) || pipe_split_cfg;
   const bool split = allow_split && want_split && !(c->flags & MDR_FLAG_NO_CLUSTER && N <= MDR_MAX_HOUSES_PER_ENV) &&
                      c->action_source != MDR_ACT_GREEDY && split_geometry(c, &slice, &ncl);
   if (!split && N > MDR_MAX_HOUSES_PER_ENV) return MDR_ERR_UNSUPPORTED;
@@ -208,6 +218,12 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
     const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride, g->pro_batch);
     if (ps <= (size_t)MDR_MAX_SMEM_BYTES) g->pipe_smem_bytes = ps;
   }
+  if (rb == MDR_F32 && extra && threads <= 256 && split && ncl <= 8) {
+    g->pro_batch = mdr::pipe_pro_batch(1, has_obs);
+    const size_t ps = mdr::pipe_split_smem_layout(nullptr, house_threads, slice, F, need_val, has_obs, c->n_comm, ncl, house_warps,
+                                                  g->pro_batch);
+    if (ps <= (size_t)MDR_MAX_SMEM_BYTES) g->pipe_smem_bytes = ps;
+  }
   return MDR_OK;
 }
 
@@ -234,7 +250,8 @@ extern "C" int mdr_launch_geometry(const MdrConfig* cfg, int has_obs, int32_t* e
   if (ctas) *ctas = g.ctas;
   KernelParams k;
   fill_config(k, cfg);
-  const bool pipe = !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::pipe_eligible(k, g, cfg->precision);
+  const bool pipe = !(cfg->flags & MDR_FLAG_NO_PIPELINE) &&
+                    (mdr::pipe_eligible(k, g, cfg->precision) || (k.comm_defect_prob <= 0.0 && mdr::pipe_split_eligible(k, g, cfg->precision)));
   if (smem_bytes) *smem_bytes = pipe ? g.pipe_smem_bytes : g.smem_bytes;
   if (pipelined) *pipelined = pipe ? 1 : 0;
   return MDR_OK;
@@ -465,6 +482,13 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
                         k.metrics != nullptr, g.part_slots);
   cudaError_t err = cudaSetDevice(cfg->device);
   if (err != cudaSuccess) return cuda_fail(err);
+  const bool pipe_split = !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::pipe_split_eligible(k, g, cfg->precision);
+  if (pipe_split) {
+    k.pro_batch = g.pro_batch;
+    k.in_stride = k.hmax * 52;
+    mdr::pipe_split_smem_layout(&k, k.hmax, g.cluster_slice, cfg->n_features, cfg->base_power_mode == MDR_BASE_INTERPOLATION,
+                                out->obs != nullptr, cfg->n_comm, g.cluster, g.house_warps, g.pro_batch);
+  }
   const bool pipe = !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::pipe_eligible(k, g, cfg->precision);
   if (pipe) {
     k.pro_batch = g.pro_batch;
@@ -481,7 +505,9 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     return err == cudaSuccess ? MDR_OK : cuda_fail(err);
   }
   for (int i = 0; i < n_steps; ++i) {
-    err = pipe ? mdr::launch_pipe(k, g, stream) : mdr::launch_step_any(k, g, cfg->precision, stream);
+    err = pipe_split ? mdr::launch_pipe_split(k, g, stream)
+          : pipe     ? mdr::launch_pipe(k, g, stream)
+                     : mdr::launch_step_any(k, g, cfg->precision, stream);
     if (err != cudaSuccess) return cuda_fail(err);
     k.step_index += 1;
   }

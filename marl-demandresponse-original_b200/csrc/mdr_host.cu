@@ -18,6 +18,7 @@
 #include <thread>
 #include <vector>
 
+#include "mdr_expand.h"
 #include "mdr_kernels.h"
 
 namespace {
@@ -84,45 +85,6 @@ struct MdrHostCtx {
 };
 
 namespace mdr {
-
-// expands the compact records of envs [e0, e1) into rows of F = 11 + 4*C reals (utils.normStateDict order; neighbours
-// :816-828 = the C houses around house i, skipping itself, wrapping around the env)
-template <typename R>
-static void expand_envs(const R* compact, R* obs, int e0, int e1, int N, int C, std::vector<R>& block) {
-  const int F = 11 + 4 * C, half = C >> 1;
-  block.resize((size_t)N * F);
-  for (int e = e0; e < e1; ++e) {
-    const R* c = compact + (size_t)e * N * 16;
-    R* b = block.data();
-    for (int i = 0; i < N; ++i, b += F) {
-      const R* own = c + (size_t)i * 16;
-      for (int k = 0; k < 11; ++k) b[k] = own[k];
-      const R inv_lock = own[15];
-      R* m = b + 11;
-      for (int k = 0; k < C; ++k, m += 4) {
-        int j = i - half + k + (k >= half ? 1 : 0);
-        if (j < 0) j += N;
-        if (j >= N) j -= N;
-        const R* s = c + (size_t)j * 16 + 11;
-        m[0] = s[0];
-        m[1] = s[1] * inv_lock;
-        m[2] = s[2];
-        m[3] = s[3];
-      }
-    }
-    R* dst = obs + (size_t)e * N * F;
-    const size_t bytes = (size_t)N * F * sizeof(R);
-    if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15) == 0) {
-      // the caller's buffer is written once and not read here: stream it past the caches (no read-for-ownership)
-      const __m128i* src = reinterpret_cast<const __m128i*>(block.data());
-      __m128i* d = reinterpret_cast<__m128i*>(dst);
-      for (size_t q = 0; q < bytes / 16; ++q) _mm_stream_si128(d + q, _mm_loadu_si128(src + q));
-    } else {
-      memcpy(dst, block.data(), bytes);
-    }
-  }
-  _mm_sfence();
-}
 
 static inline const void* off(const void* p, size_t bytes) { return p ? static_cast<const char*>(p) + bytes : nullptr; }
 static inline void* off(void* p, size_t bytes) { return p ? static_cast<char*>(p) + bytes : nullptr; }

@@ -65,8 +65,8 @@ struct PipeEnv {
   int time_sec;
   double sig_new;    // grid signal after this step (metric accumulators; not final when `due`)
   float gain;        // solar gain of this step (0 with solar gain off), utils.py:1277-1350
-  int pad0;
-  double pad1;
+  uint32_t t_new;    // clock after this step (naive epoch seconds)
+  double base;       // base power the signal was evaluated with (not final when `due`)
 };
 static_assert(sizeof(PipeEnv) == 64, "PipeEnv must stay 64 bytes");
 
@@ -131,9 +131,20 @@ __device__ __noinline__ double interp_eval(const KernelParams& p, int key, doubl
   const R* __restrict__ table = reinterpret_cast<const R*>(p.interp_table);
   const int n4 = p.interp_dims[4], n5 = p.interp_dims[5], n6 = p.interp_dims[6], n7 = p.interp_dims[7],
             n8 = p.interp_dims[8], n9 = p.interp_dims[9];
-  double value = 0.0;
-#pragma unroll 1
+  // All 32 corner values are fetched first (independent loads in flight together: the table lives in L2 and a corner
+  // after corner walk pays the L2 latency 32 times -- measured 11 us per refresh), then accumulated in scipy's order.
+  const size_t s9 = 1, s8 = (size_t)n9, s7 = s8 * n8, s6 = s7 * n7, s5 = s6 * n6, s4 = s5 * n5;
+  const size_t base_off = (((((size_t)therm * n4 + idx[0]) * n5 + idx[1]) * n6 + idx[2]) * n7 + ih) * s7 + (size_t)idx[3] * s8 +
+                          (size_t)idx[4] * s9;
+  R corner[32];
+#pragma unroll
   for (int c = 0; c < 32; ++c) {  // itertools.product order: first dimension slowest
+    const size_t off = base_off + ((c >> 4) & 1) * s4 + ((c >> 3) & 1) * s5 + ((c >> 2) & 1) * s6 + ((c >> 1) & 1) * s8 + (c & 1) * s9;
+    corner[c] = __ldg(table + off);
+  }
+  double value = 0.0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
     const int b0 = (c >> 4) & 1, b1 = (c >> 3) & 1, b2 = (c >> 2) & 1, b3 = (c >> 1) & 1, b4 = c & 1;
     double weight = 1.0;
     weight = mul_rn(weight, b0 ? w[0] : 1.0 - w[0]);
@@ -141,14 +152,7 @@ __device__ __noinline__ double interp_eval(const KernelParams& p, int key, doubl
     weight = mul_rn(weight, b2 ? w[2] : 1.0 - w[2]);
     weight = mul_rn(weight, b3 ? w[3] : 1.0 - w[3]);
     weight = mul_rn(weight, b4 ? w[4] : 1.0 - w[4]);
-    size_t off = (size_t)therm;
-    off = off * n4 + (idx[0] + b0);
-    off = off * n5 + (idx[1] + b1);
-    off = off * n6 + (idx[2] + b2);
-    off = off * n7 + ih;
-    off = off * n8 + (idx[3] + b3);
-    off = off * n9 + (idx[4] + b4);
-    value = add_rn(value, mul_rn((double)__ldg(table + off), weight));
+    value = add_rn(value, mul_rn((double)corner[c], weight));
   }
   return value;
 }
@@ -336,19 +340,26 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
       pe.time_sec = time_sec;
       pe.sig_new = sig;
       pe.gain = (float)gain;
-      if (p.solar) p.solar_gain[e2] = gain;
-      p.t_epoch[e2] = (int64_t)t;
-      p.od_temp[e2] = od_new;  // the house threads take the OLD value from the record
-      if (!due) {
-        p.base_power[e2] = base;
-        p.signal[e2] = sig;
-        if (interp_mode) p.time_since_interp[e2] = tsi;
-      } else {
-        // deferred refresh (pipe_refresh_pass, after the tile loop of the same launch): the env is
-        // marked with time_since_interp = -1 and its perlin value parked in base_power, both of
-        // which the refresh overwrites
-        p.time_since_interp[e2] = -1;
-        p.base_power[e2] = sig_noise;
+      pe.t_new = t;
+      pe.base = base;
+      // An env split over a cluster (mdr_pipe_split.cuh) is evaluated by the prologue warp of EVERY CTA of the cluster,
+      // each for itself: nobody may overwrite the per-env state while a peer can still read it.  There the house
+      // thread of rank 0 writes these outputs from the record, after the cluster's rendezvous of the tile.
+      if (p.cl <= 1) {
+        if (p.solar) p.solar_gain[e2] = gain;
+        p.t_epoch[e2] = (int64_t)t;
+        p.od_temp[e2] = od_new;  // the house threads take the OLD value from the record
+        if (!due) {
+          p.base_power[e2] = base;
+          p.signal[e2] = sig;
+          if (interp_mode) p.time_since_interp[e2] = tsi;
+        } else {
+          // deferred refresh (pipe_refresh_pass, after the tile loop of the same launch): the env is
+          // marked with time_since_interp = -1 and its perlin value parked in base_power, both of
+          // which the refresh overwrites
+          p.time_since_interp[e2] = -1;
+          p.base_power[e2] = sig_noise;
+        }
       }
     }
     return valid ? due : 0;
@@ -1071,6 +1082,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMaxThreads <= 256 ? MDR_BLOCKS_2
 }
 
 #include "mdr_pipe.cuh"
+#include "mdr_pipe_split.cuh"
 #include "mdr_fused.cuh"
 #include "mdr_populate.cuh"
 #include "mdr_big.cuh"
@@ -1244,6 +1256,8 @@ cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t 
   if (kp.obs != nullptr) return kp.C == 10 ? launch_pipe_v<10, true>(kp, g, stream) : launch_pipe_v<0, true>(kp, g, stream);
   return kp.C == 10 ? launch_pipe_v<10, false>(kp, g, stream) : launch_pipe_v<0, false>(kp, g, stream);
 }
+
+#include "mdr_pipe_split_host.cuh"
 
 // tiles per prologue pass (power of two): as deep as the lanes (one per env at least), the ring
 // (kMaxRing slots) and the shared-memory budget (the observation staging tile is the big consumer)

@@ -87,6 +87,10 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
 int pipe_pro_batch(int envs_per_cta, bool has_obs);
 bool pipe_eligible(const KernelParams& kp, const Geometry& g, int precision);
 cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t stream);
+cudaError_t launch_pipe_split(const KernelParams& kp, const Geometry& g, cudaStream_t stream);
+bool pipe_split_eligible(const KernelParams& kp, const Geometry& g, int precision);
+size_t pipe_split_smem_layout(KernelParams* kp, int hmax, int slice, int n_features, bool need_val, bool has_obs, int n_comm,
+                              int cluster, int house_warps, int pro_batch);
 cudaError_t launch_populate(const KernelParams& kp, const MdrPopulationSpec& spec, const uint8_t* env_mask, double* ua, double* cm,
                             double* ca, double* hm, double* cap, double* target, double* deadband, int32_t* lockout_dur,
                             int precision, uint64_t draw_index, cudaStream_t stream);

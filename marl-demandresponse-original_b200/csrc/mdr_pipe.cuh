@@ -139,8 +139,9 @@ __device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B
   }
   MDR_STAMP_AT(7, it0, 0);
   const int tile_c = tile_valid ? tile : blockIdx.x;  // lanes of an absent tile compute but never write
-  const int env0 = tile_c * p.G;
-  const int genvs = min(p.G, p.E - env0);
+  // (split env, mdr_pipe_split.cuh: the tile is the slice of rank tile % cl of env tile / cl)
+  const int env0 = p.cl > 1 ? tile_c / p.cl : tile_c * p.G;
+  const int genvs = p.cl > 1 ? 1 : min(p.G, p.E - env0);
   PipeEnv* buf = s_env + slot * p.G;
   EnvScratch unused;
   int my_due = 0;

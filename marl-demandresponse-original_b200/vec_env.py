@@ -342,7 +342,7 @@ class VecDemandResponseEnv:
         if obs_out is not None or reward_out is not None:
             # zero-copy: the kernel writes straight into the caller's rollout storage
             obs = self._check_out(obs_out, (self.n_envs, self.n_houses, self.n_features)) if obs_out is not None else obs
-            reward = self._check_out(reward_out, (self.n_envs, self.n_houses)) if reward_out is not None else reward
+            reward = self._check_out(reward_out, (self.n_envs, self.n_houses), align=1) if reward_out is not None else reward
             self.out_s.obs = C.c_void_p(obs.data_ptr()) if obs is not None else None
             self.out_s.reward = C.c_void_p(reward.data_ptr())
         try:
@@ -355,9 +355,10 @@ class VecDemandResponseEnv:
         self.step_index += int(n_steps)
         return obs, reward, self.env["cluster_power"], self.env["signal"]
 
-    def _check_out(self, t, shape):
+    def _check_out(self, t, shape, align=16):
+        # (the observation is written with 16-byte bulk stores; rewards with element stores)
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device and t.dtype == self.dtype
-                and t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.data_ptr() % 16 == 0):
+                and t.is_contiguous() and tuple(t.shape) == tuple(shape) and t.data_ptr() % align == 0):
             raise ValueError("output tensor must be a contiguous, 16-byte aligned %s CUDA tensor of shape %s on %s"
                              % (self.dtype, tuple(shape), self.device))
         return t
@@ -510,7 +511,8 @@ class VecDemandResponseEnv:
         _lib.check(self.lib.mdr_launch_geometry(self._refs[0], int(self.with_obs), C.byref(g), C.byref(t), C.byref(c),
                                                 C.byref(s), C.byref(pl), C.byref(cl)), "mdr_launch_geometry")
         return dict(envs_per_cta=g.value, threads=t.value, tiles=c.value, smem_bytes=s.value, cluster_size=cl.value,
-                    kernel="mdr::step_pipe_kernel (persistent, software-pipelined)" if pl.value else
+                    kernel=("mdr::step_pipe_split_kernel (persistent, software-pipelined, env split over a cluster)"
+                            if pl.value and cl.value > 1 else "mdr::step_pipe_kernel (persistent, software-pipelined)") if pl.value else
                     ("mdr::big_update/env/finish_kernel (three launches)" if cl.value == 0 else "mdr::step_kernel"))
 
     # ------------------------------------------------------------------ checkpoint / copy

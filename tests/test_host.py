@@ -84,18 +84,18 @@ def test_launch_geometry():
                                            ctypes.byref(sm), ctypes.byref(pl), ctypes.byref(cl)) == 0
             # persistent pipelined kernel: fp32, whole envs of <= 224 houses per tile -- with solar gain on (the shipped
             # default) or off, it is a run-time variant of the same kernel
-            assert pl.value == (1 if (prec == _lib.F32 and n <= 100) else 0)
+            assert pl.value == (1 if prec == _lib.F32 else 0)   # N = 1000 / 1024: the split (cluster) instantiation
             cfg2 = __import__('copy').deepcopy(cfg)
             cfg2['default_house_prop']['solar_gain_bool'] = False
             s2 = mdr_b200.FlatConfig(cfg2).to_struct(e, prec, 0)
             assert lib.mdr_launch_geometry(ctypes.byref(s2), 1, None, None, None, None, ctypes.byref(pl), None) == 0
-            assert pl.value == (1 if (prec == _lib.F32 and n <= 100) else 0)
+            assert pl.value == (1 if prec == _lib.F32 else 0)
             assert t.value <= 1024 and t.value % 32 == 0
             if n <= 224:
                 assert cl.value == 1 and g.value * n <= t.value and c.value == -(-e // g.value)
-            else:  # one env split over a thread-block cluster: 1000 -> 5 CTAs x 200 houses, 1024 -> 5 x 208
+            else:  # one env split over a thread-block cluster (e.g. 1000 houses -> 8 CTAs x 128 or 5 x 200)
                 assert g.value == 1 and 2 <= cl.value <= 8 and c.value == e * cl.value
-                assert (cl.value - 1) * (t.value - 32) < n <= cl.value * (t.value - 32)
+                assert n <= cl.value * (t.value - 32)
             assert sm.value <= 227 * 1024
             out[(n, prec)] = (g.value, t.value, c.value, sm.value)
     assert out[(50, 4)][0] == 4 and out[(100, 4)][0] == 2  # CTA start rows 16-byte aligned for the bulk store

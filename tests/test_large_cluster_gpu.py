@@ -37,6 +37,9 @@ def _case(n_envs, n, seed, interp=False, penalty="individual_L2", signal="perlin
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("n_envs,n,kw", [
     (2, 225, dict()),                                                     # smallest split: 2 CTAs
+    (301, 300, dict(interp=True)),                                        # many envs: persistent split kernel, 2 CTAs per env, sampled refresh
+    (160, 1000, dict(solar=True, signal="sinusoidals")),                  # c3big's tile shape (5 x 200), solar gain on
+    (9, 1790, dict(interp=True)),                                         # largest env of the split pipelined kernel (8 x 224)
     (3, 1000, dict(interp=True)),                                         # config 1's shape: 5 CTAs x 200, sampled interpolation
     (2, 1025, dict(penalty="common_L2", signal="sinusoidals")),          # just past the one-CTA limit
     (2, 4096, dict(interp=True, penalty="mixture", solar=True)),         # 9 CTAs x 456
@@ -57,8 +60,10 @@ def test_split_env_matches_oracle(n_envs, n, kw, precision):
         comm = mdr_b200.comm_table("random_fixed", n, flat.nb_agents_comm, sampler=lambda possible, k: rnd.sample(possible, k=k))
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, interp_table=table, comm_table=comm)
     geo = env.launch_geometry()
-    assert geo["cluster_size"] >= 2 and geo["kernel"] == "mdr::step_kernel", geo
-    with_metrics = "penalty" in kw or "comm" in kw   # metrics select the generic instantiation; default flags keep kFast
+    assert geo["cluster_size"] >= 2 and geo["kernel"].startswith("mdr::step_"), geo
+    if precision == "fp32" and not kw.get("penalty") and not kw.get("comm") and n <= 1792:
+        assert geo["kernel"].startswith("mdr::step_pipe_split_kernel"), geo
+    with_metrics = "penalty" in kw or "comm" in kw or n == 300   # (metrics are an epilogue variant of every kernel)
     if with_metrics:
         env.enable_metrics()
     oracle = orc.OracleEnv(cfg, {k: v for k, v in pop.items() if k != "perlin_seed"}, comm_table=comm,

@@ -68,6 +68,8 @@ def _compare(env, oracle, ids, out, o_out, t):
     (70, 160, True, "sinusoidals", 10, 3),    # one env per tile, sampled interpolation ids, 23+ tiles per CTA
     (301, 30, True, "regular_steps", 4, 2),   # generic message count (kC = 0), 7 envs per tile, 22 tiles per CTA
     (53, 224, False, "flat", 10, 2),          # largest cluster of the pipelined kernel, 26+ tiles per CTA
+    (45, 500, True, "perlin", 10, 6),         # split kernel: 3 CTAs per env, 2 clusters walk 22+ envs each, inline refreshes
+    (64, 1000, False, "sinusoidals", 10, 5),  # split kernel, c3big's tile shape (5 x 200): ONE cluster walks all 64 envs
 ])
 def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_ctas):
     import mdr_b200
@@ -82,7 +84,7 @@ def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
     env.set_launch_options(max_ctas=max_ctas)
     geo = env.launch_geometry()
-    assert geo["kernel"].startswith("mdr::step_pipe_kernel")
+    assert geo["kernel"].startswith("mdr::step_pipe_split_kernel" if n > 224 else "mdr::step_pipe_kernel")
     assert geo["tiles"] >= 20 * max_ctas, geo
     oracle = orc.OracleEnv(cfg, {k: v for k, v in pop.items() if k != "perlin_seed"},
                            interp=orc.PowerInterp(table, gu.INTERP_GRID, gu.INTERP_KEYS) if interp else None)
