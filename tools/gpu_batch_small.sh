@@ -17,3 +17,10 @@ for w in sys.argv[2:]:
         print("%s value %.4g us/step %.2f e2e %.4g frac %.3f d2h %s pipe %s" % (w, d["value"], d["ms_per_step"]*1e3, d["e2e"]["value"], r.get("frac"), d["e2e"].get("d2h_bytes_per_step"), d["e2e"].get("pipeline")))
     except Exception as ex: print(w,"ERR",ex, open("gpurun_out/bench_%s_%s.err"%(w,tag)).read()[-600:])
 PY
+# host expansion bandwidth of this box (compact observation records -> [E,N,51] rows)
+g++ -O3 -std=c++17 -pthread -o /tmp/expand_bw tools/microbench/expand_bw.cpp 2>/dev/null && {
+  nproc; lscpu | grep -E "Model name|Socket|NUMA node\(s\)|Thread" ;
+  for t in 1 4 8 16 32; do /tmp/expand_bw $t | tail -2 | head -1; done
+  for t in 8 16; do MDR_HOST_NT=0 /tmp/expand_bw $t | tail -2 | head -1; done
+} > gpurun_out/expand_bw_$tag.log 2>&1
+cat gpurun_out/expand_bw_$tag.log
