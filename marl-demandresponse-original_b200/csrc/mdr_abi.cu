@@ -119,6 +119,19 @@ static bool split_geometry(const MdrConfig* c, int* slice, int* k) {
       }
     }
   }
+  static const int forced_k = [] {  // experiments: MDR_SPLIT_K forces the cluster size of envs that fit (read once)
+    const char* s = getenv("MDR_SPLIT_K");
+    const int v = s ? atoi(s) : 0;
+    return v >= 2 && v <= 16 ? v : 0;
+  }();
+  if (forced_k) {
+    int S = ((N + forced_k - 1) / forced_k + 3) & ~3;
+    if (S <= 1024 && N - (forced_k - 1) * S >= 1 && S >= need) {
+      *slice = S;
+      *k = forced_k;
+      return true;
+    }
+  }
   const int caps[4] = {224, 480, 992, 1024};
   for (int max_k = 8; max_k <= 16; max_k += 8)
     for (int i = 0; i < 4; ++i) {

@@ -23,6 +23,7 @@
 #include "mdr_kernels.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <atomic>

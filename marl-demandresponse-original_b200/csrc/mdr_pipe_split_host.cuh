@@ -44,6 +44,13 @@ static cudaError_t launch_pipe_split_t(const KernelParams& kp_in, const Geometry
   if (g.max_ctas > 0 && clusters * g.cluster > g.max_ctas) clusters = g.max_ctas / g.cluster > 0 ? g.max_ctas / g.cluster : 1;
   if (clusters > kp.E) clusters = kp.E;
   lc.gridDim = dim3((unsigned)(clusters * g.cluster));
+  static const bool verbose = getenv("MDR_VERBOSE") != nullptr;
+  if (verbose) {
+    static int printed = 0;
+    if (printed++ < 4)
+      fprintf(stderr, "[mdr] step_pipe_split_kernel: cluster %d x %d threads, smem %zu B, co-resident clusters %d -> grid %d CTAs, %d tiles\n",
+              g.cluster, g.threads, g.pipe_smem_bytes, max_clusters, clusters * g.cluster, kp.n_tiles);
+  }
   if (!g.no_pdl) {
     attrs[n_attrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[n_attrs].val.programmaticStreamSerializationAllowed = 1;

@@ -60,7 +60,8 @@ def test_split_env_matches_oracle(n_envs, n, kw, precision):
         comm = mdr_b200.comm_table("random_fixed", n, flat.nb_agents_comm, sampler=lambda possible, k: rnd.sample(possible, k=k))
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, interp_table=table, comm_table=comm)
     geo = env.launch_geometry()
-    assert geo["cluster_size"] >= 2 and geo["kernel"].startswith("mdr::step_"), geo
+    # (fp64 with many envs of <= 1024 houses keeps one CTA per env: more, smaller CTAs of the non-persistent kernel only add waves)
+    assert (geo["cluster_size"] >= 2 or (precision == "fp64" and n <= 1024 and n_envs >= 148)) and geo["kernel"].startswith("mdr::step_"), geo
     if precision == "fp32" and not kw.get("penalty") and not kw.get("comm") and n <= 1792:
         assert geo["kernel"].startswith("mdr::step_pipe_split_kernel"), geo
     with_metrics = "penalty" in kw or "comm" in kw or n == 300   # (metrics are an epilogue variant of every kernel)
