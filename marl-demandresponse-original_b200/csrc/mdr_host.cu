@@ -54,12 +54,15 @@ struct Pool {
         }
       });
   }
-  void run(std::function<void(int)> j) {  // every worker runs j(index) once; returns when all are done
-    std::unique_lock<std::mutex> lk(mu);
+  void start(std::function<void(int)> j) {  // every worker runs j(index) once
+    std::lock_guard<std::mutex> lk(mu);
     job = std::move(j);
     pending = (int)threads.size();
     ++generation;
     cv.notify_all();
+  }
+  void finish() {  // returns when all workers are done with the job of the last start()
+    std::unique_lock<std::mutex> lk(mu);
     done_cv.wait(lk, [&] { return pending == 0; });
   }
   ~Pool() {
@@ -166,27 +169,45 @@ int host_pipeline_step(MdrHostCtx* ctx, const MdrConfig* cfg, const MdrHouses* h
     CK(cudaEventRecord(ctx->ev_end[k], ctx->streams[k]));
     CK(cudaStreamWaitEvent(user_stream, ctx->ev_end[k], 0));
   }
-  // expansion: every worker takes its share of every slice as soon as that slice has landed
+  // expansion: every worker takes its share of every slice as soon as that slice has landed.  ONE thread (the caller's)
+  // waits on the slice events and publishes the count of landed slices; the workers poll that counter.
   std::atomic<int> cuda_error{0};
+  std::atomic<int> landed{0};
   const int T = ctx->n_threads;
-  auto work = [&](int w) {
-    cudaSetDevice(cfg->device);
-    std::vector<float> bf;
-    std::vector<double> bd;
+  auto expand_share = [&](int w, int s) {
+    const int e0 = s * per, ne = (E - e0 < per ? E - e0 : per);
+    const int a = e0 + (int)((long long)ne * w / T), b = e0 + (int)((long long)ne * (w + 1) / T);
+    if (a >= b) return;
+    thread_local std::vector<float> bf;
+    thread_local std::vector<double> bd;
+    if (cfg->precision == MDR_F32) expand_envs<float>((const float*)ctx->h_compact, (float*)host_obs, a, b, N, C, bf);
+    else expand_envs<double>((const double*)ctx->h_compact, (double*)host_obs, a, b, N, C, bd);
+  };
+  auto wait_slices = [&]() {
     for (int s = 0; s < n_slices; ++s) {
-      const int e0 = s * per, ne = (E - e0 < per ? E - e0 : per);
       const cudaError_t err = cudaEventSynchronize(ctx->ev_slice[s]);
-      if (err != cudaSuccess) { cuda_error.store((int)err); return; }
-      const int a = e0 + (int)((long long)ne * w / T), b = e0 + (int)((long long)ne * (w + 1) / T);
-      if (a >= b) continue;
-      if (cfg->precision == MDR_F32)
-        expand_envs<float>((const float*)ctx->h_compact, (float*)host_obs, a, b, N, C, bf);
-      else
-        expand_envs<double>((const double*)ctx->h_compact, (double*)host_obs, a, b, N, C, bd);
+      if (err != cudaSuccess) { cuda_error.store((int)err); landed.store(n_slices + 1, std::memory_order_release); return; }
+      landed.store(s + 1, std::memory_order_release);
     }
   };
-  if (ctx->pool) ctx->pool->run(work);
-  else work(0);
+  if (ctx->pool) {
+    auto work = [&](int w) {
+      for (int s = 0; s < n_slices; ++s) {
+        while (landed.load(std::memory_order_acquire) <= s) _mm_pause();
+        if (cuda_error.load() != 0) return;
+        expand_share(w, s);
+      }
+    };
+    ctx->pool->start(work);
+    wait_slices();
+    ctx->pool->finish();
+  } else {
+    for (int s = 0; s < n_slices; ++s) {
+      const cudaError_t err = cudaEventSynchronize(ctx->ev_slice[s]);
+      if (err != cudaSuccess) return fail(err);
+      expand_share(0, s);
+    }
+  }
   if (cuda_error.load() != 0) return fail((cudaError_t)cuda_error.load());
   CK(cudaStreamSynchronize(user_stream));
 #undef CK

@@ -218,10 +218,13 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
     cp_async_commit();
     const int slot = it & ring_mask;
     const PipeEnv* const pe = s_env + slot;  // one env per tile
+    MDR_STAMP(0);
     mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);
     const float od_old = pe->od_old;
     const float gain = pe->gain;
+    MDR_STAMP(1);
     cp_async_wait<1>();
+    MDR_STAMP(2);
 
     // ---------------- phase A: per house ---------------------------------------------------
     float t_air = 0, t_mass = 0, target = 0, p_on = 0, deadband = 0, inv_lock = 1, pen = 0, pw = 0, terr = 0;
@@ -292,13 +295,16 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
         }
       }
     }
+    MDR_STAMP(3);
     // the staging rows of this warp may still be read by the previous tile's bulk store
     if (kObs && it > 0) {
       if (lane == 0) bulk_wait_read_all();
       __syncwarp();
     }
+    MDR_STAMP(4);
     // the tile's only rendezvous: every warp of every CTA of the env has delivered its messages and partials
     mbar_wait_cluster(&sctl.xbar[sbuf], (it >> 1) & 1);
+    MDR_STAMP(5);
 
     float P = 0;
     {
@@ -400,8 +406,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
         }
       }
     }
+    MDR_STAMP(6);
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctl.empty[slot]);
+    MDR_STAMP(7);
   }
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();

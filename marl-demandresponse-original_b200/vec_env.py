@@ -466,7 +466,11 @@ class VecDemandResponseEnv:
                                 reward=pin(e, n, dtype=self.dtype), power=pin(e, dtype=torch.float64),
                                 signal=pin(e, dtype=torch.float64))
         pb = self._pinned
-        pb["actions"].numpy()[...] = np.asarray(host_actions).reshape(e, n) != 0
+        ha = np.asarray(host_actions)
+        if ha.dtype == np.bool_:
+            ha = ha.view(np.uint8)
+        # (the kernels read "nonzero = ON": uint8 / bool actions are copied as they are, one pass over 1 byte per house)
+        np.copyto(pb["actions"].numpy(), ha.reshape(e, n) if ha.dtype == np.uint8 else (ha.reshape(e, n) != 0))
         self._set_inputs(None, od_noise, signal_noise, interp_ids, msg_keep, comm)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
         skip_obs = not want_obs and self.obs is not None
