@@ -346,7 +346,8 @@ def gpu_arm(args):
     host_actions = [r.cpu().numpy() for r in ring[:4]]
     if not args.serial_e2e:
         ncpu = len(os.sched_getaffinity(0))
-        env.host_pipeline(True, n_threads=max(1, min(24, ncpu if not distributed else ncpu // max(1, world // 2))))
+        # single rank: every core of the affinity mask but one (auto); several ranks: an equal share of the cores
+        env.host_pipeline(True, n_threads=0 if not distributed else max(1, min(24, (os.cpu_count() or ncpu) // world - 1)))
     for i in range(2):
         env.step_host(host_actions[i & 3])
     if distributed:

@@ -174,14 +174,22 @@ int host_pipeline_step(MdrHostCtx* ctx, const MdrConfig* cfg, const MdrHouses* h
   std::atomic<int> cuda_error{0};
   std::atomic<int> landed{0};
   const int T = ctx->n_threads;
-  auto expand_share = [&](int w, int s) {
+  // chunks of a slice are claimed dynamically (a worker that lost its core for a moment does not hold up the slice)
+  std::atomic<int> next_chunk[kMaxSlices];
+  for (int s = 0; s < kMaxSlices; ++s) next_chunk[s].store(0, std::memory_order_relaxed);
+  int chunk = (int)(262144 / ((size_t)N * (11 + 4 * C) * rb));  // ~256 KB of rows per claim
+  if (chunk < 1) chunk = 1;
+  auto expand_share = [&](int /*w*/, int s) {
     const int e0 = s * per, ne = (E - e0 < per ? E - e0 : per);
-    const int a = e0 + (int)((long long)ne * w / T), b = e0 + (int)((long long)ne * (w + 1) / T);
-    if (a >= b) return;
     thread_local std::vector<float> bf;
     thread_local std::vector<double> bd;
-    if (cfg->precision == MDR_F32) expand_envs<float>((const float*)ctx->h_compact, (float*)host_obs, a, b, N, C, bf);
-    else expand_envs<double>((const double*)ctx->h_compact, (double*)host_obs, a, b, N, C, bd);
+    for (;;) {
+      const int a = next_chunk[s].fetch_add(chunk, std::memory_order_relaxed);
+      if (a >= ne) break;
+      const int b = a + chunk < ne ? a + chunk : ne;
+      if (cfg->precision == MDR_F32) expand_envs<float>((const float*)ctx->h_compact, (float*)host_obs, e0 + a, e0 + b, N, C, bf);
+      else expand_envs<double>((const double*)ctx->h_compact, (double*)host_obs, e0 + a, e0 + b, N, C, bd);
+    }
   };
   auto wait_slices = [&]() {
     for (int s = 0; s < n_slices; ++s) {
@@ -227,6 +235,7 @@ extern "C" int mdr_host_ctx_create(const MdrConfig* cfg, int32_t n_threads, int3
     cpu_set_t set;
     CPU_ZERO(&set);
     n_threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : (int)std::thread::hardware_concurrency();
+    if (n_threads > 1) n_threads -= 1;  // the caller's thread issues the work and waits for the slices
     if (n_threads > 24) n_threads = 24;
   }
   if (n_threads < 1) n_threads = 1;
@@ -238,7 +247,9 @@ extern "C" int mdr_host_ctx_create(const MdrConfig* cfg, int32_t n_threads, int3
             cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&c->ev_end[0], cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&c->ev_end[1], cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; ok && i < kMaxSlices; ++i) ok = cudaEventCreateWithFlags(&c->ev_slice[i], cudaEventDisableTiming) == cudaSuccess;
+  // (blocking sync: the thread that waits for a slice sleeps instead of spinning on a core the expansion needs)
+  for (int i = 0; ok && i < kMaxSlices; ++i)
+    ok = cudaEventCreateWithFlags(&c->ev_slice[i], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
   ok = ok && cudaMalloc(&c->d_compact, c->compact_bytes) == cudaSuccess;
   // pinned staging, first touched (and therefore placed) by this thread: pin the process to the GPU's NUMA node first
   ok = ok && cudaHostAlloc(&c->h_compact, c->compact_bytes, cudaHostAllocDefault) == cudaSuccess;
