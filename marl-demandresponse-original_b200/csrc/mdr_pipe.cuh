@@ -37,7 +37,18 @@ __device__ __forceinline__ unsigned long long global_ns() {
       g_trace[((w) * MDR_TRACE_TILES + (t)) * MDR_TRACE_POINTS + (k)] = global_ns();                  \
   } while (0)
 #define MDR_STAMP(k) MDR_STAMP_AT(warp, it, k)
+// per-CTA span of the launch: [0] kernel entry, [1] past griddepcontrol.wait, [2] tile loop done, [3] kernel exit
+__device__ unsigned long long g_cta_span[2048 * 4];
+#define MDR_CTA_STAMP(k)                                                                              \
+  do {                                                                                                \
+    if (threadIdx.x == 0 && blockIdx.x < 2048) g_cta_span[blockIdx.x * 4 + (k)] = global_ns();        \
+  } while (0)
 }  // namespace mdr
+extern "C" int mdr_debug_cta_span(unsigned long long* host, size_t n) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -5;
+  if (cudaMemcpyFromSymbol(host, mdr::g_cta_span, n * sizeof(unsigned long long)) != cudaSuccess) return -5;
+  return 0;
+}
 // trace builds only (tools/trace_tile.py): copies the globaltimer stamps of the traced CTA to the host
 extern "C" int mdr_debug_trace(unsigned long long* host, size_t n, int clear) {
   if (cudaDeviceSynchronize() != cudaSuccess) return -5;
@@ -53,6 +64,7 @@ namespace mdr {
 #else
 #define MDR_STAMP_AT(w, t, k) do { } while (0)
 #define MDR_STAMP(k) do { } while (0)
+#define MDR_CTA_STAMP(k) do { } while (0)
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -262,6 +274,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
   const int ring_mask = 2 * p.pro_batch - 1;
   const int ring_shift = 31 - __clz(ring_mask + 1);
+  MDR_CTA_STAMP(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
   if (tid == 0) {
     ctl.due_n = 0;
@@ -338,6 +351,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   int cmd_next = 0;
   int any_due = 0;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
+  MDR_CTA_STAMP(1);
   if (tile < n_tiles) {
     issue_tile(tile, 0);
     cmd_next = fetch_action(tile);
@@ -567,6 +581,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   }
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();
+  MDR_CTA_STAMP(2);
   if (interp_mode && any_due) pipe_refresh_pass(p, le, li);  // CTA-uniform: every house thread read the same flags
+  MDR_CTA_STAMP(3);
 }
 

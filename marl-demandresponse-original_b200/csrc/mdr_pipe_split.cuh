@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   const int ring_shift = 31 - __clz(ring_mask + 1);
   const int ncl = p.cl;
   const int rank = (int)cluster_ctarank();
+  MDR_CTA_STAMP(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     ctl.due_n = 0;
@@ -217,6 +218,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   int cmd_next = 0;
   int n_refresh = 0;  // refreshes of this CTA so far (phase of rbar; identical in every CTA of the cluster)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  MDR_CTA_STAMP(1);
   if (tile < n_tiles) {
     issue_tile(tile, 0);
     cmd_next = fetch_action(tile);
@@ -435,5 +437,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   }
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();
+  MDR_CTA_STAMP(2);
+  MDR_CTA_STAMP(3);
 }
 

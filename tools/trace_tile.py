@@ -45,3 +45,22 @@ for wi in (0, 3, 6):
     print(rel[wi, :, :8])
 print("prologue warp: per pass starting at tile it0: [wait for slot, start, end]")
 print(rel[7][:, [8, 0, 7]])
+
+# per-CTA span of the traced launch (every CTA): entry, past griddepcontrol.wait, tile loop done, exit
+if hasattr(lib, "mdr_debug_cta_span"):
+    span = (C.c_ulonglong * (2048 * 4))()
+    lib.mdr_debug_cta_span.argtypes = [C.c_void_p, C.c_size_t]
+    lib.mdr_debug_cta_span(span, 2048 * 4)
+    sp = np.frombuffer(span, dtype=np.uint64).reshape(2048, 4).astype(np.int64)
+    sp = sp[sp[:, 0] > 0]
+    base = sp[:, 0].min()
+    r = (sp - base) / 1e3
+    print("CTAs traced: %d; kernel span %.1f us (first entry -> last exit)" % (len(sp), r[:, 3].max()))
+    for k, name in enumerate(["entry", "past griddepcontrol.wait", "tile loop done", "exit"]):
+        q = np.percentile(r[:, k], [0, 10, 50, 90, 100])
+        print("  %-26s min %.1f  p10 %.1f  median %.1f  p90 %.1f  max %.1f us" % (name, *q))
+    busy = r[:, 2] - r[:, 1]
+    print("  tile loop duration per CTA: min %.1f median %.1f max %.1f us; refresh pass: median %.1f max %.1f us"
+          % (busy.min(), np.median(busy), busy.max(), np.median(r[:, 3] - r[:, 2]), (r[:, 3] - r[:, 2]).max()))
+    late = np.argsort(r[:, 3])[-8:]
+    print("  last CTAs to exit (blockIdx, entry, start, loop done, exit):", [(int(i), *np.round(r[i], 1)) for i in late])
