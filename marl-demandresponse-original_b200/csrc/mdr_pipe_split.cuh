@@ -6,9 +6,10 @@
 // env's CTAs owe each other crosses distributed shared memory, pushed by the producer:
 //   * every warp's partial power sum (and metric partials) into all cl CTAs' [rank][warp] slots,
 //   * the first / last houses' messages into the neighbouring CTAs' halo entries of the message window,
-// followed by ONE remote mbarrier arrive per warp and peer (release at cluster scope); the tile's only rendezvous is the
-// wait on the CTA's own mbarrier (count cl x house warps, acquire at cluster scope) -- it replaces the CTA barrier of
-// the single-CTA kernel.  Windows, partial slots and mbarriers are double buffered by tile parity.
+// as asynchronous remote stores that credit their bytes to the DESTINATION CTA's mbarrier (st.async ... complete_tx); the
+// tile's only rendezvous is the wait on the CTA's own mbarrier (its own warps arrive, one of them announcing the bytes
+// the peers owe) -- it replaces the CTA barrier of the single-CTA kernel; no fence, no remote arrive.  Windows, partial
+// slots and mbarriers are double buffered by tile parity.
 // The prologue warp of every CTA evaluates the env's record for itself (same inputs, same result); the per-env outputs
 // are written once, by rank 0, after the rendezvous (nobody may overwrite what a peer's prologue can still read).
 // An interpolation refresh due for the env is evaluated inside the tile (by every CTA, redundantly: it is rare).
@@ -27,11 +28,20 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, int rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+// Asynchronous remote stores (DSMEM) that signal the DESTINATION CTA's mbarrier with the bytes they deliver
+// (complete_tx): the consumer's wait on its own mbarrier is all the synchronisation the data needs -- no release fence,
+// no remote arrive on the producer's side (a fence + 5 arrives per warp cost 1-3 us per tile).
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(raddr), "f"(v), "r"(rmbar)
+               : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t raddr, const float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, const float4 v, uint32_t rmbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(rmbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // One release fence at cluster scope, then relaxed arrives on every peer: a release per arrive would pay the fence
 // (and wait for everything this thread has in flight) once per peer -- measured 2.8 us per tile with 5 peers.
@@ -142,8 +152,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
       mbar_init(&ctl.full[i], 1);
       mbar_init(&ctl.empty[i], p.house_warps);
     }
-    mbar_init(&sctl.xbar[0], ncl * p.house_warps);
-    mbar_init(&sctl.xbar[1], ncl * p.house_warps);
+    mbar_init(&sctl.xbar[0], p.house_warps);  // local arrivals; the peers' contributions are transaction bytes
+    mbar_init(&sctl.xbar[1], p.house_warps);
     mbar_init(&sctl.rbar, ncl * p.house_warps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -177,6 +187,9 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   const uint32_t win_base = smem_u32(smem_raw + p.off_msg);
   const uint32_t hi_addr = mapa_shared(win_base + (uint32_t)(half + H_prev + tid) * 16u, prev);
   const uint32_t lo_addr = mapa_shared(win_base + (uint32_t)(tid - (H - half)) * 16u, next);
+  const uint32_t xbar_prev = mapa_shared(smem_u32(&sctl.xbar[0]), prev), xbar_next = mapa_shared(smem_u32(&sctl.xbar[0]), next);
+  // bytes this CTA receives per tile: cl x nw partial sums (x 6 with metric partials) + the C halo messages
+  const uint32_t tx_bytes = (uint32_t)(ncl * nw) * (kMetrics ? 24u : 4u) + (uint32_t)C * 16u;
   // warp-partial power sums of the whole env: [2][cl][nw] (+ metric partials [2][cl][nw][5])
   float* const part_base = reinterpret_cast<float*>(smem_raw + p.off_pw);
   float* const met_base = reinterpret_cast<float*>(smem_raw + p.off_met);
@@ -230,6 +243,11 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
     const unsigned h = (unsigned)e * (unsigned)N + (unsigned)(lo + tid);
     int cmd = cmd_next;
     const int next_tile = tile + tile_stride;
+    if (next_tile < n_tiles) {
+      issue_tile(next_tile, sbuf ^ 1);
+      cmd_next = fetch_action(next_tile);
+    }
+    cp_async_commit();
     const int slot = it & ring_mask;
     const PipeEnv* const pe = s_env + slot;  // one env per tile
     MDR_STAMP(0);
@@ -237,7 +255,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
     const float od_old = pe->od_old;
     const float gain = pe->gain;
     MDR_STAMP(1);
-    cp_async_wait<0>();  // (the next tile's inputs are requested after this tile's release fence, see below)
+    cp_async_wait<1>();
     MDR_STAMP(2);
 
     // ---------------- phase A: per house ---------------------------------------------------
@@ -277,8 +295,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
       const float4 m = make_float4((t_air - target) * 0.2f, (float)sso, pw * inv_norm, p_on * inv_norm);
       msg[0] = m;
       const uint32_t boff = (uint32_t)(sbuf * ws) * 16u;
-      if (push_hi) st_cluster_v4(hi_addr + boff, m);
-      if (push_lo) st_cluster_v4(lo_addr + boff, m);
+      if (push_hi) st_async_v4(hi_addr + boff, m, xbar_prev + (uint32_t)sbuf * 8u);
+      if (push_lo) st_async_v4(lo_addr + boff, m, xbar_next + (uint32_t)sbuf * 8u);
       // utils.deadbandL2, utils.py:1266-1274
       const float hi = target + deadband * 0.5f, lw = target - deadband * 0.5f;
       if (hi < t_air) pen = (t_air - hi) * (t_air - hi);
@@ -293,32 +311,26 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
         s0 = warp_sum_f(pen); s1 = warp_sum_f(terr); s2 = warp_sum_f(fabsf(terr)); s3 = warp_sum_f(terr * terr);
         s4 = warp_max_f(fabsf(terr));
       }
-      __syncwarp();  // this warp's window entries and halo pushes precede lane 0's release
+      __syncwarp();  // this warp's window entries precede lane 0's (release) arrive on the CTA's own mbarrier
       if (lane == 0) {
         const uint32_t pb = (uint32_t)(sbuf * part_buf) * 4u, mb = (uint32_t)(sbuf * part_buf) * 20u;
         for (int r = 0; r < ncl; ++r) {
-          st_cluster_f32(mapa_shared(part_saddr + pb, r), psum);
+          const uint32_t rbar = mapa_shared(xbar_saddr + (uint32_t)sbuf * 8u, r);
+          st_async_f32(mapa_shared(part_saddr + pb, r), psum, rbar);
           if (kMetrics) {
             const uint32_t ma = mapa_shared(met_saddr + mb, r);
-            st_cluster_f32(ma, s0); st_cluster_f32(ma + 4, s1); st_cluster_f32(ma + 8, s2); st_cluster_f32(ma + 12, s3);
-            st_cluster_f32(ma + 16, s4);
+            st_async_f32(ma, s0, rbar); st_async_f32(ma + 4, s1, rbar); st_async_f32(ma + 8, s2, rbar);
+            st_async_f32(ma + 12, s3, rbar); st_async_f32(ma + 16, s4, rbar);
           }
         }
-        fence_release_cluster();
-        for (int r = 0; r < ncl; ++r) mbar_arrive_remote(mapa_shared(xbar_saddr + (uint32_t)sbuf * 8u, r));
+        if (warp == 0) mbar_arrive_expect_tx(&sctl.xbar[sbuf], tx_bytes);
+        else mbar_arrive(&sctl.xbar[sbuf]);
       }
     }
-    // the state goes back to HBM, and the next tile's inputs are requested, AFTER the arrives: the release fence above
-    // then has nothing of this warp's in flight to wait for (with the prefetch issued before it: +1 us per tile)
     if (active) {
       reinterpret_cast<float2*>(p.temps)[h] = make_float2(t_air, t_mass);
       p.hvac[h] = (sso << 2) | (lock << 1) | on;
     }
-    if (next_tile < n_tiles) {
-      issue_tile(next_tile, sbuf ^ 1);
-      cmd_next = fetch_action(next_tile);
-    }
-    cp_async_commit();
     MDR_STAMP(3);
     // the staging rows of this warp may still be read by the previous tile's bulk store
     if (kObs && it > 0) {
@@ -327,7 +339,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
     }
     MDR_STAMP(4);
     // the tile's only rendezvous: every warp of every CTA of the env has delivered its messages and partials
-    mbar_wait_cluster(&sctl.xbar[sbuf], (it >> 1) & 1);
+    mbar_wait(&sctl.xbar[sbuf], (it >> 1) & 1);
     MDR_STAMP(5);
 
     float P = 0;
