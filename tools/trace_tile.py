@@ -21,6 +21,8 @@ table = mdr_b200.synthetic_interp_table() if w["interp"] else None
 env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", device="cuda:0", seed=1234, interp_table=table,
                                     action_source=w["action_source"], with_obs=w["obs"])
 env.reset_tensor()
+if w["interp"] and os.environ.get("MDR_TRACE_STAGGER", "1") == "1":
+    env.stagger_interp_clock(seed=77)   # like bench.py: every step refreshes ~1/75 of the clusters
 act = (torch.rand(E, N, device="cuda:0") < 0.5).to(torch.uint8)
 a = act if w["action_source"] == "array" else None
 for _ in range(20):
