@@ -209,12 +209,14 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
     const int e = tile * G + le;
     const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
     const bool due = active && p.time_since_interp[e] < 0;
-    int any;
-    asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.or.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
-                 : "=r"(any)
-                 : "r"((int)due), "r"(T)
-                 : "memory");
-    if (!any) continue;
+    if (!listed) {  // (a listed tile has a due env by construction)
+      int any;
+      asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.or.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
+                   : "=r"(any)
+                   : "r"((int)due), "r"(T)
+                   : "memory");
+      if (!any) continue;
+    }
     double od_new = 0.0, hour_s = 0.0, date = 0.0;
     if (due) {
       od_new = p.od_temp[e];
@@ -225,6 +227,7 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
         date = (double)cal.yday;
       }
     }
+    double val = 0.0;
     if (due && li < nsamp) {
       int src = li;
       if (N > nb) {
@@ -238,12 +241,22 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       const size_t hs = (size_t)e * N + src;
       const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
       const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-      s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
+      val = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
+    }
+    s_val[tid] = val;  // 0 for houses that are not sampled
+    house_sync(T);
+    // per-env sum by the env's first 32 threads (one warp when N >= 32; the fp32 mode's tolerance does not need the
+    // reference's id order here -- the fp64 kernels keep it)
+    if (due && li < 32) {
+      double part = 0.0;
+      for (int i = li; i < nsamp; i += 32) part += s_val[le * N + i];
+      s_val[T + le * 32 + li] = part;
     }
     house_sync(T);
     if (due && li == 0) {
       double base = 0.0;
-      for (int i = 0; i < nsamp; ++i) base = add_rn(base, s_val[le * N + i]);  // id order, :1218-1232
+      const int np = nsamp < 32 ? nsamp : 32;
+      for (int i = 0; i < np; ++i) base += s_val[T + le * 32 + i];
       if (N > nb) base = mul_rn(base, (double)N / (double)nb);
       const Calendar cal = calendar_time((uint32_t)p.t_epoch[e]);
       const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
@@ -258,7 +271,8 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
     }
     house_sync(T);
     if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
-    house_sync(T);  // s_val / s_fsig are reused by the next due tile
+    // (s_val / s_fsig are reused by the next due tile: its first writes come after this tile's last reads of the same
+    //  thread's entries, and its first barrier orders the rest)
   }
 }
 
