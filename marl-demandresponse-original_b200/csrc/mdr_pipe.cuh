@@ -38,10 +38,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
   } while (0)
 #define MDR_STAMP(k) MDR_STAMP_AT(warp, it, k)
 // per-CTA span of the launch: [0] kernel entry, [1] past griddepcontrol.wait, [2] tile loop done, [3] kernel exit
-__device__ unsigned long long g_cta_span[2048 * 4];
+__device__ unsigned long long g_cta_span[2048 * 8];
 #define MDR_CTA_STAMP(k)                                                                              \
   do {                                                                                                \
-    if (threadIdx.x == 0 && blockIdx.x < 2048) g_cta_span[blockIdx.x * 4 + (k)] = global_ns();        \
+    if (threadIdx.x == 0 && blockIdx.x < 2048) g_cta_span[blockIdx.x * 8 + (k)] = global_ns();        \
   } while (0)
 }  // namespace mdr
 extern "C" int mdr_debug_cta_span(unsigned long long* host, size_t n) {
@@ -199,6 +199,7 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
   __syncwarp();
   PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
   house_sync(T);  // the due-tile list written by thread 0 during the tile loop
+  MDR_CTA_STAMP(4);
   const int n_due = ctl.due_n;
   const bool listed = n_due <= kMaxDue;  // (overflow: walk every tile of this CTA)
   const int n_visit = listed ? n_due : (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -244,7 +245,9 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       val = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
     }
     s_val[tid] = val;  // 0 for houses that are not sampled
+    if (v == 0) MDR_CTA_STAMP(5);
     house_sync(T);
+    if (v == 0) MDR_CTA_STAMP(6);
     // per-env sum by the env's first 32 threads (one warp when N >= 32; the fp32 mode's tolerance does not need the
     // reference's id order here -- the fp64 kernels keep it)
     if (due && li < 32) {
@@ -271,6 +274,7 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
     }
     house_sync(T);
     if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
+    if (v == 0) MDR_CTA_STAMP(7);
     // (s_val / s_fsig are reused by the next due tile: its first writes come after this tile's last reads of the same
     //  thread's entries, and its first barrier orders the rest)
   }

@@ -50,10 +50,10 @@ print(rel[7][:, [8, 0, 7]])
 
 # per-CTA span of the traced launch (every CTA): entry, past griddepcontrol.wait, tile loop done, exit
 if hasattr(lib, "mdr_debug_cta_span"):
-    span = (C.c_ulonglong * (2048 * 4))()
+    span = (C.c_ulonglong * (2048 * 8))()
     lib.mdr_debug_cta_span.argtypes = [C.c_void_p, C.c_size_t]
-    lib.mdr_debug_cta_span(span, 2048 * 4)
-    sp = np.frombuffer(span, dtype=np.uint64).reshape(2048, 4).astype(np.int64)
+    lib.mdr_debug_cta_span(span, 2048 * 8)
+    sp = np.frombuffer(span, dtype=np.uint64).reshape(2048, 8).astype(np.int64)
     sp = sp[sp[:, 0] > 0]
     base = sp[:, 0].min()
     r = (sp - base) / 1e3
@@ -64,5 +64,9 @@ if hasattr(lib, "mdr_debug_cta_span"):
     busy = r[:, 2] - r[:, 1]
     print("  tile loop duration per CTA: min %.1f median %.1f max %.1f us; refresh pass: median %.1f max %.1f us"
           % (busy.min(), np.median(busy), busy.max(), np.median(r[:, 3] - r[:, 2]), (r[:, 3] - r[:, 2]).max()))
+    for i in np.argsort(r[:, 3] - r[:, 2])[-6:]:
+        print("  CTA %4d refresh pass: loop done %.1f | list ready +%.1f | first tile: thread 0 evaluated +%.1f, all evaluated +%.1f, "
+              "patched +%.1f | exit +%.1f" % (i, r[i, 2], r[i, 4] - r[i, 2], r[i, 5] - r[i, 2], r[i, 6] - r[i, 2], r[i, 7] - r[i, 2],
+                                            r[i, 3] - r[i, 2]))
     late = np.argsort(r[:, 3])[-8:]
     print("  last CTAs to exit (blockIdx, entry, start, loop done, exit):", [(int(i), *np.round(r[i], 1)) for i in late])
