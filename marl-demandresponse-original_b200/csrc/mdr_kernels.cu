@@ -103,16 +103,26 @@ inline SmemLayout smem_layout(int real_bytes, int hmax, int genvs_max, int nwarp
 // multilinear interpolation, monteCarlo/interpolation.py:113-142 + scipy linear interpn.
 // `key` = (flat index over the 4 nearest thermal-ratio cells) * 16 + nearest HVAC-power index.
 // ----------------------------------------------------------------------------------------
-__device__ __forceinline__ double clip_axis(const KernelParams& p, int d, double v) {
+// The interpolation grid (dims + axes) as the kernels read it: KernelParams holds it (constant bank when accessed from
+// the kernel body), and the pipelined kernels keep a copy in shared memory -- their refresh code lives in out-of-line
+// functions that only see KernelParams through a reference, where every access is a generic global load (measured:
+// 14 us per refreshed tile, all of it dependent parameter loads).
+struct InterpGrid {
+  int interp_dims[MDR_INTERP_DIMS];
+  double interp_axes[MDR_INTERP_DIMS][MDR_INTERP_MAX_AXIS];
+};
+
+template <typename G>
+__device__ __forceinline__ double clip_axis(const G& p, int d, double v) {
   const double lo = p.interp_axes[d][0], hi = p.interp_axes[d][p.interp_dims[d] - 1];
   if (v > hi) v = hi;
   else if (v < lo) v = lo;
   return v;
 }
 
-template <typename R>
-__device__ __noinline__ double interp_eval(const KernelParams& p, int key, double air, double mass, double od,
-                                           double hour, double date) {
+template <typename R, typename G>
+__device__ __noinline__ double interp_eval_grid(const G& p, const void* table_v, int key, double air, double mass, double od,
+                                                double hour, double date) {
   const int dims[5] = {4, 5, 6, 8, 9};
   const double x[5] = {clip_axis(p, 4, air), clip_axis(p, 5, mass), clip_axis(p, 6, od), clip_axis(p, 8, hour),
                        clip_axis(p, 9, date)};
@@ -132,7 +142,7 @@ __device__ __noinline__ double interp_eval(const KernelParams& p, int key, doubl
     w[k] = (x[k] - p.interp_axes[d][i]) / (p.interp_axes[d][i + 1] - p.interp_axes[d][i]);
   }
   const int therm = key >> 4, ih = key & 15;
-  const R* __restrict__ table = reinterpret_cast<const R*>(p.interp_table);
+  const R* __restrict__ table = reinterpret_cast<const R*>(table_v);
   const int n4 = p.interp_dims[4], n5 = p.interp_dims[5], n6 = p.interp_dims[6], n7 = p.interp_dims[7],
             n8 = p.interp_dims[8], n9 = p.interp_dims[9];
   // All 32 corner values are fetched first (independent loads in flight together: the table lives in L2 and a corner
@@ -159,6 +169,12 @@ __device__ __noinline__ double interp_eval(const KernelParams& p, int key, doubl
     value = add_rn(value, mul_rn((double)corner[c], weight));
   }
   return value;
+}
+
+template <typename R>
+__device__ __forceinline__ double interp_eval(const KernelParams& p, int key, double air, double mass, double od, double hour,
+                                              double date) {
+  return interp_eval_grid<R, KernelParams>(p, p.interp_table, key, air, mass, od, hour, date);
 }
 
 // PowerGrid.step signal shapes, env/MA_DemandResponse.py:1257-1314
@@ -1306,6 +1322,7 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   const size_t off_pw = o;    o += align16((size_t)2 * genvs * part_stride * sizeof(double));
   const size_t off_met = o;   o += align16((size_t)2 * genvs * part_stride * 5 * sizeof(float));  // metric partials
   const size_t off_val = o;   o += need_val ? align16(((size_t)hmax + (size_t)genvs * 32) * sizeof(double)) : 0;  // values | per-env partial sums
+  const size_t off_grid = o;  o += need_val ? align16(sizeof(InterpGrid)) : 0;
   const size_t off_env = o;   o += align16((size_t)2 * pro_batch * genvs * sizeof(PipeEnv));
   const size_t off_ctl = o;   o += align16(sizeof(PipeCtl));
   const size_t off_stage = o; o += has_obs ? align16((size_t)genvs * n_houses * n_features * sizeof(float)) : 0;
@@ -1313,7 +1330,7 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   if (kp) {
     kp->off_msg = (int)off_msg; kp->off_pw = (int)off_pw; kp->off_val = (int)off_val; kp->off_pen = 0;
     kp->off_env = (int)off_env; kp->off_stage = (int)off_stage; kp->off_in = (int)off_in; kp->off_ctl = (int)off_ctl;
-    kp->off_met = (int)off_met;
+    kp->off_met = (int)off_met; kp->off_grid = (int)off_grid;
   }
   return o;
 }

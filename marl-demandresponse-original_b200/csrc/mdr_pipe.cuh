@@ -242,7 +242,8 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       const size_t hs = (size_t)e * N + src;
       const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
       const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-      val = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
+      val = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
+                                                p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
     }
     s_val[tid] = val;  // 0 for houses that are not sampled
     if (v == 0) MDR_CTA_STAMP(5);
@@ -294,6 +295,11 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   const int ring_shift = 31 - __clz(ring_mask + 1);
   MDR_CTA_STAMP(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
+  if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
+    InterpGrid* g = reinterpret_cast<InterpGrid*>(smem_raw + p.off_grid);
+    if (tid < MDR_INTERP_DIMS) g->interp_dims[tid] = p.interp_dims[tid];
+    if (tid < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS) (&g->interp_axes[0][0])[tid] = (&p.interp_axes[0][0])[tid];
+  }
   if (tid == 0) {
     ctl.due_n = 0;
     for (int i = 0; i <= ring_mask; ++i) {

@@ -120,7 +120,8 @@ __device__ __noinline__ double split_refresh(const KernelParams& p, int e, const
     const size_t hs = (size_t)e * N + src;
     const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
     const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-    s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, pe.od_new - tg, hour_s, date);
+    s_val[tid] = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
+                                                     p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, pe.od_new - tg, hour_s, date);
   }
   house_sync(T);
   if (tid == 0) {
@@ -146,6 +147,11 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   const int ncl = p.cl;
   const int rank = (int)cluster_ctarank();
   MDR_CTA_STAMP(0);
+  if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
+    InterpGrid* g = reinterpret_cast<InterpGrid*>(smem_raw + p.off_grid);
+    if (tid < MDR_INTERP_DIMS) g->interp_dims[tid] = p.interp_dims[tid];
+    if (tid < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS) (&g->interp_axes[0][0])[tid] = (&p.interp_axes[0][0])[tid];
+  }
   if (tid == 0) {
     ctl.due_n = 0;
     for (int i = 0; i <= ring_mask; ++i) {
