@@ -1322,7 +1322,7 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   const size_t off_pw = o;    o += align16((size_t)2 * genvs * part_stride * sizeof(double));
   const size_t off_met = o;   o += align16((size_t)2 * genvs * part_stride * 5 * sizeof(float));  // metric partials
   const size_t off_val = o;   o += need_val ? align16(((size_t)hmax + (size_t)genvs * 32) * sizeof(double)) : 0;  // values | per-env partial sums
-  const size_t off_params = o; o += align16(sizeof(KernelParams));  // shared-memory copy of the parameters
+  const size_t off_grid = o;  o += need_val ? align16(sizeof(InterpGrid)) : 0;
   const size_t off_env = o;   o += align16((size_t)2 * pro_batch * genvs * sizeof(PipeEnv));
   const size_t off_ctl = o;   o += align16(sizeof(PipeCtl));
   const size_t off_stage = o; o += has_obs ? align16((size_t)genvs * n_houses * n_features * sizeof(float)) : 0;
@@ -1330,7 +1330,7 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   if (kp) {
     kp->off_msg = (int)off_msg; kp->off_pw = (int)off_pw; kp->off_val = (int)off_val; kp->off_pen = 0;
     kp->off_env = (int)off_env; kp->off_stage = (int)off_stage; kp->off_in = (int)off_in; kp->off_ctl = (int)off_ctl;
-    kp->off_met = (int)off_met; kp->off_params = (int)off_params;
+    kp->off_met = (int)off_met; kp->off_grid = (int)off_grid;
   }
   return o;
 }

@@ -22,7 +22,7 @@ struct KernelParams {
   int precision;                                              // MDR_F32 / MDR_F64 (kernels that are not templated on it)
   int pro_lanes;                                              // lanes of the prologue warp cooperating on one env (power of two)
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
-  int off_params;                                             // pipelined kernels: shared-memory copy of this struct
+  int off_grid;                                               // pipelined kernels: shared-memory copy of the interpolation grid
   int cl, cl_slice, off_cl;                                   // env split over a cluster of `cl` CTAs, `cl_slice` houses each; ClusterTot offset
   unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)
   int is_reset, comm_mode, state_flags, msg_flags, temp_penalty_mode, solar, base_power_mode, signal_mode;

@@ -242,7 +242,8 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       const size_t hs = (size_t)e * N + src;
       const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
       const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-      val = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);  // p: smem copy
+      val = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
+                                                p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
     }
     s_val[tid] = val;  // 0 for houses that are not sampled
     if (v == 0) MDR_CTA_STAMP(5);
@@ -294,14 +295,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   const int ring_shift = 31 - __clz(ring_mask + 1);
   MDR_CTA_STAMP(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
-  // Shared-memory copy of the kernel parameters for the out-of-line parts (prologue warp, deferred refresh): inside a
-  // __noinline__ function the parameters are only reachable through a reference, i.e. as generic loads from global
-  // memory -- chains of dependent cold misses (measured: 10-14 us per refreshed tile); the copy makes them LDS.
-  const KernelParams& sp = *reinterpret_cast<const KernelParams*>(smem_raw + p.off_params);
-  {
-    uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw + p.off_params);
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(&p);
-    for (int i = tid; i < (int)(sizeof(KernelParams) / 8); i += blockDim.x) dst[i] = src[i];
+  if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
+    InterpGrid* g = reinterpret_cast<InterpGrid*>(smem_raw + p.off_grid);
+    if (tid < MDR_INTERP_DIMS) g->interp_dims[tid] = p.interp_dims[tid];
+    if (tid < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS) (&g->interp_axes[0][0])[tid] = (&p.interp_axes[0][0])[tid];
   }
   if (tid == 0) {
     ctl.due_n = 0;
@@ -318,7 +315,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     // on the envs of tiles that exist, not on absent ones)
     int B = p.pro_batch;
     while (B > 1 && (B >> 1) * (int)gridDim.x >= p.n_tiles) B >>= 1;
-    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(sp, it0, B);
+    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
     return;
   }
 
@@ -609,7 +606,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();
   MDR_CTA_STAMP(2);
-  if (interp_mode && any_due) pipe_refresh_pass(sp, le, li);  // CTA-uniform: every house thread read the same flags
+  if (interp_mode && any_due) pipe_refresh_pass(p, le, li);  // CTA-uniform: every house thread read the same flags
   MDR_CTA_STAMP(3);
 }
 

@@ -120,7 +120,8 @@ __device__ __noinline__ double split_refresh(const KernelParams& p, int e, const
     const size_t hs = (size_t)e * N + src;
     const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
     const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-    s_val[tid] = interp_eval<float>(p, p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, pe.od_new - tg, hour_s, date);
+    s_val[tid] = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
+                                                     p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, pe.od_new - tg, hour_s, date);
   }
   house_sync(T);
   if (tid == 0) {
@@ -146,12 +147,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   const int ncl = p.cl;
   const int rank = (int)cluster_ctarank();
   MDR_CTA_STAMP(0);
-  // shared-memory copy of the kernel parameters for the out-of-line parts (see step_pipe_kernel)
-  const KernelParams& sp = *reinterpret_cast<const KernelParams*>(smem_raw + p.off_params);
-  {
-    uint64_t* dst = reinterpret_cast<uint64_t*>(smem_raw + p.off_params);
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(&p);
-    for (int i = tid; i < (int)(sizeof(KernelParams) / 8); i += blockDim.x) dst[i] = src[i];
+  if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
+    InterpGrid* g = reinterpret_cast<InterpGrid*>(smem_raw + p.off_grid);
+    if (tid < MDR_INTERP_DIMS) g->interp_dims[tid] = p.interp_dims[tid];
+    if (tid < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS) (&g->interp_axes[0][0])[tid] = (&p.interp_axes[0][0])[tid];
   }
   if (tid == 0) {
     ctl.due_n = 0;
@@ -171,7 +170,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int B = p.pro_batch;
     while (B > 1 && (B >> 1) * (int)gridDim.x >= p.n_tiles) B >>= 1;
-    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(sp, it0, B);
+    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
     return;
   }
 
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
     double sig_new = pe->sig_new;
     float f_sig = pe->f_sig;
     if (interp_mode && pe->due) {  // CTA- and cluster-uniform
-      sig_new = split_refresh(sp, e, *pe, T, n_refresh++);
+      sig_new = split_refresh(p, e, *pe, T, n_refresh++);
       f_sig = (float)(sig_new * p.inv_norm_sig_agents);
     }
     if (env_head) {

@@ -93,7 +93,7 @@ size_t pipe_split_smem_layout(KernelParams* kp, int hmax, int slice, int n_featu
   const size_t off_pw = o;    o += align16((size_t)2 * cluster * house_warps * sizeof(float));
   const size_t off_met = o;   o += align16((size_t)2 * cluster * house_warps * 5 * sizeof(float));
   const size_t off_val = o;   o += need_val ? align16(((size_t)hmax + 2) * sizeof(double)) : 0;
-  const size_t off_params = o; o += align16(sizeof(KernelParams));  // shared-memory copy of the parameters
+  const size_t off_grid = o;  o += need_val ? align16(sizeof(InterpGrid)) : 0;
   const size_t off_env = o;   o += align16((size_t)2 * pro_batch * sizeof(PipeEnv));
   const size_t off_ctl = o;   o += align16(sizeof(SplitCtl));
   const size_t off_stage = o; o += has_obs ? align16((size_t)slice * n_features * sizeof(float)) : 0;
@@ -101,7 +101,7 @@ size_t pipe_split_smem_layout(KernelParams* kp, int hmax, int slice, int n_featu
   if (kp) {
     kp->off_msg = (int)off_msg; kp->off_pw = (int)off_pw; kp->off_val = (int)off_val; kp->off_pen = 0;
     kp->off_env = (int)off_env; kp->off_stage = (int)off_stage; kp->off_in = (int)off_in; kp->off_ctl = (int)off_ctl;
-    kp->off_met = (int)off_met; kp->off_params = (int)off_params;
+    kp->off_met = (int)off_met; kp->off_grid = (int)off_grid;
   }
   return o;
 }
