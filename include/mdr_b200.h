@@ -246,9 +246,11 @@ const char *mdr_last_cuda_error(void);
 /* F of utils.normStateDict (utils.py:740-880) for these flags; negative MdrStatus on error. */
 int mdr_obs_width(const MdrConfig *cfg);
 
-/* Device scratch a step of this configuration needs in MdrEnvs.workspace: 0 unless an env is larger than a
-   thread-block cluster can hold (n_houses > MDR_MAX_HOUSES_PER_CLUSTER), where the cluster power, the penalties and
-   the per-env record cross the CTAs through global memory (three launches per step). */
+/* Device scratch a step of this configuration uses in MdrEnvs.workspace (zero it once after allocating; the kernels
+   leave it zeroed): for envs larger than a thread-block cluster can hold (n_houses > MDR_MAX_HOUSES_PER_CLUSTER) the
+   per-env records and per-CTA totals of the three-launch path (required there); with interpolated base power the
+   queue through which the CTAs of the pipelined kernel share the tiles whose refresh is due (optional: without it
+   every CTA refreshes its own tiles, which costs tens of microseconds of tail when refresh clocks are staggered). */
 int mdr_workspace_bytes(const MdrConfig *cfg, size_t *bytes);
 
 /* Validates cfg (modes, shapes) the way the reference constructors raise ValueError

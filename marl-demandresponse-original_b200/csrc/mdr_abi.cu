@@ -94,7 +94,14 @@ extern "C" int mdr_workspace_bytes(const MdrConfig* cfg, size_t* bytes) {
   if (!cfg || !bytes) return MDR_ERR_NULL;
   int st = mdr_validate(cfg);
   if (st != MDR_OK) return st;
-  *bytes = needs_big_path(cfg) ? mdr::big_workspace(cfg->n_envs, cfg->n_houses) : 0;
+  // big path: per-env records + per-CTA totals; pipelined kernel with interpolated base power: the due-tile queue of a
+  // launch (64-byte header + one word per tile), twice (the host-buffer pipeline runs two slices concurrently)
+  size_t need = needs_big_path(cfg) ? mdr::big_workspace(cfg->n_envs, cfg->n_houses) : 0;
+  if (cfg->base_power_mode == MDR_BASE_INTERPOLATION && !needs_big_path(cfg)) {
+    const size_t q = 2 * (size_t)mdr::due_queue_bytes(cfg->n_envs);
+    if (q > need) need = q;
+  }
+  *bytes = need;
   return MDR_OK;
 }
 
@@ -504,6 +511,8 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
   }
   const bool pipe = !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::pipe_eligible(k, g, cfg->precision);
   if (pipe) {
+    // the due queue needs its full size; a caller that passes less scratch (or none) gets the per-CTA refresh
+    if (k.workspace && !aligned16(k.workspace)) return MDR_ERR_ALIGN;
     k.pro_batch = g.pro_batch;
     int L = 16;  // lanes per env within one tile's lane group
     while (L > 1 && L * g.envs_per_cta * g.pro_batch > 32) L >>= 1;

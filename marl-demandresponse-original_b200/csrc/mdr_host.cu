@@ -140,6 +140,8 @@ int host_pipeline_step(MdrHostCtx* ctx, const MdrConfig* cfg, const MdrHouses* h
     es.time_since_interp = (int32_t*)off(e->time_since_interp, (size_t)e0 * 4);
     es.perlin_seed = (const double*)off(e->perlin_seed, (size_t)e0 * 8);
     es.metrics = (double*)off(e->metrics, (size_t)e0 * MDR_N_METRICS * 8);
+    // two slices are in flight at a time: each parity has its own due-tile queue in the workspace
+    es.workspace = off(e->workspace, (size_t)(s & 1) * due_queue_bytes(cfg->n_envs));
     MdrStepInputs is = *in;
     is.actions = (const uint8_t*)off(in->actions, h0);
     is.od_noise = (const double*)off(in->od_noise, (size_t)e0 * 8);

@@ -98,6 +98,7 @@ cudaError_t launch_populate(const KernelParams& kp, const MdrPopulationSpec& spe
 bool fused_eligible(const KernelParams& kp);
 cudaError_t launch_big(const KernelParams& kp, int precision, void* workspace, cudaStream_t stream);
 size_t big_workspace(int n_envs, int n_houses);
+inline size_t due_queue_bytes(int n_envs) { return (64 + 4 * (size_t)n_envs + 63) & ~(size_t)63; }  // header + a word per tile
 cudaError_t launch_compact_obs(const KernelParams& kp, int precision, void* out, cudaStream_t stream);
 cudaError_t launch_sample_actions(const float* probs, long long n_rows, int n_actions, uint64_t seed, uint64_t draw_index,
                                   const uint64_t* draw_counter, uint8_t* actions, float* chosen_prob, cudaStream_t stream);

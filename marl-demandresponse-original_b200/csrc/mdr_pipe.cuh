@@ -178,14 +178,36 @@ __device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B
 // re-evaluates the signal and patches observation feature 9 (the only output that depends on it).
 // signal-dependent metric accumulators of one env and step (MDR_M_SUM_SIGNAL ..., main-deploy.py:140-149)
 __device__ __forceinline__ void metrics_signal_terms(double* m, double sig, double P) {
-  const double d = sig - P;
-  m[MDR_M_SUM_SIGNAL] += sig;
-  m[MDR_M_SUM_SIGNAL_OFFSET] += d;
-  m[MDR_M_SUM_SIGNAL_ERROR] += fabs(d);
-  m[MDR_M_SUM_SQ_SIGNAL_ERROR] += d * d;
+  const double d = sig - P;  // (read-modify-write through L2: a due env's terms may be added by another SM's CTA)
+  __stcg(m + MDR_M_SUM_SIGNAL, __ldcg(m + MDR_M_SUM_SIGNAL) + sig);
+  __stcg(m + MDR_M_SUM_SIGNAL_OFFSET, __ldcg(m + MDR_M_SUM_SIGNAL_OFFSET) + d);
+  __stcg(m + MDR_M_SUM_SIGNAL_ERROR, __ldcg(m + MDR_M_SUM_SIGNAL_ERROR) + fabs(d));
+  __stcg(m + MDR_M_SUM_SQ_SIGNAL_ERROR, __ldcg(m + MDR_M_SUM_SQ_SIGNAL_ERROR) + d * d);
 }
 
-__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li) {
+// Queue of tiles with an interpolation refresh due, shared by ALL CTAs of a launch (in MdrEnvs.workspace, zeroed by its
+// owner once; the kernel leaves it zeroed).  With staggered refresh clocks a few percent of the tiles are due at every
+// step: a CTA that refreshed its own due tiles after its tile loop would hold the whole launch back by 10+ us per
+// tile (measured: 30-40 us of tail on 16 384 x 100), so every CTA publishes its due tiles here and then takes tiles
+// from the queue until it is empty -- the refresh work of a step is spread over the whole grid.
+struct DueQueue {
+  unsigned reserved;   // slots handed out to publishers
+  unsigned taken;      // slots claimed by consumers
+  unsigned ctas_done;  // CTAs that have published everything they have
+  unsigned exited;     // CTAs that are done with the queue (the last one re-zeroes the header)
+  unsigned pad[12];
+  unsigned tiles[1];   // [n_tiles] tile index + 1, 0 = empty
+};
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// refresh of ONE due tile (all house threads of the CTA): table walk on the houses' NEW state, base power, signal,
+// observation feature 9 (PowerGrid.step :1250-1255, interpolatePower :1195-1234)
+__device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int tile, int le, int li) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
   float* s_fsig = reinterpret_cast<float*>(smem_raw + p.off_pw);  // [G], the power partials are dead by now
@@ -194,90 +216,142 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
   const int nb = p.interp_nb_agents;
   const int nsamp = N <= nb ? N : nb;
   const int T = p.hmax;
-  // the bulk stores of this warp's rows must have landed before feature 9 is patched
-  if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  __syncwarp();
-  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
-  house_sync(T);  // the due-tile list written by thread 0 during the tile loop
-  MDR_CTA_STAMP(4);
-  const int n_due = ctl.due_n;
-  const bool listed = n_due <= kMaxDue;  // (overflow: walk every tile of this CTA)
-  const int n_visit = listed ? n_due : (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  for (int v = 0; v < n_visit; ++v) {
-    const int tile = listed ? ctl.due_list[v] : (int)blockIdx.x + v * (int)gridDim.x;
-    const int H = min(GN, (p.E - tile * G) * N);
-    const bool active = tid < H;
-    const int e = tile * G + le;
-    const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
-    const bool due = active && p.time_since_interp[e] < 0;
-    if (!listed) {  // (a listed tile has a due env by construction)
-      int any;
-      asm volatile("{ .reg .pred a, b; setp.ne.s32 a, %1, 0; bar.red.or.pred b, 1, %2, a; selp.s32 %0, 1, 0, b; }"
-                   : "=r"(any)
-                   : "r"((int)due), "r"(T)
-                   : "memory");
-      if (!any) continue;
+  const int H = min(GN, (p.E - tile * G) * N);
+  const bool active = tid < H;
+  const int e = tile * G + le;
+  const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+  // (another SM may have written this tile's state in this launch: L1 is not coherent across SMs, read through L2)
+  const bool due = active && __ldcg(p.time_since_interp + e) < 0;
+  double od_new = 0.0, hour_s = 0.0, date = 0.0;
+  if (due) {
+    od_new = __ldcg(p.od_temp + e);
+    if (p.solar) {  // interpolatePower point :1198-1207: seconds since midnight and tm_yday, 0 with solar gain off
+      Calendar cal = calendar_time((uint32_t)__ldcg(p.t_epoch + e));
+      calendar_date(cal);
+      hour_s = (double)cal.sod;
+      date = (double)cal.yday;
     }
-    double od_new = 0.0, hour_s = 0.0, date = 0.0;
-    if (due) {
-      od_new = p.od_temp[e];
-      if (p.solar) {  // interpolatePower point :1198-1207: seconds since midnight and tm_yday, 0 with solar gain off
-        Calendar cal = calendar_time((uint32_t)p.t_epoch[e]);
-        calendar_date(cal);
-        hour_s = (double)cal.sod;
-        date = (double)cal.yday;
+  }
+  double val = 0.0;
+  if (due && li < nsamp) {
+    int src = li;
+    if (N > nb) {
+      if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
+      else {
+        const uint4 r = philox4x32((uint32_t)(e + p.env_base), (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
+                                   STREAM_IDS + 16 * (uint32_t)li, p.seed);
+        src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
       }
     }
-    double val = 0.0;
-    if (due && li < nsamp) {
-      int src = li;
-      if (N > nb) {
-        if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
-        else {
-          const uint4 r = philox4x32((uint32_t)(e + p.env_base), (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
-                                     STREAM_IDS + 16 * (uint32_t)li, p.seed);
-          src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
+    const size_t hs = (size_t)e * N + src;
+    const float2 t2 = __ldcg(reinterpret_cast<const float2*>(p.temps) + hs);
+    const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
+    val = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
+                                              p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
+  }
+  s_val[tid] = val;  // 0 for houses that are not sampled
+  house_sync(T);
+  // per-env sum by the env's first 32 threads (the fp32 mode's tolerance does not need the reference's id order here --
+  // the fp64 kernels keep it)
+  if (due && li < 32) {
+    double part = 0.0;
+    for (int i = li; i < nsamp; i += 32) part += s_val[le * N + i];
+    s_val[T + le * 32 + li] = part;
+  }
+  house_sync(T);
+  if (due && li == 0) {
+    double base = 0.0;
+    const int np = nsamp < 32 ? nsamp : 32;
+    for (int i = 0; i < np; ++i) base += s_val[T + le * 32 + i];
+    if (N > nb) base = mul_rn(base, (double)N / (double)nb);
+    const Calendar cal = calendar_time((uint32_t)__ldcg(p.t_epoch + e));
+    const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
+    const double sig_noise = __ldcg(p.base_power + e);  // parked by the prologue
+    const double sig = grid_signal(p, base, time_sec, sig_noise, p.artificial_ratio[e], p.max_power[e]);
+    p.base_power[e] = base;
+    p.time_since_interp[e] = 0;
+    p.signal[e] = sig;
+    s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
+    // the tile loop left the signal-dependent accumulators of a due env to this pass (its signal was not final)
+    if (p.metrics != nullptr) metrics_signal_terms(p.metrics + (size_t)e * MDR_N_METRICS, sig, __ldcg(p.cluster_power + e));
+  }
+  house_sync(T);
+  if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
+  // (s_val / s_fsig are reused by the next tile: its first writes come after this tile's last reads of the same
+  //  thread's entries, and its first barrier orders the rest)
+}
+
+// Deferred interpolation refresh (every interp_update_period seconds).  It runs on 1 step in 75 per env, needs fp64
+// and a 32-corner table walk per house, and would cost the tile loop registers if it sat inside it.  So the tile loop
+// treats a due env like any other (the prologue parks its perlin value and marks it), and this pass -- after the loop,
+// same launch -- evaluates the table on the houses' NEW state, re-evaluates the signal and patches observation
+// feature 9 (the only output that depends on it).
+__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int T = p.hmax;
+  PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
+  // this CTA's state stores and the bulk stores of its rows must have landed (and be visible to the whole GPU: another
+  // CTA may refresh these tiles) before anything is published or patched
+  if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __threadfence();
+  house_sync(T);  // ... and the due-tile list written by thread 0 during the tile loop is complete
+  const int n_due = ctl.due_n;
+  DueQueue* q = reinterpret_cast<DueQueue*>(p.workspace);
+  if (q == nullptr || n_due > kMaxDue) {
+    // no shared queue (no workspace), or more due tiles than the list holds: this CTA refreshes its own tiles
+    const bool listed = n_due <= kMaxDue;
+    const int n_visit = listed ? n_due : (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int v = 0; v < n_visit; ++v)
+      pipe_refresh_tile(p, listed ? ctl.due_list[v] : (int)blockIdx.x + v * (int)gridDim.x, le, li);
+    if (q == nullptr) return;
+  }
+  int* s_take = &ctl.tile_due[0];  // (the ring's due flags are dead after the tile loop)
+  if (tid == 0) {
+    if (n_due <= kMaxDue && n_due > 0) {
+      const unsigned base = atomicAdd(&q->reserved, (unsigned)n_due);
+      for (int i = 0; i < n_due; ++i) atomicExch(&q->tiles[base + i], (unsigned)ctl.due_list[i] + 1u);
+    }
+    __threadfence();
+    atomicAdd(&q->ctas_done, 1u);
+  }
+  for (;;) {
+    if (tid == 0) {
+      const unsigned idx = atomicAdd(&q->taken, 1u);
+      int got = -1;
+      unsigned long long t0 = 0;
+      for (unsigned spin = 0;; ++spin) {
+        const unsigned v = ld_volatile_u32(&q->tiles[idx]);
+        if (v != 0) {
+          q->tiles[idx] = 0;  // leave the queue zeroed for the next launch
+          got = (int)v - 1;
+          break;
+        }
+        if (ld_volatile_u32(&q->ctas_done) == gridDim.x) {  // every publisher is done: reserved is final
+          if (idx >= ld_volatile_u32(&q->reserved)) break;
+          continue;  // the slot was written before its publisher counted itself done: re-read it
+        }
+        if ((spin & 1023) == 1023) {  // a stuck peer must not hang the GPU: give up after ~2 s
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 2000000000ull) break;
         }
       }
-      const size_t hs = (size_t)e * N + src;
-      const float2 t2 = reinterpret_cast<const float2*>(p.temps)[hs];
-      const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
-      val = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
-                                                p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
-    }
-    s_val[tid] = val;  // 0 for houses that are not sampled
-    if (v == 0) MDR_CTA_STAMP(5);
-    house_sync(T);
-    if (v == 0) MDR_CTA_STAMP(6);
-    // per-env sum by the env's first 32 threads (one warp when N >= 32; the fp32 mode's tolerance does not need the
-    // reference's id order here -- the fp64 kernels keep it)
-    if (due && li < 32) {
-      double part = 0.0;
-      for (int i = li; i < nsamp; i += 32) part += s_val[le * N + i];
-      s_val[T + le * 32 + li] = part;
+      __threadfence();  // (acquire side of the publisher's fence)
+      *s_take = got;
     }
     house_sync(T);
-    if (due && li == 0) {
-      double base = 0.0;
-      const int np = nsamp < 32 ? nsamp : 32;
-      for (int i = 0; i < np; ++i) base += s_val[T + le * 32 + i];
-      if (N > nb) base = mul_rn(base, (double)N / (double)nb);
-      const Calendar cal = calendar_time((uint32_t)p.t_epoch[e]);
-      const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
-      const double sig_noise = p.base_power[e];  // parked by the prologue
-      const double sig = grid_signal(p, base, time_sec, sig_noise, p.artificial_ratio[e], p.max_power[e]);
-      p.base_power[e] = base;
-      p.time_since_interp[e] = 0;
-      p.signal[e] = sig;
-      s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
-      // the tile loop left the signal-dependent accumulators of a due env to this pass (its signal was not final)
-      if (p.metrics != nullptr) metrics_signal_terms(p.metrics + (size_t)e * MDR_N_METRICS, sig, p.cluster_power[e]);
+    const int tile = *s_take;
+    if (tile < 0) break;
+    pipe_refresh_tile(p, tile, le, li);
+    house_sync(T);  // s_take is rewritten by thread 0
+  }
+  if (tid == 0) {
+    if (atomicAdd(&q->exited, 1u) == gridDim.x - 1) {  // last one out re-zeroes the header
+      q->reserved = 0; q->taken = 0; q->ctas_done = 0; q->exited = 0;
+      __threadfence();
     }
-    house_sync(T);
-    if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
-    if (v == 0) MDR_CTA_STAMP(7);
-    // (s_val / s_fsig are reused by the next due tile: its first writes come after this tile's last reads of the same
-    //  thread's entries, and its first barrier orders the rest)
   }
 }
 
@@ -606,7 +680,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();
   MDR_CTA_STAMP(2);
-  if (interp_mode && any_due) pipe_refresh_pass(p, le, li);  // CTA-uniform: every house thread read the same flags
+  // (with a shared due queue every CTA enters: it may have nothing due itself and still take tiles from the others)
+  if (interp_mode && (any_due || p.workspace != nullptr)) pipe_refresh_pass(p, le, li);  // CTA-uniform
   MDR_CTA_STAMP(3);
 }
 
