@@ -114,6 +114,7 @@ struct PipeCtl {
   // different times) a few percent of the tiles are due at EVERY step, and the deferred pass must only visit those
   int due_n;
   int due_list[kMaxDue];
+  int pub_count[2];  // warps that have fenced a due tile of even / odd position (shared due queue: early publication)
 };
 
 // The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
@@ -281,12 +282,30 @@ __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int til
   //  thread's entries, and its first barrier orders the rest)
 }
 
+// Publication of a due tile to the shared queue, one tile after it was processed (called by every house thread): once
+// every warp's bulk store of that tile has completed and its state stores are fenced, the last warp hands the tile to
+// whichever CTA is idle first -- the refresh of a due tile overlaps the rest of its owner's tile loop.
+__device__ __noinline__ void publish_due_tile(DueQueue* q, int tile, int* counter, int house_warps) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) {
+    if (atomicAdd(counter, 1) == house_warps - 1) {
+      *counter = 0;
+      __threadfence();
+      const unsigned idx = atomicAdd(&q->reserved, 1u);
+      atomicExch(&q->tiles[idx], (unsigned)tile + 1u);
+    }
+  }
+}
+
 // Deferred interpolation refresh (every interp_update_period seconds).  It runs on 1 step in 75 per env, needs fp64
 // and a 32-corner table walk per house, and would cost the tile loop registers if it sat inside it.  So the tile loop
 // treats a due env like any other (the prologue parks its perlin value and marks it), and this pass -- after the loop,
 // same launch -- evaluates the table on the houses' NEW state, re-evaluates the signal and patches observation
 // feature 9 (the only output that depends on it).
-__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li) {
+__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li, int pend_tile) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int T = p.hmax;
@@ -296,21 +315,22 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
   if ((tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   __threadfence();
   house_sync(T);  // ... and the due-tile list written by thread 0 during the tile loop is complete
-  const int n_due = ctl.due_n;
   DueQueue* q = reinterpret_cast<DueQueue*>(p.workspace);
-  if (q == nullptr || n_due > kMaxDue) {
-    // no shared queue (no workspace), or more due tiles than the list holds: this CTA refreshes its own tiles
+  if (q == nullptr) {
+    // no shared queue (no workspace): this CTA refreshes its own due tiles (listed by thread 0 during the loop; when
+    // the list overflowed, every tile of the CTA is visited)
+    const int n_due = ctl.due_n;
     const bool listed = n_due <= kMaxDue;
     const int n_visit = listed ? n_due : (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     for (int v = 0; v < n_visit; ++v)
       pipe_refresh_tile(p, listed ? ctl.due_list[v] : (int)blockIdx.x + v * (int)gridDim.x, le, li);
-    if (q == nullptr) return;
+    return;
   }
   int* s_take = &ctl.tile_due[0];  // (the ring's due flags are dead after the tile loop)
   if (tid == 0) {
-    if (n_due <= kMaxDue && n_due > 0) {
-      const unsigned base = atomicAdd(&q->reserved, (unsigned)n_due);
-      for (int i = 0; i < n_due; ++i) atomicExch(&q->tiles[base + i], (unsigned)ctl.due_list[i] + 1u);
+    if (pend_tile >= 0) {  // the CTA's last tile was due (the earlier ones were published during the loop)
+      const unsigned idx = atomicAdd(&q->reserved, 1u);
+      atomicExch(&q->tiles[idx], (unsigned)pend_tile + 1u);
     }
     __threadfence();
     atomicAdd(&q->ctas_done, 1u);
@@ -372,10 +392,12 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
     InterpGrid* g = reinterpret_cast<InterpGrid*>(smem_raw + p.off_grid);
     if (tid < MDR_INTERP_DIMS) g->interp_dims[tid] = p.interp_dims[tid];
-    if (tid < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS) (&g->interp_axes[0][0])[tid] = (&p.interp_axes[0][0])[tid];
+    for (int i = tid; i < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS; i += blockDim.x)  // (a CTA may have fewer than 120 threads)
+      (&g->interp_axes[0][0])[i] = (&p.interp_axes[0][0])[i];
   }
   if (tid == 0) {
     ctl.due_n = 0;
+    ctl.pub_count[0] = ctl.pub_count[1] = 0;
     for (int i = 0; i <= ring_mask; ++i) {
       mbar_init(&ctl.full[i], 1);
       mbar_init(&ctl.empty[i], p.house_warps);
@@ -448,6 +470,9 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   int tile = blockIdx.x;
   int cmd_next = 0;
   int any_due = 0;
+  // shared due queue (see DueQueue): a due tile is published one tile later, once its stores have landed
+  DueQueue* const due_q = interp_mode ? reinterpret_cast<DueQueue*>(p.workspace) : nullptr;
+  int pend_tile = -1;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
   MDR_CTA_STAMP(1);
   if (tile < n_tiles) {
@@ -636,9 +661,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       }
     }
     MDR_STAMP(6);
-    if (ctl.tile_due[slot]) {
+    const int due_now = interp_mode ? ctl.tile_due[slot] : 0;
+    if (due_now) {
       any_due = 1;
-      if (tid == 0) {
+      if (due_q == nullptr && tid == 0) {
         const int k = ctl.due_n;
         if (k < kMaxDue) ctl.due_list[k] = tile;
         ctl.due_n = k + 1;
@@ -672,6 +698,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
         }
       }
     }
+    if (due_q != nullptr) {
+      if (pend_tile >= 0) publish_due_tile(due_q, pend_tile, &ctl.pub_count[(it & 1) ^ 1], p.house_warps);
+      pend_tile = due_now ? tile : -1;
+    }
     // this warp is done with ring slot `slot`: let the prologue warp reuse it for tile it+ring
     __syncwarp();
     if (lane == 0) mbar_arrive(&ctl.empty[slot]);
@@ -681,7 +711,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   if (kObs && lane == 0) bulk_wait_read_all();
   MDR_CTA_STAMP(2);
   // (with a shared due queue every CTA enters: it may have nothing due itself and still take tiles from the others)
-  if (interp_mode && (any_due || p.workspace != nullptr)) pipe_refresh_pass(p, le, li);  // CTA-uniform
+  if (interp_mode && (any_due || due_q != nullptr)) pipe_refresh_pass(p, le, li, pend_tile);  // CTA-uniform
   MDR_CTA_STAMP(3);
 }
 

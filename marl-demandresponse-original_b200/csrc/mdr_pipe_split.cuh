@@ -150,7 +150,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
     InterpGrid* g = reinterpret_cast<InterpGrid*>(smem_raw + p.off_grid);
     if (tid < MDR_INTERP_DIMS) g->interp_dims[tid] = p.interp_dims[tid];
-    if (tid < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS) (&g->interp_axes[0][0])[tid] = (&p.interp_axes[0][0])[tid];
+    for (int i = tid; i < MDR_INTERP_DIMS * MDR_INTERP_MAX_AXIS; i += blockDim.x)  // (a CTA may have fewer than 120 threads)
+      (&g->interp_axes[0][0])[i] = (&p.interp_axes[0][0])[i];
   }
   if (tid == 0) {
     ctl.due_n = 0;
