@@ -105,7 +105,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
 // shared-memory control block of the pipelined kernel (at off_ctl).  The PipeEnv ring has
 // ring = 2 * pro_batch <= kMaxRing slots; slot = it % ring for the it-th tile of this CTA.
 constexpr int kMaxRing = 16;
-constexpr int kMaxDue = 12;   // (no-queue fallback only; more due tiles than this: every tile of the CTA is visited)
+constexpr int kMaxDue = 60;
 struct PipeCtl {
   uint64_t full[kMaxRing];   // prologue -> house warps: slot is ready            (count 1)
   uint64_t empty[kMaxRing];  // house warps -> prologue: slot may be overwritten   (count house_warps)
@@ -120,10 +120,10 @@ struct PipeCtl {
   // the end of the slowest CTA's loop (a refresh has ~10 us of latency).  order[it] = position in the static walk.
   int use_order;
   uint64_t order_ready;  // mbarrier: the prologue warp has written order[]
-  unsigned char order[64];
-  unsigned char order_flag[64];
+  unsigned char order[256];
+  unsigned char order_flag[256];
 };
-constexpr int kMaxLocal = 64;  // (a CTA with more tiles keeps the static order; shared memory is what limits 3 CTAs/SM)
+constexpr int kMaxLocal = 256;
 
 // The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
 // groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  The deeper the
