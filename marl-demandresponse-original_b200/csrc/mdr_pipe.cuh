@@ -115,15 +115,7 @@ struct PipeCtl {
   int due_n;
   int due_list[kMaxDue];
   int pub_count[2];  // warps that have fenced a due tile of even / odd position (shared due queue: early publication)
-  // Order in which this CTA walks its tiles (shared due queue only): tiles with a refresh due FIRST, so that they are
-  // published early in the launch and refreshed by the CTAs that finish their loops first, instead of surfacing near
-  // the end of the slowest CTA's loop (a refresh has ~10 us of latency).  order[it] = position in the static walk.
-  int use_order;
-  uint64_t order_ready;  // mbarrier: the prologue warp has written order[]
-  unsigned char order[256];
-  unsigned char order_flag[256];
 };
-constexpr int kMaxLocal = 256;
 
 // The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
 // groups (one per tile), each group into lane sets of `pro_lanes` lanes per env.  The deeper the
@@ -146,9 +138,8 @@ __device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B
   const int my_k = lane / lanes_per_tile;  // which tile of the pass this lane works for
   const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
   const int it = it0 + my_k;
-  const int n_local = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
-  const bool tile_valid = it < n_local;
-  const int tile = blockIdx.x + (ctl.use_order && tile_valid ? (int)ctl.order[it] : it) * gridDim.x;
+  const int tile = blockIdx.x + it * gridDim.x;
+  const bool tile_valid = tile < p.n_tiles;
   const int slot = it & (ring - 1);
   MDR_STAMP_AT(7, it0, 8);
   // the house warps must have released the pass's ring slots.  Warp-uniform loop over the B barriers:
@@ -156,7 +147,7 @@ __device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B
   // up to 8 us late (tools/trace_tile.py)
   for (int k = 0; k < B; ++k) {
     const int itk = it0 + k;
-    if (itk < n_local && (itk >> ring_shift) >= 1)
+    if (blockIdx.x + itk * gridDim.x < p.n_tiles && (itk >> ring_shift) >= 1)
       mbar_wait(&ctl.empty[itk & (ring - 1)], (((itk >> ring_shift) & 1) ^ 1));
   }
   MDR_STAMP_AT(7, it0, 0);
@@ -396,8 +387,6 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
   const int ring_mask = 2 * p.pro_batch - 1;
   const int ring_shift = 31 - __clz(ring_mask + 1);
-  const int n_local = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
-  const int use_order = p.base_power_mode == MDR_BASE_INTERPOLATION && p.workspace != nullptr && n_local <= kMaxLocal && n_local > 1;
   MDR_CTA_STAMP(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
   if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
@@ -409,8 +398,6 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   if (tid == 0) {
     ctl.due_n = 0;
     ctl.pub_count[0] = ctl.pub_count[1] = 0;
-    ctl.use_order = use_order;
-    mbar_init(&ctl.order_ready, 1);
     for (int i = 0; i <= ring_mask; ++i) {
       mbar_init(&ctl.full[i], 1);
       mbar_init(&ctl.empty[i], p.house_warps);
@@ -420,31 +407,11 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   __syncthreads();
   if (warp >= p.house_warps) {
     asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
-    if (use_order) {
-      // due tiles first (see PipeCtl::order): a tile is due when any of its envs reaches the refresh period at this step
-      for (int c = 0; c < n_local; c += 32) {
-        const int itl = c + lane;
-        int due = 0;
-        if (itl < n_local) {
-          const int e0 = ((int)blockIdx.x + itl * (int)gridDim.x) * p.G;
-          for (int g = 0; g < p.G && e0 + g < p.E; ++g) due |= p.time_since_interp[e0 + g] + p.dt >= p.interp_update_period;
-          ctl.order_flag[itl] = (unsigned char)due;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        int k = 0;
-        for (int i = 0; i < n_local; ++i) if (ctl.order_flag[i]) ctl.order[k++] = (unsigned char)i;
-        for (int i = 0; i < n_local; ++i) if (!ctl.order_flag[i]) ctl.order[k++] = (unsigned char)i;
-        mbar_arrive(&ctl.order_ready);
-      }
-      __syncwarp();
-    }
     // tiles per pass: pro_batch, but not more than this launch gives a CTA (a small problem should spend its lanes
     // on the envs of tiles that exist, not on absent ones)
     int B = p.pro_batch;
     while (B > 1 && (B >> 1) * (int)gridDim.x >= p.n_tiles) B >>= 1;
-    for (int it0 = 0; it0 < n_local; it0 += B) prologue_pass(p, it0, B);
+    for (int it0 = 0; blockIdx.x + it0 * gridDim.x < p.n_tiles; it0 += B) prologue_pass(p, it0, B);
     return;
   }
 
@@ -500,7 +467,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     return 0;
   };
 
-  auto tile_at = [&](int it) { return (int)blockIdx.x + (use_order ? (int)ctl.order[it] : it) * tile_stride; };
+  int tile = blockIdx.x;
   int cmd_next = 0;
   int any_due = 0;
   // shared due queue (see DueQueue): a due tile is published one tile later, once its stores have landed
@@ -508,16 +475,13 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   int pend_tile = -1;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
   MDR_CTA_STAMP(1);
-  if (use_order) mbar_wait(&ctl.order_ready, 0);
-  int tile = tile_at(0);
-  {
+  if (tile < n_tiles) {
     issue_tile(tile, 0);
     cmd_next = fetch_action(tile);
   }
   cp_async_commit();
 
-  for (int it = 0; it < n_local; ++it) {
-    if (it > 0) tile = tile_at(it);
+  for (int it = 0; tile < n_tiles; ++it, tile += tile_stride) {
     const int sbuf = it & 1;
     const int H = tile_houses(tile);
     const bool active = tid < H;
@@ -525,8 +489,8 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const int e = tile * G + le;
     MDR_STAMP(0);
     int cmd = cmd_next;
-    if (it + 1 < n_local) {
-      const int next = tile_at(it + 1);
+    const int next = tile + tile_stride;
+    if (next < n_tiles) {
       issue_tile(next, sbuf ^ 1);
       cmd_next = fetch_action(next);
     }

@@ -155,7 +155,6 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
   }
   if (tid == 0) {
     ctl.due_n = 0;
-    ctl.use_order = 0;
     for (int i = 0; i <= ring_mask; ++i) {
       mbar_init(&ctl.full[i], 1);
       mbar_init(&ctl.empty[i], p.house_warps);
