@@ -73,7 +73,8 @@ def config_block(args, w):
     obs = w["obs"]
     return {"workload": args.workload + ": " + w["desc"], "envs_per_gpu": args.envs or w["envs"], "houses_per_env": w["houses"],
             "obs_features": 51 if obs else 0, "precision": args.precision,
-            "base_power": "interpolation (synthetic table, refresh every 75 steps, staggered clocks)" if w["interp"] else "constant",
+            "base_power": ("interpolation (synthetic table, refresh every 75 steps, %s clocks)"
+                           % ("in-phase" if getattr(args, "in_phase", False) else "staggered")) if w["interp"] else "constant",
             "actions": ("seeded Actor(51,2,[100,100]) on device" if w.get("actor") else
                         "python bang-bang per house" if w.get("dict_api") else
                         "uint8 [E,N] tensors" if w["action_source"] == "array" else w["action_source"])}
@@ -260,7 +261,7 @@ def gpu_arm(args):
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision=args.precision, device=dev, seed=1234 + rank,
                                         interp_table=table, action_source=w["action_source"], with_obs=w["obs"])
     env.reset_tensor()
-    if w["interp"]:
+    if w["interp"] and not args.in_phase:
         env.stagger_interp_clock(seed=77 + rank)  # rollouts restart clusters at different times: refreshes are spread out
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     ring = [(torch.rand(E, N, device=dev, generator=gen) < 0.5).to(torch.uint8) for _ in range(8)]
@@ -493,6 +494,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3000,
                     help="env steps per CPU-baseline process (default: ~3 s per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--in-phase", action="store_true", help="keep every cluster's interpolation clock in phase (all refresh on the "
+                    "same step, once per 75 steps) instead of staggering them (round-1 behaviour, for comparison)")
     ap.add_argument("--serial-e2e", action="store_true", help="e2e leg without the MdrHostCtx pipeline (one H2D, one launch, four D2H)")
     args = ap.parse_args()
     if args.warmup < 3:
