@@ -10,7 +10,9 @@ SOURCES = ("mdr_kernels.cu", "mdr_abi.cu", "mdr_host.cu")
 HEADERS = ("mdr_kernels.h", "mdr_device.cuh", "mdr_pipe.cuh", "mdr_pipe_split.cuh", "mdr_pipe_split_host.cuh", "mdr_fused.cuh", "mdr_populate.cuh", "mdr_big.cuh", "mdr_rollout.cuh", "mdr_compact.cuh", "mdr_expand.h",
            os.path.join("..", "..", "include", "mdr_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "--split-compile", "0"]  # split-compile: the many kernel instantiations in parallel
+              "-Xcompiler", "-fPIC"]
+# (`--split-compile 0` builds 2.5x faster but measurably slower code: the fused kernel 13.6 vs 10.7 us per step, the
+#  no-observation pipelined kernel 21.2 vs 18.9 us -- A/B on the same box, tools/ab_libs.sh; MDR_NVCC_EXTRA for dev builds)
 
 
 class NvccMissing(RuntimeError):
