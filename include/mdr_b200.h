@@ -141,7 +141,8 @@ enum {
   MDR_FLAG_NO_PIPELINE = 1, /* never take the persistent pipelined kernel (generic kernel instead) */
   MDR_FLAG_NO_FUSED = 2,    /* never take the fused multi-step kernel (one launch per step instead) */
   MDR_FLAG_NO_PDL = 4,      /* launch without programmatic dependent launch */
-  MDR_FLAG_NO_CLUSTER = 8   /* never split an env of 225..1024 houses over a thread-block cluster (one CTA per env) */
+  MDR_FLAG_NO_CLUSTER = 8,  /* never split an env of 225..1024 houses over a thread-block cluster (one CTA per env) */
+  MDR_FLAG_STATIC_TILES = 16 /* pipelined kernel: every CTA walks a fixed, strided list of tiles (no in-order claiming) */
 };
 
 /* Per-house struct-of-arrays.  Packed vectors keep every access a coalesced 8/16-byte load. */
@@ -246,11 +247,16 @@ const char *mdr_last_cuda_error(void);
 /* F of utils.normStateDict (utils.py:740-880) for these flags; negative MdrStatus on error. */
 int mdr_obs_width(const MdrConfig *cfg);
 
-/* Device scratch a step of this configuration uses in MdrEnvs.workspace (zero it once after allocating; the kernels
-   leave it zeroed): for envs larger than a thread-block cluster can hold (n_houses > MDR_MAX_HOUSES_PER_CLUSTER) the
-   per-env records and per-CTA totals of the three-launch path (required there); with interpolated base power the
-   queue through which the CTAs of the pipelined kernel share the tiles whose refresh is due (optional: without it
-   every CTA refreshes its own tiles, which costs tens of microseconds of tail when refresh clocks are staggered). */
+/* Device scratch a step of this configuration uses in MdrEnvs.workspace (zero it ONCE after allocating; the kernels
+   keep it consistent from launch to launch, and it must not be shared by launches that can run concurrently):
+   - envs larger than a thread-block cluster can hold (n_houses > MDR_MAX_HOUSES_PER_CLUSTER): the per-env records
+     and per-CTA totals of the three-launch path (required there);
+   - the persistent pipelined kernel (optional; NULL = every CTA walks a fixed list of tiles and refreshes its own due
+     tiles): the hand-over records of the per-env prologue, a ready flag per tile and the counter from which the CTAs
+     claim their tiles in address order, and -- with interpolated base power -- the queue through which the CTAs
+     share the tiles whose table refresh is due.  Sized for two launches in flight (mdr_step_host's two streams).
+     In this mode the CTAs of one launch depend on each other and must be co-resident: the grid never exceeds
+     SMs x resident CTAs, so do not run it next to other kernels that hold SMs indefinitely. */
 int mdr_workspace_bytes(const MdrConfig *cfg, size_t *bytes);
 
 /* Validates cfg (modes, shapes) the way the reference constructors raise ValueError

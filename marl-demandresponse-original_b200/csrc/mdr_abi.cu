@@ -94,11 +94,11 @@ extern "C" int mdr_workspace_bytes(const MdrConfig* cfg, size_t* bytes) {
   if (!cfg || !bytes) return MDR_ERR_NULL;
   int st = mdr_validate(cfg);
   if (st != MDR_OK) return st;
-  // big path: per-env records + per-CTA totals; pipelined kernel with interpolated base power: the due-tile queue of a
-  // launch (64-byte header + one word per tile), twice (the host-buffer pipeline runs two slices concurrently)
+  // big path: per-env records + per-CTA totals; pipelined kernels: due-tile queue + in-order tile claiming area of a
+  // launch (pipe_ws_bytes), twice (the host-buffer pipeline runs two slices concurrently)
   size_t need = needs_big_path(cfg) ? mdr::big_workspace(cfg->n_envs, cfg->n_houses) : 0;
-  if (cfg->base_power_mode == MDR_BASE_INTERPOLATION && !needs_big_path(cfg)) {
-    const size_t q = 2 * (size_t)mdr::due_queue_bytes(cfg->n_envs);
+  if (!needs_big_path(cfg)) {
+    const size_t q = 2 * (size_t)mdr::pipe_ws_bytes(cfg->n_envs);
     if (q > need) need = q;
   }
   *bytes = need;
@@ -233,6 +233,8 @@ static int choose_geometry(const MdrConfig* c, bool has_obs, Geometry* g, bool n
   g->l2_hit_ratio = (float)(c->l2_hit_ratio > 0.0 && c->l2_hit_ratio <= 1.0 ? c->l2_hit_ratio : 1.0);
   g->max_ctas = c->max_ctas > 0 ? c->max_ctas : 0;
   g->no_pdl = (c->flags & MDR_FLAG_NO_PDL) != 0;
+  static const bool env_static_tiles = [] { const char* s = getenv("MDR_STATIC_TILES"); return s && atoi(s) != 0; }();  // A/B runs
+  g->static_tiles = (c->flags & MDR_FLAG_STATIC_TILES) != 0 || env_static_tiles;
   if (rb == MDR_F32 && extra && threads <= 256 && rpp == 32 && !split) {
     g->pro_batch = mdr::pipe_pro_batch(G, has_obs);
     const size_t ps = mdr::pipe_smem_layout(nullptr, house_threads, G, N, F, need_val, has_obs, c->n_comm, part_stride, g->pro_batch);
@@ -440,7 +442,7 @@ extern "C" int mdr_precompute(const MdrConfig* cfg, const MdrHouses* houses, voi
 }
 
 static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnvs* envs, const MdrStepInputs* in,
-                     const MdrOutputs* out, int n_steps, int is_reset, cudaStream_t stream, int env_base = 0) {
+                     const MdrOutputs* out, int n_steps, int is_reset, cudaStream_t stream, int env_base = 0, int ws_envs = 0) {
   int st = mdr_validate(cfg);
   if (st != MDR_OK) return st;
   if (n_steps < 1) return MDR_ERR_SHAPE;
@@ -514,6 +516,11 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     // the due queue needs its full size; a caller that passes less scratch (or none) gets the per-CTA refresh
     if (k.workspace && !aligned16(k.workspace)) return MDR_ERR_ALIGN;
     k.pro_batch = g.pro_batch;
+    // in-order tile claiming needs the scratch area; without it (or on request) every CTA walks a fixed tile list
+    // (the layout follows the n_envs the workspace was sized for: slices of the host pipeline share it with whole steps)
+    const int cap = ws_envs > 0 ? ws_envs : cfg->n_envs;
+    k.dyn_off = (k.workspace && !g.static_tiles) ? (int)mdr::due_queue_bytes(cap) : 0;
+    k.dyn_rec_off = k.dyn_off + 64 + (int)mdr::dyn_flags_bytes(cap);
     int L = 16;  // lanes per env within one tile's lane group
     while (L > 1 && L * g.envs_per_cta * g.pro_batch > 32) L >>= 1;
     k.pro_lanes = L;
@@ -565,8 +572,8 @@ namespace mdr {
 // entry points of the host-buffer pipeline (mdr_host.cu): one step / the compact observation record of a slice of the
 // env axis (`env_base` keeps the Philox keys those of the whole shard)
 int run_steps_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, const MdrStepInputs* in, const MdrOutputs* out,
-                    int env_base, cudaStream_t stream) {
-  return run_steps(cfg, h, e, in, out, 1, 0, stream, env_base);
+                    int env_base, int ws_envs, cudaStream_t stream) {
+  return run_steps(cfg, h, e, in, out, 1, 0, stream, env_base, ws_envs);
 }
 int compact_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, void* out, cudaStream_t stream) {
   KernelParams k;

@@ -141,7 +141,7 @@ int host_pipeline_step(MdrHostCtx* ctx, const MdrConfig* cfg, const MdrHouses* h
     es.perlin_seed = (const double*)off(e->perlin_seed, (size_t)e0 * 8);
     es.metrics = (double*)off(e->metrics, (size_t)e0 * MDR_N_METRICS * 8);
     // two slices are in flight at a time: each parity has its own due-tile queue in the workspace
-    es.workspace = off(e->workspace, (size_t)(s & 1) * due_queue_bytes(cfg->n_envs));
+    es.workspace = off(e->workspace, (size_t)(s & 1) * pipe_ws_bytes(cfg->n_envs));
     MdrStepInputs is = *in;
     is.actions = (const uint8_t*)off(in->actions, h0);
     is.od_noise = (const double*)off(in->od_noise, (size_t)e0 * 8);
@@ -154,7 +154,7 @@ int host_pipeline_step(MdrHostCtx* ctx, const MdrConfig* cfg, const MdrHouses* h
       if (!in->actions) return MDR_ERR_NULL;
       CK(cudaMemcpyAsync(const_cast<uint8_t*>(is.actions), host_actions + h0, (size_t)ne * N, cudaMemcpyHostToDevice, st));
     }
-    int status = run_steps_slice(&c, &hs, &es, &is, &os, e0, st);
+    int status = run_steps_slice(&c, &hs, &es, &is, &os, e0, cfg->n_envs, st);
     if (status != MDR_OK) return status;
     void* dcomp = off(ctx->d_compact, h0 * 16 * rb);
     status = compact_slice(&c, &hs, &es, dcomp, st);

@@ -24,6 +24,7 @@ struct KernelParams {
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
   int off_grid;                                               // pipelined kernels: shared-memory copy of the interpolation grid
   int cl, cl_slice, off_cl;                                   // env split over a cluster of `cl` CTAs, `cl_slice` houses each; ClusterTot offset
+  int dyn_off, dyn_rec_off;                                   // pipelined kernel: byte offsets of the tile-claim header (0 = static tiles) and of the records in `workspace`
   unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)
   int is_reset, comm_mode, state_flags, msg_flags, temp_penalty_mode, solar, base_power_mode, signal_mode;
   int n_sinusoids, interp_update_period, interp_nb_agents, perlin_nb_octaves, perlin_octaves_step, action_source;
@@ -78,6 +79,7 @@ struct Geometry {
   int cluster, cluster_slice;  // one env split over `cluster` CTAs (thread-block cluster) of `cluster_slice` houses; 1 = whole envs per CTA
   int max_ctas;  // cap on the persistent pipelined grid (0 = SMs x resident CTAs)
   bool no_pdl;   // MDR_FLAG_NO_PDL
+  bool static_tiles;  // MDR_FLAG_STATIC_TILES
 };
 
 size_t step_smem_layout(KernelParams* kp, int real_bytes, int hmax, int genvs, int nwarps, int rows_per_pass,
@@ -99,6 +101,10 @@ bool fused_eligible(const KernelParams& kp);
 cudaError_t launch_big(const KernelParams& kp, int precision, void* workspace, cudaStream_t stream);
 size_t big_workspace(int n_envs, int n_houses);
 inline size_t due_queue_bytes(int n_envs) { return (64 + 4 * (size_t)n_envs + 63) & ~(size_t)63; }  // header + a word per tile
+// Scratch of ONE pipelined launch in MdrEnvs.workspace: [due-tile queue | claim header (64 B) | a flag word per tile |
+// a 64-byte hand-over record per env] (mdr_pipe.cuh: DueQueue, DynHdr).  Two launches may be in flight (host pipeline).
+inline size_t dyn_flags_bytes(int n_envs) { return (4 * (size_t)n_envs + 63) & ~(size_t)63; }
+inline size_t pipe_ws_bytes(int n_envs) { return due_queue_bytes(n_envs) + 64 + dyn_flags_bytes(n_envs) + 64 * (size_t)n_envs; }
 cudaError_t launch_compact_obs(const KernelParams& kp, int precision, void* out, cudaStream_t stream);
 cudaError_t launch_sample_actions(const float* probs, long long n_rows, int n_actions, uint64_t seed, uint64_t draw_index,
                                   const uint64_t* draw_counter, uint8_t* actions, float* chosen_prob, cudaStream_t stream);
@@ -112,7 +118,7 @@ int host_pipeline_step(MdrHostCtx* ctx, const MdrConfig* cfg, const MdrHouses* h
                        const MdrOutputs* out, const uint8_t* host_actions, void* host_obs, void* host_reward,
                        double* host_power, double* host_signal, cudaStream_t user_stream, int (*fail)(cudaError_t));
 int run_steps_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, const MdrStepInputs* in, const MdrOutputs* out,
-                    int env_base, cudaStream_t stream);
+                    int env_base, int ws_envs, cudaStream_t stream);  // ws_envs: n_envs the workspace was sized (and laid out) for
 int compact_slice(const MdrConfig* cfg, const MdrHouses* h, const MdrEnvs* e, void* out, cudaStream_t stream);
 
 }  // namespace mdr

@@ -102,6 +102,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, int parity) {
       : "memory");
 }
 
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // shared-memory control block of the pipelined kernel (at off_ctl).  The PipeEnv ring has
 // ring = 2 * pro_batch <= kMaxRing slots; slot = it % ring for the it-th tile of this CTA.
 constexpr int kMaxRing = 16;
@@ -115,6 +121,8 @@ struct PipeCtl {
   int due_n;
   int due_list[kMaxDue];
   int pub_count[2];  // warps that have fenced a due tile of even / odd position (shared due queue: early publication)
+  int claim[2];      // in-order tile claiming: the tile thread 0 claimed for position it + 2 (even / odd it)
+  int n_due;         // ... and the launch's number of due tiles (copied from the queue header by thread 0)
 };
 
 // The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
@@ -171,6 +179,104 @@ __device__ __noinline__ void prologue_pass(const KernelParams& p, int it0, int B
   MDR_STAMP_AT(7, it0, 7);
 }
 
+// Queue of tiles with an interpolation refresh due, shared by ALL CTAs of a launch (in MdrEnvs.workspace, zeroed by its
+// owner once; the kernel leaves it zeroed).  With staggered refresh clocks a few percent of the tiles are due at every
+// step: a CTA that refreshed its own due tiles after its tile loop would hold the whole launch back by 10+ us per
+// tile (measured: 30-40 us of tail on 16 384 x 100), so every CTA publishes its due tiles here and then takes tiles
+// from the queue until it is empty -- the refresh work of a step is spread over the whole grid.
+struct DueQueue {
+  unsigned reserved;   // slots handed out to publishers
+  unsigned taken;      // slots claimed by consumers
+  unsigned ctas_done;  // CTAs that have published everything they have
+  unsigned exited;     // CTAs that are done with the queue (the last one re-zeroes the header)
+  unsigned n_due;      // in-order claiming: due tiles of this launch, counted by env_pro_kernel before the step kernel starts
+  unsigned pad[11];
+  unsigned tiles[1];   // [n_tiles] tile index + 1, 0 = empty
+};
+
+// ----------------------------------------------------------------------------------------
+// In-order tile claiming (KernelParams.dyn_off != 0).  With a fixed, strided tile list per CTA the CTAs of a launch
+// drift apart (per-CTA trace of 16 384 x 100: tile loops end between 67 and 84 us) -- the launch waits for the slowest
+// one, and the drifting write front costs DRAM locality (tools/microbench/write_patterns_bw.cu: 5.85 TB/s against
+// 6.85 TB/s for tiles claimed in address order).  Claiming needs the per-env record of a tile that nobody planned to
+// process in this CTA, so the hand-over leaves shared memory:
+//   * a small kernel in front of the step kernel (env_pro_kernel, one warp per tile, the same env_prologue code)
+//     writes the 64-byte records of ALL envs into a global (L2-resident) array and a `due` word per tile;
+//   * the house warps take tiles blockIdx, blockIdx + grid, then whatever an atomic counter hands out (claimed two
+//     tiles ahead by thread 0), and a few loader threads fetch the tile's records next to the cp.async input stage
+//     of the NEXT tile (cp.async + mbarrier complete, 4-slot ring).
+// Both kernels carry the programmatic-dependent-launch attribute; each one's griddepcontrol.wait covers everything
+// before it in the stream.  Measured alternatives, not kept: the records produced by the step kernel's own prologue
+// warps with a ready flag per tile -- every global round trip the house warps depend on (flag, then record) needs a
+// whole tile of slack under the observation write stream (loaded L2 latency 1-2 us), the first wave starts 3 us later
+// than through shared memory, and the CTAs of a launch then depend on each other (co-residency).
+// ----------------------------------------------------------------------------------------
+struct DynHdr {
+  unsigned next_tile;  // tiles handed out beyond the first two of every CTA (zeroed by env_pro_kernel)
+  unsigned pad[15];
+};
+static_assert(sizeof(DynHdr) == 64, "DynHdr must stay 64 bytes");
+
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ DynHdr* dyn_hdr(const KernelParams& p) {
+  return reinterpret_cast<DynHdr*>(reinterpret_cast<unsigned char*>(p.workspace) + p.dyn_off);
+}
+__device__ __forceinline__ unsigned* dyn_due(const KernelParams& p) { return reinterpret_cast<unsigned*>(dyn_hdr(p) + 1); }
+__device__ __forceinline__ PipeEnv* dyn_recs(const KernelParams& p) {
+  return reinterpret_cast<PipeEnv*>(reinterpret_cast<unsigned char*>(p.workspace) + p.dyn_rec_off);
+}
+
+// Per-env prologue of a whole step, one warp per tile: records into the global array, per-env outputs in place (as
+// the in-kernel prologue warp does), one `due` word per tile.
+__global__ void __launch_bounds__(128) env_pro_kernel(const __grid_constant__ KernelParams p) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int lane = threadIdx.x & 31;
+  // B tiles per warp (pro_batch, a power of two with B * G <= 32), L lanes per env: the grid stays within one wave
+  // (16 384 x 100: 512 CTAs; one warp per tile was 2 048 CTAs in 2.3 waves, 12 us instead of 6)
+  const int B = p.pro_batch;
+  const int lanes_per_tile = 32 / B;
+  int L = 16;
+  while (L > 1 && L * p.G > lanes_per_tile) L >>= 1;
+  const int groups = lanes_per_tile / L;  // envs of a tile processed at once
+  const int tlane = lane & (lanes_per_tile - 1);
+  const int sub = tlane & (L - 1), grp = tlane / L;
+  const int my_k = lane / lanes_per_tile;
+  const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
+  const int tile = (blockIdx.x * 4 + (threadIdx.x >> 5)) * B + my_k;
+  const bool tile_valid = tile < p.n_tiles;
+  const int tile_c = tile_valid ? tile : 0;  // lanes of an absent tile compute but never write
+  const int env0 = tile_c * p.G;
+  const int genvs = min(p.G, p.E - env0);
+  PipeEnv* const recs = dyn_recs(p);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous step wrote is visible from here on
+  if (blockIdx.x == 0 && threadIdx.x == 0) dyn_hdr(p)->next_tile = 0;
+  EnvScratch unused;
+  int my_due = 0;
+  for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count
+    const int le2 = first + grp;
+    const bool valid = tile_valid && le2 < genvs;
+    const int lec = le2 < genvs ? le2 : genvs - 1;
+    PipeEnv rec;
+    my_due |= env_prologue<true>(p, unused, rec, env0 + lec, sub, L, valid, false, false);
+    if (valid && sub == 0) {
+      uint4* dst = reinterpret_cast<uint4*>(recs + env0 + lec);
+      const uint4* src = reinterpret_cast<const uint4*>(&rec);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) __stcg(dst + i, src[i]);
+    }
+  }
+  const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
+  if (tile_valid && tlane == 0) {
+    const bool due = (due_ballot & group_mask) != 0;
+    __stcg(dyn_due(p) + tile, due ? 1u : 0u);
+    // the step kernel knows how many due tiles to expect: a launch without any skips the refresh pass, and nobody has to
+    // wait for the slowest CTA to learn that the queue is complete
+    if (due) atomicAdd(&reinterpret_cast<DueQueue*>(p.workspace)->n_due, 1u);
+  }
+}
+
 // Deferred interpolation refresh (every interp_update_period seconds; PowerGrid.step :1250-1255,
 // interpolatePower :1195-1234).  It runs on 1 step in 75, needs fp64 and a 32-corner table walk per
 // house, and would cost the tile loop registers if it sat inside it.  So the tile loop treats a due
@@ -186,25 +292,6 @@ __device__ __forceinline__ void metrics_signal_terms(double* m, double sig, doub
   __stcg(m + MDR_M_SUM_SQ_SIGNAL_ERROR, __ldcg(m + MDR_M_SUM_SQ_SIGNAL_ERROR) + d * d);
 }
 
-// Queue of tiles with an interpolation refresh due, shared by ALL CTAs of a launch (in MdrEnvs.workspace, zeroed by its
-// owner once; the kernel leaves it zeroed).  With staggered refresh clocks a few percent of the tiles are due at every
-// step: a CTA that refreshed its own due tiles after its tile loop would hold the whole launch back by 10+ us per
-// tile (measured: 30-40 us of tail on 16 384 x 100), so every CTA publishes its due tiles here and then takes tiles
-// from the queue until it is empty -- the refresh work of a step is spread over the whole grid.
-struct DueQueue {
-  unsigned reserved;   // slots handed out to publishers
-  unsigned taken;      // slots claimed by consumers
-  unsigned ctas_done;  // CTAs that have published everything they have
-  unsigned exited;     // CTAs that are done with the queue (the last one re-zeroes the header)
-  unsigned pad[12];
-  unsigned tiles[1];   // [n_tiles] tile index + 1, 0 = empty
-};
-
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // refresh of ONE due tile (all house threads of the CTA): table walk on the houses' NEW state, base power, signal,
 // observation feature 9 (PowerGrid.step :1250-1255, interpolatePower :1195-1234)
@@ -305,7 +392,7 @@ __device__ __noinline__ void publish_due_tile(DueQueue* q, int tile, int* counte
 // treats a due env like any other (the prologue parks its perlin value and marks it), and this pass -- after the loop,
 // same launch -- evaluates the table on the houses' NEW state, re-evaluates the signal and patches observation
 // feature 9 (the only output that depends on it).
-__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li, int pend_tile) {
+__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li, int pend_tile, int n_due) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int T = p.hmax;
@@ -333,21 +420,23 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       atomicExch(&q->tiles[idx], (unsigned)pend_tile + 1u);
     }
     __threadfence();
-    atomicAdd(&q->ctas_done, 1u);
+    if (n_due < 0) atomicAdd(&q->ctas_done, 1u);
   }
   for (;;) {
     if (tid == 0) {
       const unsigned idx = atomicAdd(&q->taken, 1u);
       int got = -1;
       unsigned long long t0 = 0;
-      for (unsigned spin = 0;; ++spin) {
+      // (n_due >= 0: the launch's number of due tiles is known -- every slot below it WILL be published, and a CTA that
+      //  draws a slot beyond it leaves at once instead of waiting for the slowest CTA's "nothing more to publish")
+      for (unsigned spin = 0; n_due < 0 || idx < (unsigned)n_due; ++spin) {
         const unsigned v = ld_volatile_u32(&q->tiles[idx]);
         if (v != 0) {
           q->tiles[idx] = 0;  // leave the queue zeroed for the next launch
           got = (int)v - 1;
           break;
         }
-        if (ld_volatile_u32(&q->ctas_done) == gridDim.x) {  // every publisher is done: reserved is final
+        if (n_due < 0 && ld_volatile_u32(&q->ctas_done) == gridDim.x) {  // every publisher is done: reserved is final
           if (idx >= ld_volatile_u32(&q->reserved)) break;
           continue;  // the slot was written before its publisher counted itself done: re-read it
         }
@@ -369,7 +458,7 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
   }
   if (tid == 0) {
     if (atomicAdd(&q->exited, 1u) == gridDim.x - 1) {  // last one out re-zeroes the header
-      q->reserved = 0; q->taken = 0; q->ctas_done = 0; q->exited = 0;
+      q->reserved = 0; q->taken = 0; q->ctas_done = 0; q->exited = 0; q->n_due = 0;
       __threadfence();
     }
   }
@@ -385,8 +474,10 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
-  const int ring_mask = 2 * p.pro_batch - 1;
+  const bool dyn = p.dyn_off != 0;  // in-order tile claiming (see DynHdr): 4-slot record ring filled by loader threads
+  const int ring_mask = dyn ? 3 : 2 * p.pro_batch - 1;
   const int ring_shift = 31 - __clz(ring_mask + 1);
+  const int nload = min(p.hmax, 4 * p.G);  // loader threads: one 16-byte chunk of the tile's records each (or more)
   MDR_CTA_STAMP(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
   if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
@@ -399,13 +490,14 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     ctl.due_n = 0;
     ctl.pub_count[0] = ctl.pub_count[1] = 0;
     for (int i = 0; i <= ring_mask; ++i) {
-      mbar_init(&ctl.full[i], 1);
+      mbar_init(&ctl.full[i], dyn ? nload : 1);
       mbar_init(&ctl.empty[i], p.house_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (warp >= p.house_warps) {
+    if (dyn) return;  // (the records were produced by env_pro_kernel)
     asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
     // tiles per pass: pro_batch, but not more than this launch gives a CTA (a small problem should spend its lanes
     // on the envs of tiles that exist, not on absent ones)
@@ -468,14 +560,32 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   };
 
   int tile = blockIdx.x;
+  int tile_nxt = blockIdx.x + gridDim.x;  // (in-order claiming: the first two tiles of a CTA are fixed)
   int cmd_next = 0;
   int any_due = 0;
+  unsigned claimed = 0;  // thread 0: tiles handed out before its latest claim
   // shared due queue (see DueQueue): a due tile is published one tile later, once its stores have landed
   DueQueue* const due_q = interp_mode ? reinterpret_cast<DueQueue*>(p.workspace) : nullptr;
   int pend_tile = -1;
   asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
   MDR_CTA_STAMP(1);
+  // the records of tile t (and its `due` word) into ring slot `rslot`: a few loader threads copy, the slot's mbarrier
+  // completes with the copies
+  auto issue_records = [&](int t, int rslot) {
+    const int nl = min(p.hmax, 4 * p.G);
+    if (tid < nl) {
+      if (tid == 0) cp_async_4(&ctl.tile_due[rslot], dyn_due(p) + t);
+      const int nchunks = 4 * min(p.G, p.E - t * p.G);
+      unsigned char* dst = smem_raw + p.off_env + rslot * p.G * (int)sizeof(PipeEnv);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(dyn_recs(p) + (size_t)t * p.G);
+      for (int c = tid; c < nchunks; c += nl) cp_async_16(dst + c * 16, src + c * 16);
+      cp_async_mbar_arrive_noinc(&ctl.full[rslot]);
+    }
+  };
+  // (thread 0's first record copies complete after this one: ctl.n_due is visible to everybody behind the first full[])
+  if (dyn && interp_mode && tid == 0) cp_async_4(&ctl.n_due, &reinterpret_cast<DueQueue*>(p.workspace)->n_due);
   if (tile < n_tiles) {
+    if (dyn) issue_records(tile, 0);
     issue_tile(tile, 0);
     cmd_next = fetch_action(tile);
   }
@@ -489,8 +599,11 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const int e = tile * G + le;
     MDR_STAMP(0);
     int cmd = cmd_next;
-    const int next = tile + tile_stride;
+    const int next = dyn ? tile_nxt : tile + tile_stride;
+    // (claim for position it + 2: issued now, needed before this tile's barrier)
+    if (dyn && tid == 0) claimed = atomicAdd(&dyn_hdr(p)->next_tile, 1u);
     if (next < n_tiles) {
+      if (dyn) issue_records(next, (it + 1) & 3);
       issue_tile(next, sbuf ^ 1);
       cmd_next = fetch_action(next);
     }
@@ -589,6 +702,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     MDR_STAMP(4);
     // the only CTA-wide rendezvous of a tile: message window + power partials are complete.
     // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
+    if (dyn && tid == 0) ctl.claim[it & 1] = (int)min(2u * gridDim.x + claimed, (unsigned)n_tiles);
     house_sync(T);
     MDR_STAMP(5);
 
@@ -704,14 +818,19 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     }
     // this warp is done with ring slot `slot`: let the prologue warp reuse it for tile it+ring
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ctl.empty[slot]);
+    if (!dyn && lane == 0) mbar_arrive(&ctl.empty[slot]);
     MDR_STAMP(7);
+    if (dyn) {
+      tile = tile_nxt - tile_stride;  // (the loop header adds the stride)
+      tile_nxt = ctl.claim[it & 1];   // (written before this tile's barrier; rewritten two tiles from now)
+    }
   }
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();
   MDR_CTA_STAMP(2);
   // (with a shared due queue every CTA enters: it may have nothing due itself and still take tiles from the others)
-  if (interp_mode && (any_due || due_q != nullptr)) pipe_refresh_pass(p, le, li, pend_tile);  // CTA-uniform
+  const int n_due = dyn ? ctl.n_due : -1;  // in-order claiming: known up front (0 = nothing to refresh in this launch)
+  if (interp_mode && (dyn ? n_due > 0 : (any_due || due_q != nullptr))) pipe_refresh_pass(p, le, li, pend_tile, n_due);  // CTA-uniform
   MDR_CTA_STAMP(3);
 }
 
