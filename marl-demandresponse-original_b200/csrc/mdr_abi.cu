@@ -520,7 +520,8 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     // (the layout follows the n_envs the workspace was sized for: slices of the host pipeline share it with whole steps)
     const int cap = ws_envs > 0 ? ws_envs : cfg->n_envs;
     k.dyn_off = (k.workspace && !g.static_tiles) ? (int)mdr::due_queue_bytes(cap) : 0;
-    k.dyn_rec_off = k.dyn_off + 64 + (int)mdr::dyn_flags_bytes(cap);
+    k.dyn_list_off = k.dyn_off + 64 + (int)mdr::dyn_flags_bytes(cap);
+    k.dyn_rec_off = k.dyn_list_off + (int)mdr::dyn_flags_bytes(cap);
     int L = 16;  // lanes per env within one tile's lane group
     while (L > 1 && L * g.envs_per_cta * g.pro_batch > 32) L >>= 1;
     k.pro_lanes = L;

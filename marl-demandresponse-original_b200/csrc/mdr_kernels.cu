@@ -1197,12 +1197,12 @@ static cudaError_t launch_step_r(const KernelParams& kp, const Geometry& g, cuda
 // (different geometries alternate freely; any host thread may launch).
 struct OccEntry { int dev, threads; size_t smem; int ctas_per_sm, sm_count; };
 
-template <int kC, int kAct, bool kObs, int kVar>
+template <int kC, int kAct, bool kObs, int kVar, bool kDyn>
 static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, cudaStream_t stream) {
   static std::atomic<uint64_t> latch{0};
   static std::mutex mu;
   static std::vector<OccEntry> cache;
-  cudaError_t err = ensure_max_smem(step_pipe_kernel<kC, kAct, kObs, kVar>, latch);
+  cudaError_t err = ensure_max_smem(step_pipe_kernel<kC, kAct, kObs, kVar, kDyn>, latch);
   if (err != cudaSuccess) return err;
   int dev = 0;
   err = cudaGetDevice(&dev);
@@ -1215,7 +1215,7 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
     if (ctas_per_sm == 0) {
       err = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
       if (err != cudaSuccess) return err;
-      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, step_pipe_kernel<kC, kAct, kObs, kVar>, g.threads, g.pipe_smem_bytes);
+      err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, step_pipe_kernel<kC, kAct, kObs, kVar, kDyn>, g.threads, g.pipe_smem_bytes);
       if (err != cudaSuccess) return err;
       if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;
       cache.push_back(OccEntry{dev, g.threads, g.pipe_smem_bytes, ctas_per_sm, sm_count});
@@ -1246,22 +1246,13 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
     attr.val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   }
-  // In-order tile claiming pays the latency of a kernel in front of the step kernel (6 us) for a balanced, shorter tile
-  // loop: worth it from about a dozen tiles per CTA (16 384 x 100: 18), not for small problems (4 096 x 50: 4.6 tiles
-  // per CTA, 22.6 vs 17.0 us per step).  MDR_DYN_MIN_TILES overrides the threshold (tiles per CTA).
+  // In-order tile claiming pays a grid barrier behind the per-env prologue for a balanced, shorter tile loop: worth
+  // it from about a dozen tiles per CTA (16 384 x 100: 18), not for small problems (4 096 x 50: 4.6 tiles per CTA).
+  // MDR_DYN_MIN_TILES overrides the threshold (tiles per CTA).
   static const int dyn_min = [] { const char* e = getenv("MDR_DYN_MIN_TILES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 14; }();
-  if ((long long)kp.n_tiles < (long long)dyn_min * grid) kp.dyn_off = 0;
-  if (kp.dyn_off != 0) {
-    // the per-env records of the whole step come from a small kernel in front (pro_batch tiles per warp)
-    cudaLaunchConfig_t lp = {};
-    lp.gridDim = dim3((kp.n_tiles + 4 * kp.pro_batch - 1) / (4 * kp.pro_batch));
-    lp.blockDim = dim3(128);
-    lp.dynamicSmemBytes = 0;
-    lp.stream = stream;
-    lp.attrs = attrs;
-    lp.numAttrs = g.no_pdl ? 0 : 1;  // (the access-policy window is the step kernel's)
-    err = cudaLaunchKernelEx(&lp, env_pro_kernel, kp);
-    if (err != cudaSuccess) return err;
+  if (kDyn && (long long)kp.n_tiles < (long long)dyn_min * grid) {
+    kp.dyn_off = 0;
+    return launch_pipe_t<kC, kAct, kObs, kVar, false>(kp, g, stream);
   }
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3(grid);
@@ -1270,14 +1261,23 @@ static cudaError_t launch_pipe_t(const KernelParams& kp_in, const Geometry& g, c
   lc.stream = stream;
   lc.attrs = attrs;
   lc.numAttrs = n_attrs;
-  return cudaLaunchKernelEx(&lc, step_pipe_kernel<kC, kAct, kObs, kVar>, kp);
+  return cudaLaunchKernelEx(&lc, step_pipe_kernel<kC, kAct, kObs, kVar, kDyn>, kp);
 }
 
 template <int kC, bool kObs, int kVar>
 static cudaError_t launch_pipe_c(const KernelParams& kp, const Geometry& g, cudaStream_t stream) {
-  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, kObs, kVar>(kp, g, stream);
-  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, kObs, kVar>(kp, g, stream);
-  return launch_pipe_t<kC, MDR_ACT_RANDOM, kObs, kVar>(kp, g, stream);
+  // (in-order tile claiming is instantiated for kernels that write observations: without them the tiles are short and
+  //  the per-env prologue, not the tile loop, bounds the launch)
+  if (kObs && kp.dyn_off != 0) {
+    if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, kObs, kVar, kObs>(kp, g, stream);
+    if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, kObs, kVar, kObs>(kp, g, stream);
+    return launch_pipe_t<kC, MDR_ACT_RANDOM, kObs, kVar, kObs>(kp, g, stream);
+  }
+  KernelParams ks = kp;
+  ks.dyn_off = 0;
+  if (kp.action_source == MDR_ACT_ARRAY) return launch_pipe_t<kC, MDR_ACT_ARRAY, kObs, kVar, false>(ks, g, stream);
+  if (kp.action_source == MDR_ACT_BANGBANG) return launch_pipe_t<kC, MDR_ACT_BANGBANG, kObs, kVar, false>(ks, g, stream);
+  return launch_pipe_t<kC, MDR_ACT_RANDOM, kObs, kVar, false>(ks, g, stream);
 }
 
 template <int kC, bool kObs>

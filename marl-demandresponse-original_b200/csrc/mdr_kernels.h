@@ -24,7 +24,7 @@ struct KernelParams {
   int pro_warp, house_warps, part_stride;                     // prologue warp id, warps that own houses, partial-sum stride
   int off_grid;                                               // pipelined kernels: shared-memory copy of the interpolation grid
   int cl, cl_slice, off_cl;                                   // env split over a cluster of `cl` CTAs, `cl_slice` houses each; ClusterTot offset
-  int dyn_off, dyn_rec_off;                                   // pipelined kernel: byte offsets of the tile-claim header (0 = static tiles) and of the records in `workspace`
+  int dyn_off, dyn_list_off, dyn_rec_off;                     // pipelined kernel: byte offsets of the tile-claim header (0 = static tiles), the due list and the records in `workspace`
   unsigned div_magic;                                         // floor(2^32 / N) + 1: tid / N == umulhi(tid, magic)
   int is_reset, comm_mode, state_flags, msg_flags, temp_penalty_mode, solar, base_power_mode, signal_mode;
   int n_sinusoids, interp_update_period, interp_nb_agents, perlin_nb_octaves, perlin_octaves_step, action_source;
@@ -101,10 +101,11 @@ bool fused_eligible(const KernelParams& kp);
 cudaError_t launch_big(const KernelParams& kp, int precision, void* workspace, cudaStream_t stream);
 size_t big_workspace(int n_envs, int n_houses);
 inline size_t due_queue_bytes(int n_envs) { return (64 + 4 * (size_t)n_envs + 63) & ~(size_t)63; }  // header + a word per tile
-// Scratch of ONE pipelined launch in MdrEnvs.workspace: [due-tile queue | claim header (64 B) | a flag word per tile |
-// a 64-byte hand-over record per env] (mdr_pipe.cuh: DueQueue, DynHdr).  Two launches may be in flight (host pipeline).
+// Scratch of ONE pipelined launch in MdrEnvs.workspace: [due-tile queue (strided lists) | claim header (64 B) | a due
+// word per tile | the due list | a 64-byte hand-over record per env] (mdr_pipe.cuh: DueQueue, DynHdr).  Two launches
+// may be in flight (host pipeline).
 inline size_t dyn_flags_bytes(int n_envs) { return (4 * (size_t)n_envs + 63) & ~(size_t)63; }
-inline size_t pipe_ws_bytes(int n_envs) { return due_queue_bytes(n_envs) + 64 + dyn_flags_bytes(n_envs) + 64 * (size_t)n_envs; }
+inline size_t pipe_ws_bytes(int n_envs) { return due_queue_bytes(n_envs) + 64 + 2 * dyn_flags_bytes(n_envs) + 64 * (size_t)n_envs; }
 cudaError_t launch_compact_obs(const KernelParams& kp, int precision, void* out, cudaStream_t stream);
 cudaError_t launch_sample_actions(const float* probs, long long n_rows, int n_actions, uint64_t seed, uint64_t draw_index,
                                   const uint64_t* draw_counter, uint8_t* actions, float* chosen_prob, cudaStream_t stream);

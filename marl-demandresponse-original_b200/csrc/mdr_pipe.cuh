@@ -121,8 +121,7 @@ struct PipeCtl {
   int due_n;
   int due_list[kMaxDue];
   int pub_count[2];  // warps that have fenced a due tile of even / odd position (shared due queue: early publication)
-  int claim[2];      // in-order tile claiming: the tile thread 0 claimed for position it + 2 (even / odd it)
-  int n_due;         // ... and the launch's number of due tiles (copied from the queue header by thread 0)
+  int ring_tile[4];  // in-order tile claiming: tile of position it in slot it & 3 (kDuePhase flag), written by the claim warp
 };
 
 // The prologue warp produces `pro_batch` tiles per pass: the 32 lanes are split into pro_batch
@@ -189,8 +188,7 @@ struct DueQueue {
   unsigned taken;      // slots claimed by consumers
   unsigned ctas_done;  // CTAs that have published everything they have
   unsigned exited;     // CTAs that are done with the queue (the last one re-zeroes the header)
-  unsigned n_due;      // in-order claiming: due tiles of this launch, counted by env_pro_kernel before the step kernel starts
-  unsigned pad[11];
+  unsigned pad[12];
   unsigned tiles[1];   // [n_tiles] tile index + 1, 0 = empty
 };
 
@@ -200,21 +198,27 @@ struct DueQueue {
 // one, and the drifting write front costs DRAM locality (tools/microbench/write_patterns_bw.cu: 5.85 TB/s against
 // 6.85 TB/s for tiles claimed in address order).  Claiming needs the per-env record of a tile that nobody planned to
 // process in this CTA, so the hand-over leaves shared memory:
-//   * a small kernel in front of the step kernel (env_pro_kernel, one warp per tile, the same env_prologue code)
-//     writes the 64-byte records of ALL envs into a global (L2-resident) array and a `due` word per tile;
-//   * the house warps take tiles blockIdx, blockIdx + grid, then whatever an atomic counter hands out (claimed two
-//     tiles ahead by thread 0), and a few loader threads fetch the tile's records next to the cp.async input stage
-//     of the NEXT tile (cp.async + mbarrier complete, 4-slot ring).
-// Both kernels carry the programmatic-dependent-launch attribute; each one's griddepcontrol.wait covers everything
-// before it in the stream.  Measured alternatives, not kept: the records produced by the step kernel's own prologue
-// warps with a ready flag per tile -- every global round trip the house warps depend on (flag, then record) needs a
-// whole tile of slack under the observation write stream (loaded L2 latency 1-2 us), the first wave starts 3 us later
-// than through shared memory, and the CTAs of a launch then depend on each other (co-residency).
+//   * at the start of the launch ALL warps of the grid (house warps and the prologue warp alike) produce the 64-byte
+//     records of all envs into a global (L2-resident) array -- pro_batch tiles per warp, the same env_prologue code --
+//     plus a `due` word per tile and the launch's due-tile count, and meet at a grid barrier (one arrival per CTA);
+//   * the house warps then take tiles blockIdx, blockIdx + grid, and whatever an atomic counter hands out (claimed two
+//     tiles ahead by thread 0); a few loader threads fetch the tile's records next to the cp.async input stage of the
+//     NEXT tile (cp.async + mbarrier complete, 4-slot ring).
+// Measured alternatives, not kept (16 384 x 100, in-phase refresh clocks, static lists 90.0 us per step):
+//   * records from the CTA's own prologue warp (strided slice, no back-pressure) with a ready flag per tile: every
+//     global round trip the house warps depend on (flag, then record) needs a whole tile of slack under the observation
+//     write stream (loaded L2 latency 1-2 us; acquire loads also invalidate L1): 95-116 us;
+//   * a small kernel in front of the step kernel producing all records (512 CTAs, 6.5 us) -- step kernel 73 us, but
+//     13 us from one step kernel to the next: 86.1 us.
 // ----------------------------------------------------------------------------------------
 struct DynHdr {
-  unsigned next_tile;  // tiles handed out beyond the first two of every CTA (zeroed by env_pro_kernel)
-  unsigned pad[15];
+  unsigned next_tile;  // positions handed out beyond the first two of every CTA
+  unsigned exited;     // CTAs that are done claiming (the last one out re-zeroes the header)
+  unsigned arrived;    // CTAs that have written their share of the records (grid barrier in front of the tile loop)
+  unsigned n_due;      // tiles with an interpolation refresh due in this launch = entries of the due list
+  unsigned pad[12];    // (arrived | n_due are read with one 8-byte load: n_due is final once every CTA has arrived)
 };
+constexpr int kDuePhase = 1 << 30;  // flag on a claimed tile index: taken from the due list (processed AND refreshed by this CTA)
 static_assert(sizeof(DynHdr) == 64, "DynHdr must stay 64 bytes");
 
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
@@ -224,17 +228,19 @@ __device__ __forceinline__ DynHdr* dyn_hdr(const KernelParams& p) {
   return reinterpret_cast<DynHdr*>(reinterpret_cast<unsigned char*>(p.workspace) + p.dyn_off);
 }
 __device__ __forceinline__ unsigned* dyn_due(const KernelParams& p) { return reinterpret_cast<unsigned*>(dyn_hdr(p) + 1); }
+__device__ __forceinline__ unsigned* dyn_list(const KernelParams& p) {
+  return reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(p.workspace) + p.dyn_list_off);
+}
 __device__ __forceinline__ PipeEnv* dyn_recs(const KernelParams& p) {
   return reinterpret_cast<PipeEnv*>(reinterpret_cast<unsigned char*>(p.workspace) + p.dyn_rec_off);
 }
 
-// Per-env prologue of a whole step, one warp per tile: records into the global array, per-env outputs in place (as
-// the in-kernel prologue warp does), one `due` word per tile.
-__global__ void __launch_bounds__(128) env_pro_kernel(const __grid_constant__ KernelParams p) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+// Per-env prologue of a whole step by ALL warps of the step kernel (pro_batch tiles per warp and pass): records into
+// the global array, per-env outputs in place (as the strided lists' prologue warp does), a `due` word per tile and the
+// launch's due-tile count.  `warp_g` / `n_warps`: this warp's index among / the number of warps of the grid.
+__device__ __noinline__ void pro_all_tiles(const KernelParams& p, int warp_g, int n_warps) {
   const int lane = threadIdx.x & 31;
-  // B tiles per warp (pro_batch, a power of two with B * G <= 32), L lanes per env: the grid stays within one wave
-  // (16 384 x 100: 512 CTAs; one warp per tile was 2 048 CTAs in 2.3 waves, 12 us instead of 6)
+  // B tiles per warp and pass (pro_batch, a power of two with B * G <= 32), L lanes per env
   const int B = p.pro_batch;
   const int lanes_per_tile = 32 / B;
   int L = 16;
@@ -244,14 +250,13 @@ __global__ void __launch_bounds__(128) env_pro_kernel(const __grid_constant__ Ke
   const int sub = tlane & (L - 1), grp = tlane / L;
   const int my_k = lane / lanes_per_tile;
   const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
-  const int tile = (blockIdx.x * 4 + (threadIdx.x >> 5)) * B + my_k;
+  PipeEnv* const recs = dyn_recs(p);
+  for (int tile0 = warp_g * B; tile0 < p.n_tiles; tile0 += n_warps * B) {
+  const int tile = tile0 + my_k;
   const bool tile_valid = tile < p.n_tiles;
   const int tile_c = tile_valid ? tile : 0;  // lanes of an absent tile compute but never write
   const int env0 = tile_c * p.G;
   const int genvs = min(p.G, p.E - env0);
-  PipeEnv* const recs = dyn_recs(p);
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous step wrote is visible from here on
-  if (blockIdx.x == 0 && threadIdx.x == 0) dyn_hdr(p)->next_tile = 0;
   EnvScratch unused;
   int my_due = 0;
   for (int first = 0; first < p.G; first += groups) {  // warp-uniform trip count
@@ -271,9 +276,8 @@ __global__ void __launch_bounds__(128) env_pro_kernel(const __grid_constant__ Ke
   if (tile_valid && tlane == 0) {
     const bool due = (due_ballot & group_mask) != 0;
     __stcg(dyn_due(p) + tile, due ? 1u : 0u);
-    // the step kernel knows how many due tiles to expect: a launch without any skips the refresh pass, and nobody has to
-    // wait for the slowest CTA to learn that the queue is complete
-    if (due) atomicAdd(&reinterpret_cast<DueQueue*>(p.workspace)->n_due, 1u);
+    if (due) __stcg(dyn_list(p) + atomicAdd(&dyn_hdr(p)->n_due, 1u), (unsigned)tile);  // the launch's due list
+  }
   }
 }
 
@@ -392,7 +396,7 @@ __device__ __noinline__ void publish_due_tile(DueQueue* q, int tile, int* counte
 // treats a due env like any other (the prologue parks its perlin value and marks it), and this pass -- after the loop,
 // same launch -- evaluates the table on the houses' NEW state, re-evaluates the signal and patches observation
 // feature 9 (the only output that depends on it).
-__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li, int pend_tile, int n_due) {
+__device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, int li, int pend_tile) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int T = p.hmax;
@@ -420,23 +424,21 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
       atomicExch(&q->tiles[idx], (unsigned)pend_tile + 1u);
     }
     __threadfence();
-    if (n_due < 0) atomicAdd(&q->ctas_done, 1u);
+    atomicAdd(&q->ctas_done, 1u);
   }
   for (;;) {
     if (tid == 0) {
       const unsigned idx = atomicAdd(&q->taken, 1u);
       int got = -1;
       unsigned long long t0 = 0;
-      // (n_due >= 0: the launch's number of due tiles is known -- every slot below it WILL be published, and a CTA that
-      //  draws a slot beyond it leaves at once instead of waiting for the slowest CTA's "nothing more to publish")
-      for (unsigned spin = 0; n_due < 0 || idx < (unsigned)n_due; ++spin) {
+      for (unsigned spin = 0;; ++spin) {
         const unsigned v = ld_volatile_u32(&q->tiles[idx]);
         if (v != 0) {
           q->tiles[idx] = 0;  // leave the queue zeroed for the next launch
           got = (int)v - 1;
           break;
         }
-        if (n_due < 0 && ld_volatile_u32(&q->ctas_done) == gridDim.x) {  // every publisher is done: reserved is final
+        if (ld_volatile_u32(&q->ctas_done) == gridDim.x) {  // every publisher is done: reserved is final
           if (idx >= ld_volatile_u32(&q->reserved)) break;
           continue;  // the slot was written before its publisher counted itself done: re-read it
         }
@@ -458,15 +460,32 @@ __device__ __noinline__ void pipe_refresh_pass(const KernelParams& p, int le, in
   }
   if (tid == 0) {
     if (atomicAdd(&q->exited, 1u) == gridDim.x - 1) {  // last one out re-zeroes the header
-      q->reserved = 0; q->taken = 0; q->ctas_done = 0; q->exited = 0; q->n_due = 0;
+      q->reserved = 0; q->taken = 0; q->ctas_done = 0; q->exited = 0;
       __threadfence();
     }
   }
 }
 
+// In-order claiming: a tile taken from the launch's due list is refreshed by the CTA that processed it, one tile later
+// (inside the tile loop: the other CTAs simply claim more tiles meanwhile, so the refresh work of a step costs the launch
+// its share of the grid's time instead of a tail).  Every warp's bulk stores of the tile's rows must have landed before
+// feature 9 is patched; the tile's state was stored before the previous tile barrier of this CTA.
+// The tile loop LEAVES for this call and is re-entered afterwards (its thirty-odd loop-invariant registers are recomputed):
+// a call inside the loop made the compiler spill some of them for good, and with 3 x 76 KB of shared memory per SM
+// there is no L1 left for local memory -- every spill reload was an L2 round trip (16 384 x 100: 127 instead of 88 us).
+__device__ __noinline__ void pipe_refresh_own(const KernelParams& p, int tile) {
+  const int tid = threadIdx.x;
+  const int le = tid < p.G * p.N ? (p.N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
+  const int li = tid - le * p.N;
+  if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __threadfence();
+  __syncwarp();
+  pipe_refresh_tile(p, tile, le, li);  // (three house-warp barriers in front of the patch)
+}
+
 // kVar: bit 0 = metric accumulators (MDR_M_*) as an epilogue of the tile; bit 1 = message drops
 // (replayed msg_keep, or Philox against comm_defect_prob) in the observation rows.
-template <int kC, int kAct, bool kObs, int kVar>
+template <int kC, int kAct, bool kObs, int kVar, bool kDyn>
 __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant__ KernelParams p) {
   constexpr bool kMetrics = (kVar & 1) != 0;
   constexpr bool kDrops = kObs && (kVar & 2) != 0;
@@ -474,10 +493,9 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   PipeCtl& ctl = *reinterpret_cast<PipeCtl*>(smem_raw + p.off_ctl);
-  const bool dyn = p.dyn_off != 0;  // in-order tile claiming (see DynHdr): 4-slot record ring filled by loader threads
+  constexpr bool dyn = kDyn;  // in-order tile claiming (see DynHdr): 4-slot ring of tile ids + records filled by the claim warp
   const int ring_mask = dyn ? 3 : 2 * p.pro_batch - 1;
   const int ring_shift = 31 - __clz(ring_mask + 1);
-  const int nload = min(p.hmax, 4 * p.G);  // loader threads: one 16-byte chunk of the tile's records each (or more)
   MDR_CTA_STAMP(0);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next step may start occupying freed SMs
   if (p.base_power_mode == MDR_BASE_INTERPOLATION) {  // shared-memory copy of the interpolation grid (see InterpGrid)
@@ -490,14 +508,91 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     ctl.due_n = 0;
     ctl.pub_count[0] = ctl.pub_count[1] = 0;
     for (int i = 0; i <= ring_mask; ++i) {
-      mbar_init(&ctl.full[i], dyn ? nload : 1);
+      mbar_init(&ctl.full[i], dyn ? 33 : 1);  // (claim warp: 32 copy completions + lane 0's release of the tile id)
       mbar_init(&ctl.empty[i], p.house_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (dyn) {
+    // Every warp of the grid (house warps and the prologue warp alike) produces its share of the step's per-env
+    // records, then the CTA arrives at the grid barrier.  The CTAs of a launch are co-resident (grid <= SMs x resident
+    // CTAs; a dependent launch only takes the slots this one frees).
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
+    pro_all_tiles(p, warp * gridDim.x + blockIdx.x, (blockDim.x >> 5) * gridDim.x);
+    cta_sync();
+    if (warp >= p.house_warps) {
+      // ---- the claim warp: grid barrier, then the ring of (tile id, due word, records) the house warps consume ----
+      // Position q of the launch's work list is tile q for q < grid, entry q - grid of the due list (kDuePhase) for the
+      // next n_due positions, tile q - n_due after that.  The first three positions of a CTA are fixed (blockIdx + 0, 1,
+      // 2 x grid), the others come from the counter -- position it + 3 is claimed when every house warp has started
+      // tile it.  A due tile met in address order is skipped by the house warps.
+      DynHdr* const dh = dyn_hdr(p);
+      unsigned D = 0;
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(&dh->arrived, 1u);
+        unsigned long long t0 = 0;
+        unsigned long long both;  // arrived | n_due << 32, one 8-byte load: n_due is final once every CTA has arrived
+        for (unsigned spin = 1;; ++spin) {
+          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(both) : "l"(&dh->arrived) : "memory");
+          if ((unsigned)both >= gridDim.x) break;
+          __nanosleep(32);
+          if ((spin & 1023u) == 0) {  // a CTA that never becomes resident must not hang the GPU: abort loudly after ~2 s
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+          }
+        }
+        __threadfence();
+        D = (unsigned)(both >> 32);
+      }
+      D = __shfl_sync(0xffffffffu, D, 0);
+      const int n_tiles = p.n_tiles;
+      auto map_position = [&](unsigned q) -> int {  // (lane 0)
+        if (q < gridDim.x) return (int)q;
+        if (q < gridDim.x + D) return (int)ld_volatile_u32(dyn_list(p) + (q - gridDim.x)) | kDuePhase;
+        const unsigned t = q - D;
+        return t < (unsigned)n_tiles ? (int)t : n_tiles;
+      };
+      auto fill = [&](int slot, int enc) {  // tile id, due word and records of one position into ring slot `slot`
+        const int t = enc & (kDuePhase - 1);
+        if (t < n_tiles) {
+          if (lane == 0) cp_async_4(&ctl.tile_due[slot], dyn_due(p) + t);
+          const int nchunks = 4 * min(p.G, p.E - t * p.G);
+          unsigned char* dst = smem_raw + p.off_env + slot * p.G * (int)sizeof(PipeEnv);
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(dyn_recs(p) + (size_t)t * p.G);
+          for (int c = lane; c < nchunks; c += 32) cp_async_16(dst + c * 16, src + c * 16);
+        }
+        cp_async_mbar_arrive_noinc(&ctl.full[slot]);
+        if (lane == 0) {
+          ctl.ring_tile[slot] = enc;
+          mbar_arrive(&ctl.full[slot]);
+        }
+      };
+      int enc = 0;
+      fill(0, (int)blockIdx.x);
+      for (int j = 1; j < 3; ++j) {
+        if (lane == 0) enc = map_position(j * gridDim.x + blockIdx.x);
+        enc = __shfl_sync(0xffffffffu, enc, 0);
+        fill(j, enc);
+      }
+      for (int j = 3; (enc & (kDuePhase - 1)) < n_tiles; ++j) {
+        const int slot = j & 3;
+        // permission: every house warp has started tile j - 3 (and is done with the slot's previous tenant, tile j - 4).
+        // The claim (an atomic round trip) and the record copies (another one) then have two tiles to land: under the
+        // observation write stream each takes 1-2 us, and with one tile of slack the house warps waited for them.
+        mbar_wait(&ctl.empty[slot], ((j >> 2) - (slot < 3 ? 1 : 0)) & 1);
+        if (lane == 0) enc = map_position(3u * gridDim.x + atomicAdd(&dh->next_tile, 1u));
+        enc = __shfl_sync(0xffffffffu, enc, 0);
+        fill(slot, enc);
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      return;
+    }
+  }
   if (warp >= p.house_warps) {
-    if (dyn) return;  // (the records were produced by env_pro_kernel)
     asm volatile("griddepcontrol.wait;" ::: "memory");  // everything the previous launch wrote is visible from here on
     // tiles per pass: pro_batch, but not more than this launch gives a CTA (a small problem should spend its lanes
     // on the envs of tiles that exist, not on absent ones)
@@ -507,6 +602,14 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     return;
   }
 
+  // loop state that survives a refresh call between two tiles (in-order claiming, see pipe_refresh_own)
+  int it = 0;
+  int tile = blockIdx.x;
+  int refresh_prev = -1;  // due-list tile of the previous iteration, refreshed at the end of this one
+  int refresh_now = -1;
+  int cmd_next = 0;
+restart:
+  {
   // ---------------- per-thread constants of the tile loop ------------------------------------
   const int N = p.N, G = p.G;
   const int C = kC > 0 ? kC : p.C;
@@ -559,39 +662,23 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     return 0;
   };
 
-  int tile = blockIdx.x;
-  int tile_nxt = blockIdx.x + gridDim.x;  // (in-order claiming: the first two tiles of a CTA are fixed)
-  int cmd_next = 0;
   int any_due = 0;
-  unsigned claimed = 0;  // thread 0: tiles handed out before its latest claim
-  // shared due queue (see DueQueue): a due tile is published one tile later, once its stores have landed
-  DueQueue* const due_q = interp_mode ? reinterpret_cast<DueQueue*>(p.workspace) : nullptr;
+  // strided lists: shared due queue (see DueQueue): a due tile is published one tile later, once its stores have landed
+  DueQueue* const due_q = (interp_mode && !dyn) ? reinterpret_cast<DueQueue*>(p.workspace) : nullptr;
   int pend_tile = -1;
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
-  MDR_CTA_STAMP(1);
-  // the records of tile t (and its `due` word) into ring slot `rslot`: a few loader threads copy, the slot's mbarrier
-  // completes with the copies
-  auto issue_records = [&](int t, int rslot) {
-    const int nl = min(p.hmax, 4 * p.G);
-    if (tid < nl) {
-      if (tid == 0) cp_async_4(&ctl.tile_due[rslot], dyn_due(p) + t);
-      const int nchunks = 4 * min(p.G, p.E - t * p.G);
-      unsigned char* dst = smem_raw + p.off_env + rslot * p.G * (int)sizeof(PipeEnv);
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(dyn_recs(p) + (size_t)t * p.G);
-      for (int c = tid; c < nchunks; c += nl) cp_async_16(dst + c * 16, src + c * 16);
-      cp_async_mbar_arrive_noinc(&ctl.full[rslot]);
+  if (it == 0 && refresh_now < 0) {  // (not when the loop is re-entered after a refresh)
+    if (!dyn) asm volatile("griddepcontrol.wait;" ::: "memory");  // (house warps: after their loop-invariant set-up)
+    MDR_CTA_STAMP(1);
+    if (tile < n_tiles) {
+      issue_tile(tile, 0);
+      cmd_next = fetch_action(tile);
     }
-  };
-  // (thread 0's first record copies complete after this one: ctl.n_due is visible to everybody behind the first full[])
-  if (dyn && interp_mode && tid == 0) cp_async_4(&ctl.n_due, &reinterpret_cast<DueQueue*>(p.workspace)->n_due);
-  if (tile < n_tiles) {
-    if (dyn) issue_records(tile, 0);
-    issue_tile(tile, 0);
-    cmd_next = fetch_action(tile);
+    cp_async_commit();
+    if (dyn) mbar_wait(&ctl.full[1], 0);  // position 1 of this CTA is known (behind the grid barrier)
   }
-  cp_async_commit();
+  refresh_now = -1;
 
-  for (int it = 0; tile < n_tiles; ++it, tile += tile_stride) {
+  for (; tile < n_tiles; ++it, tile += tile_stride) {
     const int sbuf = it & 1;
     const int H = tile_houses(tile);
     const bool active = tid < H;
@@ -599,20 +686,40 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     const int e = tile * G + le;
     MDR_STAMP(0);
     int cmd = cmd_next;
-    const int next = dyn ? tile_nxt : tile + tile_stride;
-    // (claim for position it + 2: issued now, needed before this tile's barrier)
-    if (dyn && tid == 0) claimed = atomicAdd(&dyn_hdr(p)->next_tile, 1u);
+    if (dyn) {
+      // this warp has started tile it: position it + 3 may be claimed; position it + 1 has had two tiles to arrive
+      if (lane == 0) mbar_arrive(&ctl.empty[(it + 3) & 3]);
+      if (it > 0) mbar_wait(&ctl.full[(it + 1) & 3], ((it + 1) >> 2) & 1);
+    }
+    MDR_STAMP(8);
+    const int next = dyn ? (ctl.ring_tile[(it + 1) & 3] & (kDuePhase - 1)) : tile + tile_stride;
     if (next < n_tiles) {
-      if (dyn) issue_records(next, (it + 1) & 3);
       issue_tile(next, sbuf ^ 1);
       cmd_next = fetch_action(next);
     }
     cp_async_commit();
+    MDR_STAMP(9);
     // hand-over from the prologue warp (normally produced more than a tile ago).  Waiting here rather than
     // at the end of the tile (with the house threads prefetching od_temp themselves) measured the same.
     const int slot = it & ring_mask;
     const PipeEnv* const env_buf = s_env + slot * G;
-    mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);
+    if (!dyn || it == 0) mbar_wait(&ctl.full[slot], (it >> ring_shift) & 1);  // (in-order claiming: waited for a tile ago)
+    if (dyn && interp_mode && (ctl.ring_tile[slot] & kDuePhase) == 0 && ctl.tile_due[slot] != 0) {
+      // a due tile met in address order: it is (or was) processed from the due list in this launch.  The iteration
+      // keeps its shape -- one cp.async group, one barrier (the double-buffered windows count on it) -- and computes
+      // nothing.
+      cp_async_wait<1>();
+      house_sync(T);
+      refresh_now = refresh_prev;
+      refresh_prev = -1;
+      tile = next - tile_stride;  // (the loop header adds the stride)
+      if (refresh_now >= 0) {
+        ++it;
+        tile += tile_stride;
+        goto do_refresh;
+      }
+      continue;
+    }
     const float od_old = env_buf[le].od_old;
     const float gain = env_buf[le].gain;  // 0 with solar gain off
     MDR_STAMP(1);
@@ -702,7 +809,6 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     MDR_STAMP(4);
     // the only CTA-wide rendezvous of a tile: message window + power partials are complete.
     // (window / partials are double buffered, so nobody can overwrite what a slower warp still reads)
-    if (dyn && tid == 0) ctl.claim[it & 1] = (int)min(2u * gridDim.x + claimed, (unsigned)n_tiles);
     house_sync(T);
     MDR_STAMP(5);
 
@@ -775,7 +881,7 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
       }
     }
     MDR_STAMP(6);
-    const int due_now = interp_mode ? ctl.tile_due[slot] : 0;
+    const int due_now = (!dyn && interp_mode) ? ctl.tile_due[slot] : 0;
     if (due_now) {
       any_due = 1;
       if (due_q == nullptr && tid == 0) {
@@ -821,16 +927,44 @@ __global__ void __launch_bounds__(256, 3) step_pipe_kernel(const __grid_constant
     if (!dyn && lane == 0) mbar_arrive(&ctl.empty[slot]);
     MDR_STAMP(7);
     if (dyn) {
-      tile = tile_nxt - tile_stride;  // (the loop header adds the stride)
-      tile_nxt = ctl.claim[it & 1];   // (written before this tile's barrier; rewritten two tiles from now)
+      if (interp_mode) {  // (CTA-uniform) the due-list tile of the previous iteration: its stores have had a tile to land
+        refresh_now = refresh_prev;
+        refresh_prev = (ctl.ring_tile[slot] & kDuePhase) ? tile : -1;
+      }
+      tile = next - tile_stride;  // (the loop header adds the stride)
+      if (refresh_now >= 0) {
+        ++it;
+        tile += tile_stride;
+        goto do_refresh;
+      }
     }
   }
   cp_async_wait<0>();
   if (kObs && lane == 0) bulk_wait_read_all();
   MDR_CTA_STAMP(2);
+  if (dyn && refresh_prev >= 0) {  // (the CTA's last tile came from the due list)
+    refresh_now = refresh_prev;
+    refresh_prev = -1;
+    goto do_refresh;
+  }
   // (with a shared due queue every CTA enters: it may have nothing due itself and still take tiles from the others)
-  const int n_due = dyn ? ctl.n_due : -1;  // in-order claiming: known up front (0 = nothing to refresh in this launch)
-  if (interp_mode && (dyn ? n_due > 0 : (any_due || due_q != nullptr))) pipe_refresh_pass(p, le, li, pend_tile, n_due);  // CTA-uniform
+  if (!dyn && interp_mode && (any_due || due_q != nullptr)) pipe_refresh_pass(p, le, li, pend_tile);  // CTA-uniform
+  }
+  goto finish;
+do_refresh:
+  pipe_refresh_own(p, refresh_now);
+  goto restart;
+finish:
+  if (dyn && tid == 0) {  // the last CTA out leaves the claim header zeroed for the next launch
+    DynHdr* const dh = dyn_hdr(p);
+    if (atomicAdd(&dh->exited, 1u) == gridDim.x - 1) {
+      dh->next_tile = 0;
+      dh->arrived = 0;
+      dh->n_due = 0;
+      dh->exited = 0;
+      __threadfence();
+    }
+  }
   MDR_CTA_STAMP(3);
 }
 

@@ -45,6 +45,9 @@ np.set_printoptions(precision=1, suppress=True, linewidth=200)
 for wi in (0, 3, 6):
     print("house warp %d (us since first stamp): columns = %s" % (wi, ", ".join(names)))
     print(rel[wi, :, :8])
+    if np.isfinite(rel[wi, :, 9]).any():
+        print("  ... within 'issued next+record': [tile start, ring slot of the next tile ready, next tile's copies issued]")
+        print(rel[wi, :12][:, [0, 8, 9]])
 print("prologue warp: per pass starting at tile it0: [wait for slot, start, end]")
 print(rel[7][:, [8, 0, 7]])
 
