@@ -299,6 +299,7 @@ __device__ __forceinline__ void metrics_signal_terms(double* m, double sig, doub
 
 // refresh of ONE due tile (all house threads of the CTA): table walk on the houses' NEW state, base power, signal,
 // observation feature 9 (PowerGrid.step :1250-1255, interpolatePower :1195-1234)
+template <bool kOwn = false>  // kOwn: the CTA's own tile, its bulk row stores may still be in flight (waited for in front of the patch)
 __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int tile, int le, int li) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s_val = reinterpret_cast<double*>(smem_raw + p.off_val);
@@ -312,34 +313,57 @@ __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int til
   const bool active = tid < H;
   const int e = tile * G + le;
   const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+  // Everything that depends on nothing else is loaded up front, in flight together: under the observation write stream
+  // a dependent global round trip costs 2-3 us, and the refresh is nothing but a chain of them (it took 18 us per tile
+  // with the loads issued where their values were needed).
   // (another SM may have written this tile's state in this launch: L1 is not coherent across SMs, read through L2)
-  const bool due = active && __ldcg(p.time_since_interp + e) < 0;
-  double od_new = 0.0, hour_s = 0.0, date = 0.0;
-  if (due) {
-    od_new = __ldcg(p.od_temp + e);
-    if (p.solar) {  // interpolatePower point :1198-1207: seconds since midnight and tm_yday, 0 with solar gain off
-      Calendar cal = calendar_time((uint32_t)__ldcg(p.t_epoch + e));
-      calendar_date(cal);
-      hour_s = (double)cal.sod;
-      date = (double)cal.yday;
-    }
+  const int tsi = active ? __ldcg(p.time_since_interp + e) : 0;
+  double od_new = active ? __ldcg(p.od_temp + e) : 0.0;
+  const bool head = active && li == 0;
+  const bool need_clock = head || (active && p.solar);
+  const uint32_t t_ep = need_clock ? (uint32_t)__ldcg(p.t_epoch + e) : 0u;
+  double sig_noise = 0.0, ratio = 0.0, max_power = 0.0, cpow = 0.0;
+  if (head) {
+    sig_noise = __ldcg(p.base_power + e);  // parked by the prologue
+    ratio = p.artificial_ratio[e];
+    max_power = p.max_power[e];
+    if (p.metrics != nullptr) cpow = __ldcg(p.cluster_power + e);
+  }
+  const bool direct = N <= nb;  // every house is sampled: thread li evaluates house li
+  float2 t2 = make_float2(0.f, 0.f);
+  double tg = 0.0;
+  int key = 0;
+  if (active && direct) {
+    const size_t hs = (size_t)e * N + li;
+    t2 = __ldcg(reinterpret_cast<const float2*>(p.temps) + hs);
+    tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
+    key = p.interp_key[hs];
+  }
+  const bool due = active && tsi < 0;
+  double hour_s = 0.0, date = 0.0;
+  if (due && p.solar) {  // interpolatePower point :1198-1207: seconds since midnight and tm_yday, 0 with solar gain off
+    Calendar cal = calendar_time(t_ep);
+    calendar_date(cal);
+    hour_s = (double)cal.sod;
+    date = (double)cal.yday;
   }
   double val = 0.0;
   if (due && li < nsamp) {
-    int src = li;
-    if (N > nb) {
+    if (!direct) {
+      int src;
       if (p.interp_ids) src = p.interp_ids[(size_t)e * nb + li];
       else {
         const uint4 r = philox4x32((uint32_t)(e + p.env_base), (uint32_t)step_now(p), (uint32_t)(step_now(p) >> 32),
                                    STREAM_IDS + 16 * (uint32_t)li, p.seed);
         src = (int)(((uint64_t)r.x * (uint64_t)N) >> 32);
       }
+      const size_t hs = (size_t)e * N + src;
+      t2 = __ldcg(reinterpret_cast<const float2*>(p.temps) + hs);
+      tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
+      key = p.interp_key[hs];
     }
-    const size_t hs = (size_t)e * N + src;
-    const float2 t2 = __ldcg(reinterpret_cast<const float2*>(p.temps) + hs);
-    const double tg = (double)reinterpret_cast<const float4*>(p.coef_b)[hs].w;
     val = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
-                                              p.interp_key[hs], (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
+                                              key, (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
   }
   s_val[tid] = val;  // 0 for houses that are not sampled
   house_sync(T);
@@ -356,18 +380,18 @@ __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int til
     const int np = nsamp < 32 ? nsamp : 32;
     for (int i = 0; i < np; ++i) base += s_val[T + le * 32 + i];
     if (N > nb) base = mul_rn(base, (double)N / (double)nb);
-    const Calendar cal = calendar_time((uint32_t)__ldcg(p.t_epoch + e));
+    const Calendar cal = calendar_time(t_ep);
     const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
-    const double sig_noise = __ldcg(p.base_power + e);  // parked by the prologue
-    const double sig = grid_signal(p, base, time_sec, sig_noise, p.artificial_ratio[e], p.max_power[e]);
+    const double sig = grid_signal(p, base, time_sec, sig_noise, ratio, max_power);
     p.base_power[e] = base;
     p.time_since_interp[e] = 0;
     p.signal[e] = sig;
     s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
     // the tile loop left the signal-dependent accumulators of a due env to this pass (its signal was not final)
-    if (p.metrics != nullptr) metrics_signal_terms(p.metrics + (size_t)e * MDR_N_METRICS, sig, __ldcg(p.cluster_power + e));
+    if (p.metrics != nullptr) metrics_signal_terms(p.metrics + (size_t)e * MDR_N_METRICS, sig, cpow);
   }
-  house_sync(T);
+  if (kOwn && (tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every warp's rows have landed ...
+  house_sync(T);                                                                           // ... before anybody patches one
   if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
   // (s_val / s_fsig are reused by the next tile: its first writes come after this tile's last reads of the same
   //  thread's entries, and its first barrier orders the rest)
@@ -477,10 +501,9 @@ __device__ __noinline__ void pipe_refresh_own(const KernelParams& p, int tile) {
   const int tid = threadIdx.x;
   const int le = tid < p.G * p.N ? (p.N == 1 ? tid : (int)__umulhi((unsigned)tid, p.div_magic)) : 0;  // tid / N
   const int li = tid - le * p.N;
-  if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  __threadfence();
-  __syncwarp();
-  pipe_refresh_tile(p, tile, le, li);  // (three house-warp barriers in front of the patch)
+  // (the tile's state was stored by this CTA's threads in front of at least one house-warp barrier; the bulk stores of
+  //  its rows are waited for inside, in front of the patch, so that they drain under the table walk)
+  pipe_refresh_tile<true>(p, tile, le, li);
 }
 
 // kVar: bit 0 = metric accumulators (MDR_M_*) as an epilogue of the tile; bit 1 = message drops
