@@ -15,7 +15,7 @@ PEN = {"individual_L2": 0, "common_L2": 1, "common_max": 2, "mixture": 3}
 BASE = {"constant": 0, "interpolation": 1}
 SIG_FLAT, SIG_SINUSOIDALS, SIG_REGULAR_STEPS, SIG_PERLIN = 0, 1, 2, 3
 ACT = {"array": 0, "bangbang": 1, "random": 2, "greedy": 3}
-FLAG_NO_PIPELINE, FLAG_NO_FUSED, FLAG_NO_PDL, FLAG_NO_CLUSTER = 1, 2, 4, 8
+FLAG_NO_PIPELINE, FLAG_NO_FUSED, FLAG_NO_PDL, FLAG_NO_CLUSTER, FLAG_STATIC_TILES = 1, 2, 4, 8, 16
 HAS_CLUSTER_PATH = True
 METRIC_NAMES = ("steps", "sum_mean_reward", "sum_mean_temp_offset", "sum_mean_temp_error", "sum_sq_temp_error",
                 "sum_sq_max_temp_error", "max_temp_error", "sum_od_temp", "sum_signal", "sum_consumption",

@@ -196,11 +196,14 @@ class VecDemandResponseEnv:
         self._refs = (C.byref(self.cfg), C.byref(self.houses_s), C.byref(self.envs_s), C.byref(self.in_s),
                       C.byref(self.out_s))
 
-    def set_launch_options(self, *, no_pipeline=None, no_fused=None, no_pdl=None, no_cluster=None, max_ctas=None):
+    def set_launch_options(self, *, no_pipeline=None, no_fused=None, no_pdl=None, no_cluster=None, static_tiles=None,
+                           max_ctas=None):
         """MdrConfig.flags / max_ctas: pin the kernel choice (tests compare the pipelined, generic and fused kernels
-        on the same inputs) and cap the persistent grid (so that every CTA walks many tiles in a small test)."""
+        on the same inputs), choose between the pipelined kernel's fixed strided tile lists and in-order tile claiming
+        (default: claiming from 14 tiles per CTA), and cap the persistent grid (so that every CTA walks many tiles in
+        a small test)."""
         for bit, v in ((_lib.FLAG_NO_PIPELINE, no_pipeline), (_lib.FLAG_NO_FUSED, no_fused), (_lib.FLAG_NO_PDL, no_pdl),
-                       (_lib.FLAG_NO_CLUSTER, no_cluster)):
+                       (_lib.FLAG_NO_CLUSTER, no_cluster), (_lib.FLAG_STATIC_TILES, static_tiles)):
             if v is not None:
                 self._flags = (self._flags | bit) if v else (self._flags & ~bit)
         if max_ctas is not None:
@@ -281,7 +284,9 @@ class VecDemandResponseEnv:
         reset (None = all); the others are not touched -- a rollout worker can restart finished episodes without a
         host round trip.  The draw follows utils.applyPropertyNoise / HVAC.__init__ / ClusterHouses.__init__ /
         PowerGrid.__init__ at the distribution level (Philox streams keyed by seed, draw_index, house/env).
-        Returns the observation tensor (all envs), like reset_tensor()."""
+        Returns the observation tensor (all envs), like reset_tensor(): the rows of the envs that were not reset are
+        re-assembled from their unchanged state (identical bytes, except that with `comm_defect_prob > 0` or
+        `random_sample` neighbours their message drops / neighbour sets are drawn anew, as at any observation)."""
         from .population import population_spec
         if spec is None:
             spec = population_spec(self.flat)
@@ -534,6 +539,7 @@ class VecDemandResponseEnv:
         if self.metrics is not None:
             sd["metrics"] = self.metrics.clone()
         sd["step_index"] = self.step_index
+        sd["draws"] = getattr(self, "_draws", 0)  # population re-draws so far (reset_envs must not repeat a draw index)
         return sd
 
     def load_state_dict(self, sd):
@@ -551,6 +557,7 @@ class VecDemandResponseEnv:
             self.enable_metrics()
             self.metrics.copy_(sd["metrics"])
         self.step_index = int(sd["step_index"])
+        self._draws = int(sd.get("draws", getattr(self, "_draws", 0)))
         self._precomputed = True
 
     def __deepcopy__(self, memo):

@@ -71,8 +71,14 @@ def _compare(env, oracle, ids, out, o_out, t):
     (45, 500, True, "perlin", 10, 6),         # split kernel: 3 CTAs per env, 2 clusters walk 22+ envs each, inline refreshes
     (64, 1000, False, "sinusoidals", 10, 5),  # split kernel, c3big's tile shape (5 x 200): ONE cluster walks all 64 envs
 ])
-def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_ctas):
+@pytest.mark.parametrize("tiles", ["claimed", "strided"])
+def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_ctas, tiles):
+    """`tiles`: the pipelined kernel's two schedules -- tiles claimed in address order (all warps produce the per-env
+    records behind a grid barrier, due tiles first and refreshed by their own CTA; the default from 14 tiles per CTA,
+    i.e. here) and the fixed strided list per CTA (prologue warp + shared-memory ring, shared due-tile queue)."""
     import mdr_b200
+    if n > 224 and tiles == "strided":
+        pytest.skip("the split kernel has one schedule")
     steps = 160 if interp else 40
     cfg, flat = _config(n, interp, signal, nb_comm)
     pop = mdr_b200.synthetic_population(flat, n_envs, seed=500 + n)
@@ -82,7 +88,7 @@ def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_
         pop["base_power"] = rng.uniform(2000.0, 5000.0, n_envs) * n
     table = gu.synthetic_table() if interp else None
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
-    env.set_launch_options(max_ctas=max_ctas)
+    env.set_launch_options(max_ctas=max_ctas, static_tiles=(tiles == "strided"))
     geo = env.launch_geometry()
     assert geo["kernel"].startswith("mdr::step_pipe_split_kernel" if n > 224 else "mdr::step_pipe_kernel")
     assert geo["tiles"] >= 20 * max_ctas, geo
@@ -108,8 +114,13 @@ def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_
         assert refreshes >= 2 * n_envs
 
 
-@pytest.mark.parametrize("n_envs,n,interp", [(16384, 100, True), (4096, 50, False)])
-def test_full_size_sampled_envs_match_oracle(n_envs, n, interp):
+@pytest.mark.parametrize("n_envs,n,interp,tiles,stagger", [
+    (16384, 100, True, "claimed", False),   # the default bench kernel; refresh clocks in phase: steps 75 and 150 refresh EVERY tile
+    (16384, 100, True, "claimed", True),    # ... staggered clocks (what bench.py times): ~55 due tiles in every launch
+    (16384, 100, True, "strided", True),
+    (4096, 50, False, "strided", False),    # c2: 4.6 tiles per CTA, strided lists by default
+])
+def test_full_size_sampled_envs_match_oracle(n_envs, n, interp, tiles, stagger):
     """BASELINE configs 4 and 2 at full size: 64 sampled clusters against the oracle, every output, 160 steps."""
     import torch
     import mdr_b200
@@ -118,6 +129,7 @@ def test_full_size_sampled_envs_match_oracle(n_envs, n, interp):
     pop = mdr_b200.synthetic_population(flat, n_envs, seed=31)
     table = gu.synthetic_table() if interp else None
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
+    env.set_launch_options(static_tiles=(tiles == "strided"))
     geo = env.launch_geometry()
     assert geo["kernel"].startswith("mdr::step_pipe_kernel")
     g = geo["envs_per_cta"]
@@ -134,6 +146,9 @@ def test_full_size_sampled_envs_match_oracle(n_envs, n, interp):
         oracle.grid_step(k, orc.to_datetime(oracle.s["t_epoch"][k]), sgn0[e])
     obs0 = env.reset_tensor(signal_noise=sgn0)
     np.testing.assert_allclose(obs0[np.asarray(ids)].cpu().numpy(), oracle.obs(), **TOL_OBS)
+    if stagger:  # like a rollout whose clusters were reset at different times (bench.py's default)
+        env.stagger_interp_clock(seed=30)
+        oracle.s["time_since_interp"][:] = env.time_since_interp[np.asarray(ids)].cpu().numpy()
     gen = torch.Generator(device="cuda").manual_seed(33)
     for t in range(steps):
         act = (torch.rand(n_envs, n, device="cuda", generator=gen) < 0.5).to(torch.uint8)

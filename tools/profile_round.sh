@@ -5,6 +5,9 @@ tag=${1:-r02}
 timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/pytest_gpu_$tag.log; cat gpurun_out/pytest_gpu_$tag.log
 timeout 400 python bench.py > gpurun_out/bench_c4_$tag.json 2> gpurun_out/bench_c4_$tag.err
 timeout 300 python bench.py --in-phase --no-cpu-baseline > gpurun_out/bench_c4_inphase_$tag.json 2> gpurun_out/bench_c4_inphase_$tag.err
+# the pipelined kernel's other schedule (fixed strided tile list per CTA instead of in-order claiming), same box
+MDR_STATIC_TILES=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_c4_strided_$tag.json 2> gpurun_out/bench_c4_strided_$tag.err
+MDR_STATIC_TILES=1 timeout 300 python bench.py --in-phase --no-cpu-baseline > gpurun_out/bench_c4_strided_inphase_$tag.json 2> gpurun_out/bench_c4_strided_inphase_$tag.err
 timeout 300 python bench.py --serial-e2e --no-cpu-baseline --steps 100 --warmup 10 > gpurun_out/bench_c4_serial_e2e_$tag.json 2> gpurun_out/bench_c4_serial_e2e_$tag.err
 for w in c2 c2actor c1 c3 c3big c3fused; do
   timeout 300 python bench.py --workload $w --no-cpu-baseline > gpurun_out/bench_${w}_$tag.json 2> gpurun_out/bench_${w}_$tag.err
@@ -31,6 +34,8 @@ cp profiles/traffic.json gpurun_out/traffic_$tag.json 2>/dev/null
 # traces (needs variants/lib_trace.so: nvcc ... -DMDR_TRACE -DMDR_TRACE_CTA=100)
 if [ -f variants/lib_trace.so ]; then
   for w in c4 c2 c3big; do MDR_LIB_PATH=$PWD/variants/lib_trace.so timeout 200 python tools/trace_tile.py $w > gpurun_out/trace_${w}_$tag.log 2>&1; done
+  MDR_STATIC_TILES=1 MDR_LIB_PATH=$PWD/variants/lib_trace.so timeout 200 python tools/trace_tile.py c4 > gpurun_out/trace_c4_strided_$tag.log 2>&1
+  MDR_TRACE_STAGGER=0 MDR_LIB_PATH=$PWD/variants/lib_trace.so timeout 200 python tools/trace_tile.py c4 > gpurun_out/trace_c4_inphase_$tag.log 2>&1
 fi
 g++ -O3 -std=c++17 -pthread -o /tmp/expand_bw tools/microbench/expand_bw.cpp 2>/dev/null && {
   nproc; lscpu | grep -E "Model name|Socket|NUMA node\(s\)|Thread" ;
@@ -40,7 +45,7 @@ g++ -O3 -std=c++17 -pthread -o /tmp/expand_bw tools/microbench/expand_bw.cpp 2>/
 python - "$tag" <<'PY'
 import json, sys
 tag=sys.argv[1]
-for w in ("c4","c4_inphase","c4_serial_e2e","c4_driver","c2","c2actor","c1","c3","c3big","c3fused","c0","reference","reference_c1"):
+for w in ("c4","c4_inphase","c4_strided","c4_strided_inphase","c4_serial_e2e","c4_driver","c2","c2actor","c1","c3","c3big","c3fused","c0","reference","reference_c1"):
     try:
         d=json.load(open("gpurun_out/bench_%s_%s.json"%(w,tag)))
         r=d.get("roofline") or {}
