@@ -121,8 +121,8 @@ __device__ __forceinline__ double clip_axis(const G& p, int d, double v) {
 }
 
 template <typename R, typename G>
-__device__ __noinline__ double interp_eval_grid(const G& p, const void* table_v, int key, double air, double mass, double od,
-                                                double hour, double date) {
+__device__ __forceinline__ double interp_eval_grid_body(const G& p, const void* table_v, int key, double air, double mass,
+                                                        double od, double hour, double date) {
   const int dims[5] = {4, 5, 6, 8, 9};
   const double x[5] = {clip_axis(p, 4, air), clip_axis(p, 5, mass), clip_axis(p, 6, od), clip_axis(p, 8, hour),
                        clip_axis(p, 9, date)};
@@ -169,6 +169,14 @@ __device__ __noinline__ double interp_eval_grid(const G& p, const void* table_v,
     value = add_rn(value, mul_rn((double)corner[c], weight));
   }
   return value;
+}
+
+// Out of line (the step kernels' hot loops must not carry its 40-odd registers; inlining the body into the pipelined
+// kernel's refresh was tried and spilled twice as much under that kernel's 80-register cap).
+template <typename R, typename G>
+__device__ __noinline__ double interp_eval_grid(const G& p, const void* table_v, int key, double air, double mass, double od,
+                                                double hour, double date) {
+  return interp_eval_grid_body<R, G>(p, table_v, key, air, mass, od, hour, date);
 }
 
 template <typename R>
@@ -1338,7 +1346,7 @@ size_t pipe_smem_layout(KernelParams* kp, int hmax, int genvs, int n_houses, int
   const size_t off_msg = o;   o += align16((size_t)2 * genvs * (n_houses + n_comm) * 4 * sizeof(float));
   const size_t off_pw = o;    o += align16((size_t)2 * genvs * part_stride * sizeof(double));
   const size_t off_met = o;   o += align16((size_t)2 * genvs * part_stride * 5 * sizeof(float));  // metric partials
-  const size_t off_val = o;   o += need_val ? align16(((size_t)hmax + (size_t)genvs * 32) * sizeof(double)) : 0;  // values | per-env partial sums
+  const size_t off_val = o;   o += need_val ? align16(((size_t)hmax + (size_t)genvs * 40) * sizeof(double)) : 0;  // values | per-env partial sums | per-env scalars
   const size_t off_grid = o;  o += need_val ? align16(sizeof(InterpGrid)) : 0;
   const size_t off_env = o;   o += align16((size_t)(pro_batch < 2 ? 4 : 2 * pro_batch) * genvs * sizeof(PipeEnv));  // (in-order claiming: 4 slots)
   const size_t off_ctl = o;   o += align16(sizeof(PipeCtl));

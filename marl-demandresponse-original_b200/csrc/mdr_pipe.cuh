@@ -263,14 +263,9 @@ __device__ __noinline__ void pro_all_tiles(const KernelParams& p, int warp_g, in
     const int le2 = first + grp;
     const bool valid = tile_valid && le2 < genvs;
     const int lec = le2 < genvs ? le2 : genvs - 1;
-    PipeEnv rec;
-    my_due |= env_prologue<true>(p, unused, rec, env0 + lec, sub, L, valid, false, false);
-    if (valid && sub == 0) {
-      uint4* dst = reinterpret_cast<uint4*>(recs + env0 + lec);
-      const uint4* src = reinterpret_cast<const uint4*>(&rec);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) __stcg(dst + i, src[i]);
-    }
+    // (fields stored one by one: a local record costs this function sixteen registers it does not have -- it is compiled
+    //  under the step kernel's 80-register cap, and its spills are L2 round trips here)
+    my_due |= env_prologue<true>(p, unused, recs[env0 + lec], env0 + lec, sub, L, valid, false, false);
   }
   const unsigned due_ballot = __ballot_sync(0xffffffffu, my_due != 0);
   if (tile_valid && tlane == 0) {
@@ -313,6 +308,7 @@ __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int til
   const bool active = tid < H;
   const int e = tile * G + le;
   const unsigned h = (unsigned)tile * (unsigned)GN + (unsigned)tid;
+  MDR_STAMP_AT(tid >> 5, MDR_TRACE_TILES - 1, 0);  // (trace builds: the refresh's own timeline in the last row)
   // Everything that depends on nothing else is loaded up front, in flight together: under the observation write stream
   // a dependent global round trip costs 2-3 us, and the refresh is nothing but a chain of them (it took 18 us per tile
   // with the loads issued where their values were needed).
@@ -322,12 +318,15 @@ __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int til
   const bool head = active && li == 0;
   const bool need_clock = head || (active && p.solar);
   const uint32_t t_ep = need_clock ? (uint32_t)__ldcg(p.t_epoch + e) : 0u;
-  double sig_noise = 0.0, ratio = 0.0, max_power = 0.0, cpow = 0.0;
+  // (the env's first thread parks what it needs after the table walk in shared memory: registers are what this function
+  //  lacks -- it runs under the step kernel's 80-register cap and a spill is an L2 round trip here)
+  double* const s_head = s_val + T + G * 32 + le * 8;
   if (head) {
-    sig_noise = __ldcg(p.base_power + e);  // parked by the prologue
-    ratio = p.artificial_ratio[e];
-    max_power = p.max_power[e];
-    if (p.metrics != nullptr) cpow = __ldcg(p.cluster_power + e);
+    s_head[0] = __ldcg(p.base_power + e);  // perlin value parked by the prologue
+    s_head[1] = p.artificial_ratio[e];
+    s_head[2] = p.max_power[e];
+    s_head[3] = p.metrics != nullptr ? __ldcg(p.cluster_power + e) : 0.0;
+    s_head[4] = (double)t_ep;
   }
   const bool direct = N <= nb;  // every house is sampled: thread li evaluates house li
   float2 t2 = make_float2(0.f, 0.f);
@@ -365,8 +364,10 @@ __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int til
     val = interp_eval_grid<float, InterpGrid>(*reinterpret_cast<const InterpGrid*>(smem_raw + p.off_grid), p.interp_table,
                                               key, (double)t2.x - tg, (double)t2.y - tg, od_new - tg, hour_s, date);
   }
+  MDR_STAMP_AT(tid >> 5, MDR_TRACE_TILES - 1, 1);
   s_val[tid] = val;  // 0 for houses that are not sampled
   house_sync(T);
+  MDR_STAMP_AT(tid >> 5, MDR_TRACE_TILES - 1, 2);
   // per-env sum by the env's first 32 threads (the fp32 mode's tolerance does not need the reference's id order here --
   // the fp64 kernels keep it)
   if (due && li < 32) {
@@ -380,18 +381,21 @@ __device__ __forceinline__ void pipe_refresh_tile(const KernelParams& p, int til
     const int np = nsamp < 32 ? nsamp : 32;
     for (int i = 0; i < np; ++i) base += s_val[T + le * 32 + i];
     if (N > nb) base = mul_rn(base, (double)N / (double)nb);
-    const Calendar cal = calendar_time(t_ep);
+    const Calendar cal = calendar_time((uint32_t)s_head[4]);
     const int time_sec = cal.hour * 3600 + cal.minute * 60 + cal.second;
-    const double sig = grid_signal(p, base, time_sec, sig_noise, ratio, max_power);
+    const double sig = grid_signal(p, base, time_sec, s_head[0], s_head[1], s_head[2]);
     p.base_power[e] = base;
     p.time_since_interp[e] = 0;
     p.signal[e] = sig;
     s_fsig[le] = (float)(sig * p.inv_norm_sig_agents);
     // the tile loop left the signal-dependent accumulators of a due env to this pass (its signal was not final)
-    if (p.metrics != nullptr) metrics_signal_terms(p.metrics + (size_t)e * MDR_N_METRICS, sig, cpow);
+    if (p.metrics != nullptr) metrics_signal_terms(p.metrics + (size_t)e * MDR_N_METRICS, sig, s_head[3]);
   }
+  MDR_STAMP_AT(tid >> 5, MDR_TRACE_TILES - 1, 3);
   if (kOwn && (tid & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every warp's rows have landed ...
+  MDR_STAMP_AT(tid >> 5, MDR_TRACE_TILES - 1, 4);
   house_sync(T);                                                                           // ... before anybody patches one
+  MDR_STAMP_AT(tid >> 5, MDR_TRACE_TILES - 1, 5);
   if (due && p.obs != nullptr) reinterpret_cast<float*>(p.obs)[(size_t)h * p.F + 9] = s_fsig[le];
   // (s_val / s_fsig are reused by the next tile: its first writes come after this tile's last reads of the same
   //  thread's entries, and its first barrier orders the rest)
