@@ -53,18 +53,22 @@ WORKLOADS = {
                     desc="BASELINE config 3 through the fused multi-step kernel: 1M houses (10000 clusters x 100), 75 env "
                          "steps (5 simulated minutes) per launch with the house state in registers, on-device bang-bang + "
                          "deploy metrics; scored with the per-step 67 B/house-step, flagged fused-K (not an HBM figure)"),
-    "c3big": dict(envs=1000, houses=1000, interp=False, action_source="bangbang", obs=False,
-                  desc="BASELINE config 3 as 1000 clusters x 1000 houses"),
+    "c3big": dict(envs=1000, houses=1000, interp=False, action_source="bangbang", obs=False, launch_batch=25,
+                  desc="BASELINE config 3 as 1000 clusters x 1000 houses (one CTA walks a whole cluster; 25 env steps per C "
+                       "call: one python call per step is slower than the kernel)"),
 }
 
 
-def workload_config(w):
+def workload_config(w, variant=None):
+    """`variant` (bench.py --solar / --comm-defect P): non-default settings that stay on the pipelined kernel."""
     import mdr_b200
     cfg = mdr_b200.make_default_config()
     ep = cfg["default_env_prop"]
     ep["cluster_prop"]["nb_agents"] = w["houses"]
     ep["power_grid_prop"]["base_power_mode"] = "interpolation" if w["interp"] else "constant"
-    cfg["default_house_prop"]["solar_gain_bool"] = False  # both reference CLIs force solar gain off
+    cfg["default_house_prop"]["solar_gain_bool"] = bool(variant and variant.get("solar"))  # both reference CLIs force it off
+    if variant and variant.get("comm_defect"):
+        ep["cluster_prop"]["comm_defect_prob"] = float(variant["comm_defect"])  # message drops (:992), Philox on the device
     return cfg
 
 
@@ -75,6 +79,9 @@ def config_block(args, w):
             "obs_features": 51 if obs else 0, "precision": args.precision,
             "base_power": ("interpolation (synthetic table, refresh every 75 steps, %s clocks)"
                            % ("in-phase" if getattr(args, "in_phase", False) else "staggered")) if w["interp"] else "constant",
+            "variant": ", ".join(x for x in ("solar gain on" if getattr(args, "solar", False) else "",
+                                             "comm_defect_prob %g" % args.comm_defect if getattr(args, "comm_defect", 0) else "",
+                                             "device metrics on" if getattr(args, "metrics", False) else "") if x) or "default",
             "actions": ("seeded Actor(51,2,[100,100]) on device" if w.get("actor") else
                         "python bang-bang per house" if w.get("dict_api") else
                         "uint8 [E,N] tensors" if w["action_source"] == "array" else w["action_source"])}
@@ -254,7 +261,8 @@ def gpu_arm(args):
         return dict_api_arm(args, w, dev)
     E = args.envs or w["envs"]
     N = w["houses"]
-    cfg = workload_config(w)
+    variant = {"solar": args.solar, "comm_defect": args.comm_defect, "metrics": args.metrics}
+    cfg = workload_config(w, variant)
     flat = mdr_b200.FlatConfig(cfg)
     pop = mdr_b200.synthetic_population(flat, E, seed=1234 + rank)
     table = mdr_b200.synthetic_interp_table() if w["interp"] else None
@@ -274,8 +282,8 @@ def gpu_arm(args):
     if chunk > 1:
         args.steps = max(chunk, (args.steps // chunk) * chunk)
         args.warmup = max(chunk, -(-args.warmup // chunk) * chunk)
-    if fused > 1:
-        env.enable_metrics()
+    if fused > 1 or args.metrics:
+        env.enable_metrics()   # the 13 deploy / training accumulators on the device (main-deploy.py:124-209)
     collector = actor = None
     if rollout:
         torch.manual_seed(1)
@@ -426,7 +434,10 @@ def gpu_arm(args):
                          "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_house_step": algo,
                          "kernel": geom["kernel"], "launch_us": launch_s * 1e6 * fused, "fused_k": fused,
                          "note": ("fused-K: the house state never leaves the SM between the K steps; `achieved` is nominal "
-                                  "(SURVEY 8d scoring rule), not HBM utilisation") if fused > 1 else None},
+                                  "(SURVEY 8d scoring rule), not HBM utilisation") if fused > 1 else
+                                 ("per-step working set %.0f MB fits the 126 MB L2: state and parameters are re-read from L2, so "
+                                  "`achieved` (algorithmic bytes / launch time) is nominal, not HBM utilisation"
+                                  % (algo * E * N / 1e6)) if algo * E * N <= 126e6 else None},
             "cpu_baseline": cpu,
         }
         if rollout:
@@ -511,6 +522,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--in-phase", action="store_true", help="keep every cluster's interpolation clock in phase (all refresh on the "
                     "same step, once per 75 steps) instead of staggering them (round-1 behaviour, for comparison)")
+    ap.add_argument("--solar", action="store_true", help="solar gain on (config.py's default; the reference CLIs force it off)")
+    ap.add_argument("--comm-defect", type=float, default=0.0, help="comm_defect_prob > 0: message drops drawn on the device")
+    ap.add_argument("--metrics", action="store_true", help="accumulate the deploy / training metrics on the device in every step")
     ap.add_argument("--serial-e2e", action="store_true", help="e2e leg without the MdrHostCtx pipeline (one H2D, one launch, four D2H)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -265,7 +265,8 @@ int mdr_validate(const MdrConfig *cfg);
 
 /* Launch geometry the step kernel will use (for tests and the roofline report).  `ctas` counts the
    G-env tiles; `pipelined` is 1 when a plain production-mode step of this configuration runs the
-   persistent software-pipelined kernel (grid = SMs x resident CTAs, looping over the tiles);
+   persistent software-pipelined kernel (grid = SMs x resident CTAs, looping over the tiles), 2 when -- without an
+   observation, on clusters of 225 .. 8 192 houses -- one CTA walks a whole env (no inter-CTA traffic at all);
    `cluster_size` > 1 when one env is split over the CTAs of a thread-block cluster (N > 224: cluster power and
    penalties cross the CTAs through distributed shared memory, ClusterHouses.step :1005-1055 for any nb_agents). */
 int mdr_launch_geometry(const MdrConfig *cfg, int has_obs, int32_t *envs_per_cta, int32_t *threads,

@@ -7,7 +7,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.path.join(CSRC, "libmdr_b200.so")
 SOURCES = ("mdr_kernels.cu", "mdr_abi.cu", "mdr_host.cu")
-HEADERS = ("mdr_kernels.h", "mdr_device.cuh", "mdr_pipe.cuh", "mdr_pipe_split.cuh", "mdr_pipe_split_host.cuh", "mdr_fused.cuh", "mdr_populate.cuh", "mdr_big.cuh", "mdr_rollout.cuh", "mdr_compact.cuh", "mdr_expand.h",
+HEADERS = ("mdr_kernels.h", "mdr_device.cuh", "mdr_pipe.cuh", "mdr_pipe_split.cuh", "mdr_pipe_split_host.cuh", "mdr_fused.cuh", "mdr_populate.cuh", "mdr_big.cuh", "mdr_wide.cuh", "mdr_rollout.cuh", "mdr_compact.cuh", "mdr_expand.h",
            os.path.join("..", "..", "include", "mdr_b200.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]

@@ -276,6 +276,13 @@ extern "C" int mdr_launch_geometry(const MdrConfig* cfg, int has_obs, int32_t* e
                     (mdr::pipe_eligible(k, g, cfg->precision) || (k.comm_defect_prob <= 0.0 && mdr::pipe_split_eligible(k, g, cfg->precision)));
   if (smem_bytes) *smem_bytes = pipe ? g.pipe_smem_bytes : g.smem_bytes;
   if (pipelined) *pipelined = pipe ? 1 : 0;
+  if (!has_obs && !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::wide_eligible(k)) {  // one CTA per env (mdr_wide.cuh)
+    if (envs_per_cta) *envs_per_cta = 1;
+    if (threads) *threads = 256;
+    if (ctas) *ctas = cfg->n_envs;
+    if (cluster_size) *cluster_size = 1;
+    if (pipelined) *pipelined = 2;
+  }
   return MDR_OK;
 }
 
@@ -468,7 +475,7 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     return MDR_OK;
   }
   // Geometry: whole envs per CTA (N <= 1024) is what the fused multi-step kernel needs; otherwise an env of more
-  // than 224 houses is split over a thread-block cluster.
+  // than 224 houses is split over a thread-block cluster -- or, without an observation, walked by one CTA (mdr_wide.cuh).
   Geometry g;
   bool fused = false;
   if (cfg->n_houses <= MDR_MAX_HOUSES_PER_ENV) {
@@ -476,6 +483,16 @@ static int run_steps(const MdrConfig* cfg, const MdrHouses* houses, const MdrEnv
     if (st != MDR_OK) return st;
     fused = !(cfg->flags & MDR_FLAG_NO_FUSED) && mdr::fused_eligible(k) && g.pro_warp >= g.house_warps &&
             (n_steps > 1 || k.metrics != nullptr);
+  }
+  if (!fused && !(cfg->flags & MDR_FLAG_NO_PIPELINE) && mdr::wide_eligible(k)) {
+    cudaError_t werr = cudaSetDevice(cfg->device);
+    if (werr != cudaSuccess) return cuda_fail(werr);
+    for (int i = 0; i < n_steps; ++i) {
+      werr = mdr::launch_wide(k, cfg->precision, (cfg->flags & MDR_FLAG_NO_PDL) != 0, stream);
+      if (werr != cudaSuccess) return cuda_fail(werr);
+      k.step_index += 1;
+    }
+    return MDR_OK;
   }
   if (!fused) {
     st = choose_geometry(cfg, out->obs != nullptr, &g, k.metrics != nullptr, true);

@@ -1303,6 +1303,7 @@ cudaError_t launch_pipe(const KernelParams& kp, const Geometry& g, cudaStream_t 
 }
 
 #include "mdr_pipe_split_host.cuh"
+#include "mdr_wide.cuh"
 
 // tiles per prologue pass (power of two): as deep as the lanes (one per env at least), the ring
 // (kMaxRing slots) and the shared-memory budget (the observation staging tile is the big consumer)

@@ -99,6 +99,8 @@ cudaError_t launch_populate(const KernelParams& kp, const MdrPopulationSpec& spe
                             int precision, uint64_t draw_index, cudaStream_t stream);
 bool fused_eligible(const KernelParams& kp);
 cudaError_t launch_big(const KernelParams& kp, int precision, void* workspace, cudaStream_t stream);
+bool wide_eligible(const KernelParams& kp);  // mdr_wide.cuh: one CTA per env of 225..8192 houses, no observation
+cudaError_t launch_wide(const KernelParams& kp, int precision, bool no_pdl, cudaStream_t stream);
 size_t big_workspace(int n_envs, int n_houses);
 inline size_t due_queue_bytes(int n_envs) { return (64 + 4 * (size_t)n_envs + 63) & ~(size_t)63; }  // header + a word per tile
 // Scratch of ONE pipelined launch in MdrEnvs.workspace: [due-tile queue (strided lists) | claim header (64 B) | a due

@@ -283,12 +283,15 @@ __device__ __noinline__ void pro_all_tiles(const KernelParams& p, int warp_g, in
 // loop, same launch, same CTA, same tile order -- evaluates the table on the houses' NEW state,
 // re-evaluates the signal and patches observation feature 9 (the only output that depends on it).
 // signal-dependent metric accumulators of one env and step (MDR_M_SUM_SIGNAL ..., main-deploy.py:140-149)
+// (Accumulators are advanced with reductions at L2 -- RED.ADD.F64, no value comes back: a load-add-store by the env's
+//  first thread put a 1-2 us global round trip per tile on that warp's critical path, 126 instead of 92 us per c4 step.
+//  One contributor per env and launch, launches in stream order: the sums are the same bits as a read-modify-write.)
 __device__ __forceinline__ void metrics_signal_terms(double* m, double sig, double P) {
-  const double d = sig - P;  // (read-modify-write through L2: a due env's terms may be added by another SM's CTA)
-  __stcg(m + MDR_M_SUM_SIGNAL, __ldcg(m + MDR_M_SUM_SIGNAL) + sig);
-  __stcg(m + MDR_M_SUM_SIGNAL_OFFSET, __ldcg(m + MDR_M_SUM_SIGNAL_OFFSET) + d);
-  __stcg(m + MDR_M_SUM_SIGNAL_ERROR, __ldcg(m + MDR_M_SUM_SIGNAL_ERROR) + fabs(d));
-  __stcg(m + MDR_M_SUM_SQ_SIGNAL_ERROR, __ldcg(m + MDR_M_SUM_SQ_SIGNAL_ERROR) + d * d);
+  const double d = sig - P;
+  atomicAdd(m + MDR_M_SUM_SIGNAL, sig);
+  atomicAdd(m + MDR_M_SUM_SIGNAL_OFFSET, d);
+  atomicAdd(m + MDR_M_SUM_SIGNAL_ERROR, fabs(d));
+  atomicAdd(m + MDR_M_SUM_SQ_SIGNAL_ERROR, d * d);
 }
 
 
@@ -861,15 +864,16 @@ restart:
       const double mx = (double)mxf, Pd = (double)P;
       const double dn = (Pd - pe.s_old) * p.inv_n;
       double* m = p.metrics + (size_t)e * MDR_N_METRICS;
-      m[MDR_M_STEPS] += 1.0;
-      m[MDR_M_SUM_MEAN_REWARD] += -(t[0] * p.inv_n * p.k_temp + dn * dn * p.k_sig);
-      m[MDR_M_SUM_MEAN_TEMP_OFFSET] += t[1] * p.inv_n;
-      m[MDR_M_SUM_MEAN_TEMP_ERROR] += t[2] * p.inv_n;
-      m[MDR_M_SUM_SQ_TEMP_ERROR] += t[3];
-      m[MDR_M_SUM_SQ_MAX_TEMP_ERROR] += mx * mx;
-      m[MDR_M_MAX_TEMP_ERROR] = fmax(m[MDR_M_MAX_TEMP_ERROR], mx);
-      m[MDR_M_SUM_OD_TEMP] += pe.od_new;
-      m[MDR_M_SUM_CONSUMPTION] += Pd;
+      atomicAdd(m + MDR_M_STEPS, 1.0);
+      atomicAdd(m + MDR_M_SUM_MEAN_REWARD, -(t[0] * p.inv_n * p.k_temp + dn * dn * p.k_sig));
+      atomicAdd(m + MDR_M_SUM_MEAN_TEMP_OFFSET, t[1] * p.inv_n);
+      atomicAdd(m + MDR_M_SUM_MEAN_TEMP_ERROR, t[2] * p.inv_n);
+      atomicAdd(m + MDR_M_SUM_SQ_TEMP_ERROR, t[3]);
+      atomicAdd(m + MDR_M_SUM_SQ_MAX_TEMP_ERROR, mx * mx);
+      // (mx >= 0: non-negative doubles order like their bit patterns)
+      atomicMax(reinterpret_cast<unsigned long long*>(m + MDR_M_MAX_TEMP_ERROR), (unsigned long long)__double_as_longlong(mx));
+      atomicAdd(m + MDR_M_SUM_OD_TEMP, pe.od_new);
+      atomicAdd(m + MDR_M_SUM_CONSUMPTION, Pd);
       if (!pe.due) metrics_signal_terms(m, pe.sig_new, Pd);  // a due env: after its refresh (pipe_refresh_pass)
     }
     if (kObs && active) {

@@ -390,15 +390,16 @@ __global__ void __launch_bounds__(256, 3) step_pipe_split_kernel(const __grid_co
       const double mx = (double)mxf, Pd = (double)P;
       const double dn = (Pd - pe->s_old) * p.inv_n;
       double* m = p.metrics + (size_t)e * MDR_N_METRICS;
-      m[MDR_M_STEPS] += 1.0;
-      m[MDR_M_SUM_MEAN_REWARD] += -(t[0] * p.inv_n * p.k_temp + dn * dn * p.k_sig);
-      m[MDR_M_SUM_MEAN_TEMP_OFFSET] += t[1] * p.inv_n;
-      m[MDR_M_SUM_MEAN_TEMP_ERROR] += t[2] * p.inv_n;
-      m[MDR_M_SUM_SQ_TEMP_ERROR] += t[3];
-      m[MDR_M_SUM_SQ_MAX_TEMP_ERROR] += mx * mx;
-      m[MDR_M_MAX_TEMP_ERROR] = fmax(m[MDR_M_MAX_TEMP_ERROR], mx);
-      m[MDR_M_SUM_OD_TEMP] += pe->od_new;
-      m[MDR_M_SUM_CONSUMPTION] += Pd;
+      // (reductions at L2 instead of load-add-store round trips, see metrics_signal_terms)
+      atomicAdd(m + MDR_M_STEPS, 1.0);
+      atomicAdd(m + MDR_M_SUM_MEAN_REWARD, -(t[0] * p.inv_n * p.k_temp + dn * dn * p.k_sig));
+      atomicAdd(m + MDR_M_SUM_MEAN_TEMP_OFFSET, t[1] * p.inv_n);
+      atomicAdd(m + MDR_M_SUM_MEAN_TEMP_ERROR, t[2] * p.inv_n);
+      atomicAdd(m + MDR_M_SUM_SQ_TEMP_ERROR, t[3]);
+      atomicAdd(m + MDR_M_SUM_SQ_MAX_TEMP_ERROR, mx * mx);
+      atomicMax(reinterpret_cast<unsigned long long*>(m + MDR_M_MAX_TEMP_ERROR), (unsigned long long)__double_as_longlong(mx));
+      atomicAdd(m + MDR_M_SUM_OD_TEMP, pe->od_new);
+      atomicAdd(m + MDR_M_SUM_CONSUMPTION, Pd);
       metrics_signal_terms(m, sig_new, Pd);
     }
     if (kObs && active) {

@@ -520,7 +520,8 @@ class VecDemandResponseEnv:
         _lib.check(self.lib.mdr_launch_geometry(self._refs[0], int(self.with_obs), C.byref(g), C.byref(t), C.byref(c),
                                                 C.byref(s), C.byref(pl), C.byref(cl)), "mdr_launch_geometry")
         return dict(envs_per_cta=g.value, threads=t.value, tiles=c.value, smem_bytes=s.value, cluster_size=cl.value,
-                    kernel=("mdr::step_pipe_split_kernel (persistent, software-pipelined, env split over a cluster)"
+                    kernel="mdr::step_wide_kernel (one CTA walks a whole env, no observation)" if pl.value == 2 else
+                    ("mdr::step_pipe_split_kernel (persistent, software-pipelined, env split over a cluster)"
                             if pl.value and cl.value > 1 else "mdr::step_pipe_kernel (persistent, software-pipelined)") if pl.value else
                     ("mdr::big_update/env/finish_kernel (three launches)" if cl.value == 0 else "mdr::step_kernel"))
 

@@ -104,6 +104,67 @@ def test_split_env_matches_oracle(n_envs, n, kw, precision):
         np.testing.assert_allclose(m[:, 1], sum_rew, rtol=1e-4 if precision == "fp32" else 1e-9, atol=1e-6)
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("n_envs,n,source,kw", [
+    (70, 225, "array", dict()),                                             # smallest env of the wide kernel
+    (64, 1000, "bangbang", dict(solar=True)),                               # c3big's shape: on-device bang-bang, solar gain on
+    (80, 777, "array", dict(interp=True, signal="sinusoidals")),            # sampled interpolation ids (N > 100), 3.5 sub-tiles
+    (64, 4096, "array", dict(interp=True, signal="regular_steps")),         # 18.3 sub-tiles per CTA
+])
+def test_wide_kernel_without_observation_matches_oracle(n_envs, n, source, kw, precision):
+    """No observation, clusters of 225 .. 8 192 houses: one CTA walks a whole env (mdr::step_wide_kernel) -- against the
+    oracle on state, power, signal, base power and reward, and bit for bit against the generic kernel."""
+    import torch
+    import mdr_b200
+    cfg, flat, pop = _case(n_envs, n, 900 + n, **kw)
+    interp = kw.get("interp", False)
+    steps = 80 if interp else 12
+    table = gu.synthetic_table() if interp else None
+    mk = lambda: mdr_b200.VecDemandResponseEnv(cfg, pop, precision=precision, interp_table=table, action_source=source,
+                                               with_obs=False)
+    env, ref = mk(), mk()
+    env.set_launch_options(no_fused=True)
+    ref.set_launch_options(no_fused=True, no_pipeline=True)   # generic kernel (split over a cluster)
+    assert env.launch_geometry()["kernel"].startswith("mdr::step_wide_kernel"), env.launch_geometry()
+    assert ref.launch_geometry()["kernel"] == "mdr::step_kernel", ref.launch_geometry()
+    oracle = orc.OracleEnv(cfg, {k: v for k, v in pop.items() if k != "perlin_seed"},
+                           interp=orc.PowerInterp(table, gu.INTERP_GRID, gu.INTERP_KEYS) if interp else None)
+    rng = np.random.default_rng(950 + n)
+    draw = lambda: dict(sgn=rng.uniform(-0.5, 0.5, n_envs), ids=rng.integers(0, n, (n_envs, flat.interp_nb_agents)).astype(np.int32))
+    d = draw()
+    for e in range(n_envs):
+        oracle.grid_step(e, orc.to_datetime(oracle.s["t_epoch"][e]), d["sgn"][e], d["ids"][e])
+    env.reset_tensor(signal_noise=d["sgn"], interp_ids=d["ids"])
+    ref.reset_tensor(signal_noise=d["sgn"], interp_ids=d["ids"])
+    tol, tolw = TOL[precision], TOL_W[precision]
+    for t in range(steps):
+        d = draw()
+        odn = rng.normal(0, 0.5, n_envs)
+        if source == "array":
+            act = rng.integers(0, 2, (n_envs, n)).astype(np.uint8)
+        else:
+            # bangbang_controllers.py:50-61 on the kernel's own operands (the target as stored in the working precision)
+            act = (env.temps[..., 0] > env.coef_b[..., 3]).to(torch.uint8).cpu().numpy()
+        o_obs, o_rew, o_p, o_s = oracle.step(act, odn, d["sgn"], d["ids"])
+        a_in = act if source == "array" else None
+        _, rew, p, s = env.step_tensor(a_in, od_noise=odn, signal_noise=d["sgn"], interp_ids=d["ids"])
+        _, rew_g, p_g, s_g = ref.step_tensor(a_in, od_noise=odn, signal_noise=d["sgn"], interp_ids=d["ids"])
+        assert np.array_equal(env.hvac_on.cpu().numpy(), oracle.s["on"]), t
+        assert np.array_equal(env.hvac_lockout.cpu().numpy(), oracle.s["lockout"]), t
+        assert np.array_equal(env.seconds_since_off.cpu().numpy(), oracle.s["sso"]), t
+        assert np.array_equal(p.cpu().numpy(), o_p), t
+        np.testing.assert_allclose(s.cpu().numpy(), o_s, err_msg="signal %d" % t, **tolw)
+        np.testing.assert_allclose(env.env["base_power"].cpu().numpy(), oracle.s["base_power"], err_msg="base %d" % t, **tolw)
+        np.testing.assert_allclose(env.t_air.cpu().numpy(), oracle.s["t_air"], err_msg="t_air %d" % t, **tol)
+        np.testing.assert_allclose(env.t_mass.cpu().numpy(), oracle.s["t_mass"], err_msg="t_mass %d" % t, **tol)
+        np.testing.assert_allclose(rew.cpu().numpy(), o_rew, err_msg="reward %d" % t, **tol)
+        assert np.array_equal(env.time_since_interp.cpu().numpy(), oracle.s["time_since_interp"]), t
+        # the same arithmetic as the generic kernel, operation for operation
+        assert torch.equal(env.hvac, ref.hvac) and torch.equal(env.temps, ref.temps), t
+        assert torch.equal(p, p_g) and torch.equal(s, s_g) and torch.equal(rew, rew_g), t
+        assert torch.equal(env.t_epoch, ref.t_epoch) and torch.equal(env.env["od_temp"], ref.env["od_temp"]), t
+
+
 def test_split_equals_single_cta_bitwise():
     """225..1024 houses run either way: one 1024-thread CTA (MDR_FLAG_NO_CLUSTER) or a cluster; integer state and power
     identical, reals to rounding (the penalty mean is summed in a different order)."""
