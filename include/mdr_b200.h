@@ -255,8 +255,11 @@ int mdr_obs_width(const MdrConfig *cfg);
      tiles): the hand-over records of the per-env prologue, a ready flag per tile and the counter from which the CTAs
      claim their tiles in address order, and -- with interpolated base power -- the queue through which the CTAs
      share the tiles whose table refresh is due.  Sized for two launches in flight (mdr_step_host's two streams).
-     In this mode the CTAs of one launch depend on each other and must be co-resident: the grid never exceeds
-     SMs x resident CTAs, so do not run it next to other kernels that hold SMs indefinitely. */
+     In this mode the CTAs of one launch depend on each other (a grid barrier behind the per-env prologue) and must
+     be co-resident: the grid never exceeds SMs x resident CTAs, launches of one stream follow each other, and the
+     hardware dispatches the CTAs of an older grid before those of a younger one.  Do not run it next to kernels that
+     hold SMs indefinitely, and give envs that are stepped concurrently from streams of DIFFERENT priority
+     MDR_FLAG_STATIC_TILES (two half-resident grids would wait for each other; a wait of 2 s traps instead of hanging). */
 int mdr_workspace_bytes(const MdrConfig *cfg, size_t *bytes);
 
 /* Validates cfg (modes, shapes) the way the reference constructors raise ValueError
