@@ -89,6 +89,9 @@ def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_
     table = gu.synthetic_table() if interp else None
     env = mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", interp_table=table)
     env.set_launch_options(max_ctas=max_ctas, static_tiles=(tiles == "strided"))
+    with_metrics = interp and n <= 224   # the accumulator variant of the same kernel (signal terms of due envs come from the refresh)
+    if with_metrics:
+        env.enable_metrics()
     geo = env.launch_geometry()
     assert geo["kernel"].startswith("mdr::step_pipe_split_kernel" if n > 224 else "mdr::step_pipe_kernel")
     assert geo["tiles"] >= 20 * max_ctas, geo
@@ -101,6 +104,7 @@ def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_
     env.precompute()
     ids_all = list(range(n_envs))
     refreshes = 0
+    acc = np.zeros((n_envs, 13))
     for t in range(steps):
         act = rng.integers(0, 2, (n_envs, n)).astype(np.uint8)
         odn, sgn = rng.normal(0, 0.5, n_envs), rng.uniform(-0.5, 0.5, n_envs)
@@ -110,8 +114,30 @@ def test_capped_grid_many_tiles_per_cta(n_envs, n, interp, signal, nb_comm, max_
         refreshes += int((oracle.s["base_power"] != before).sum())
         out = env.step_tensor(act, od_noise=odn, signal_noise=sgn, interp_ids=ids)
         _compare(env, oracle, ids_all, out, o_out, t)
+        # main-deploy.py:124-149 / metrics.py:22-30 on the oracle's outputs
+        err = oracle.s["t_air"] - oracle.s["target"]
+        d = o_out[3] - o_out[2]
+        acc[:, 0] += 1
+        acc[:, 1] += o_out[1].mean(axis=1)
+        acc[:, 2] += err.mean(axis=1)
+        acc[:, 3] += np.abs(err).mean(axis=1)
+        acc[:, 4] += (err ** 2).sum(axis=1)
+        acc[:, 5] += np.abs(err).max(axis=1) ** 2
+        acc[:, 6] = np.maximum(acc[:, 6], np.abs(err).max(axis=1))
+        acc[:, 7] += oracle.s["od_temp"]
+        acc[:, 8] += o_out[3]
+        acc[:, 9] += o_out[2]
+        acc[:, 10] += d
+        acc[:, 11] += np.abs(d)
+        acc[:, 12] += d ** 2
     if interp:
         assert refreshes >= 2 * n_envs
+    if with_metrics:
+        m = env.metrics.cpu().numpy()
+        assert np.array_equal(m[:, 0], acc[:, 0])
+        np.testing.assert_allclose(m[:, [7, 8, 9]], acc[:, [7, 8, 9]], rtol=1e-6)
+        np.testing.assert_allclose(m[:, [1, 2, 3, 4, 5, 6]], acc[:, [1, 2, 3, 4, 5, 6]], rtol=2e-3, atol=1e-4)   # fp32 temperatures
+        np.testing.assert_allclose(m[:, [10, 11, 12]], acc[:, [10, 11, 12]], rtol=1e-4, atol=1.0)
 
 
 @pytest.mark.parametrize("n_envs,n,interp,tiles,stagger", [
