@@ -3,9 +3,11 @@
 #pragma once
 
 // ----------------------------------------------------------------------------------------
-// Persistent, software-pipelined variant of the fast path (fp32, default observation layout,
-// solar gain off, plain steps).  The CTAs stay resident (SMs x CTAs/SM of them) and loop over
-// tiles of G envs:
+// Persistent, software-pipelined variant of the fast path (fp32, default observation layout; solar gain,
+// message drops and the metric accumulators are variants of it).  The CTAs stay resident (SMs x CTAs/SM
+// of them) and loop over tiles of G envs.  Two schedules (template parameter kDyn): a fixed, strided list
+// of tiles per CTA, described first, and tiles claimed in address order (large problems; see "In-order
+// tile claiming" below).  With the strided lists:
 //   * the house threads' inputs of tile i+1 are fetched with cp.async into a second shared-memory
 //     stage while tile i is computed (each thread copies and later reads only its own record, so
 //     cp.async.wait_group is the only synchronisation the inputs need);
@@ -200,19 +202,24 @@ struct DueQueue {
 // process in this CTA, so the hand-over leaves shared memory:
 //   * at the start of the launch ALL warps of the grid (house warps and the prologue warp alike) produce the 64-byte
 //     records of all envs into a global (L2-resident) array -- pro_batch tiles per warp, the same env_prologue code --
-//     plus a `due` word per tile and the launch's due-tile count, and meet at a grid barrier (one arrival per CTA);
-//   * the house warps then take tiles blockIdx, blockIdx + grid, and whatever an atomic counter hands out (claimed two
-//     tiles ahead by thread 0); a few loader threads fetch the tile's records next to the cp.async input stage of the
-//     NEXT tile (cp.async + mbarrier complete, 4-slot ring).
-// Measured alternatives, not kept (16 384 x 100, in-phase refresh clocks, static lists 90.0 us per step):
+//     plus a `due` word per tile and the launch's list of due tiles, and meet at a grid barrier (one arrival per CTA);
+//   * the eighth warp of the CTA then is its CLAIM WARP: it maps positions of the launch's work list to tiles (the
+//     first three of a CTA are fixed, the others come from an atomic counter, claimed three tiles ahead), and for every
+//     position puts the tile id, the tile's `due` word and its records into a 4-slot ring (cp.async + mbarrier
+//     complete); the house warps wait for a slot one tile before they need it -- no global round trip on their path;
+//   * due tiles come first in the work list and are refreshed by the CTA that processed them, between two tiles
+//     (pipe_refresh_own); a due tile met again in address order is skipped.
+// Measured alternatives, not kept (16 384 x 100, in-phase refresh clocks, static lists 90.0 us per step; final: 86.4):
 //   * records from the CTA's own prologue warp (strided slice, no back-pressure) with a ready flag per tile: every
 //     global round trip the house warps depend on (flag, then record) needs a whole tile of slack under the observation
 //     write stream (loaded L2 latency 1-2 us; acquire loads also invalidate L1): 95-116 us;
 //   * a small kernel in front of the step kernel producing all records (512 CTAs, 6.5 us) -- step kernel 73 us, but
-//     13 us from one step kernel to the next: 86.1 us.
+//     13 us from one step kernel to the next: 86.1 us;
+//   * thread 0 of the house warps claiming and a few loader threads copying the records: the claim logic and the
+//     refresh call inside the tile loop cost the loop registers (see pipe_refresh_own).
 // ----------------------------------------------------------------------------------------
 struct DynHdr {
-  unsigned next_tile;  // positions handed out beyond the first two of every CTA
+  unsigned next_tile;  // positions handed out beyond the first three of every CTA
   unsigned exited;     // CTAs that are done claiming (the last one out re-zeroes the header)
   unsigned arrived;    // CTAs that have written their share of the records (grid barrier in front of the tile loop)
   unsigned n_due;      // tiles with an interpolation refresh due in this launch = entries of the due list

@@ -106,6 +106,31 @@ def test_launch_geometry():
     assert lib.mdr_validate(ctypes.byref(s)) == -6  # the on-device greedy controller sorts inside one CTA
 
 
+def test_workspace_size_and_wide_kernel_geometry():
+    """Host-only ABI answers: the scratch of the pipelined kernel (two launches in flight: due-tile queue, claim header,
+    a due word + a due-list entry per tile, a 64-byte record per env) and the kernel a step without observation takes
+    on clusters beyond one tile (one CTA walks a whole env)."""
+    lib = mdr_b200.load_library()
+    cfg = mdr_b200.make_default_config()
+    cfg["default_env_prop"]["power_grid_prop"]["base_power_mode"] = "constant"
+    for n, e, wide in ((100, 16384, False), (1000, 1000, True), (1000, 8, False), (9000, 100, False)):
+        cfg["default_env_prop"]["cluster_prop"]["nb_agents"] = n
+        s = mdr_b200.FlatConfig(cfg).to_struct(e, _lib.F32, 0)
+        need = ctypes.c_size_t()
+        assert lib.mdr_workspace_bytes(ctypes.byref(s), ctypes.byref(need)) == 0
+        r64 = lambda x: (x + 63) // 64 * 64
+        assert need.value >= 2 * (r64(64 + 4 * e) + 64 + 2 * r64(4 * e) + 64 * e), (n, e, need.value)
+        pl, cl, c, t = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        assert lib.mdr_launch_geometry(ctypes.byref(s), 0, None, ctypes.byref(t), ctypes.byref(c), None, ctypes.byref(pl),
+                                       ctypes.byref(cl)) == 0
+        assert (pl.value == 2) == wide, (n, e, pl.value)
+        if wide:
+            assert c.value == e and t.value == 256 and cl.value == 1
+        s.flags = _lib.FLAG_NO_PIPELINE   # tests pin the generic kernel this way
+        assert lib.mdr_launch_geometry(ctypes.byref(s), 0, None, None, None, None, ctypes.byref(pl), None) == 0
+        assert pl.value == 0
+
+
 def test_bad_modes_raise_like_the_reference():
     for path, val in ((("cluster_prop", "agents_comm_mode"), "bogus"),
                       (("reward_prop", "temp_penalty_mode"), "bogus"),
