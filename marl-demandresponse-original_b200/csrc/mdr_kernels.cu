@@ -281,6 +281,14 @@ __global__ void precompute_kernel(const __grid_constant__ KernelParams p) {
 // warps' global loads and thermal update, so its latency (fp64 sin, Philox) is off the
 // critical path.
 // ----------------------------------------------------------------------------------------
+// (trace builds: timeline of the pipelined kernel's per-env prologue, row 22 of the trace buffer; see mdr_pipe.cuh)
+#ifdef MDR_TRACE
+__device__ void trace_stamp_fn(int w, int t, int k);
+#define MDR_PRO_STAMP(k) do { if (kPipe) trace_stamp_fn(threadIdx.x >> 5, 22, k); } while (0)
+#else
+#define MDR_PRO_STAMP(k) do { } while (0)
+#endif
+
 template <bool kPipe>
 __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& es, PipeEnv& pe, int e2, int sub, int L,
                                             bool valid, bool reset, bool observe_only) {
@@ -306,8 +314,10 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
   }
   const double solar_prev = (observe_only && p.solar) ? p.solar_gain[e2] : 0.0;
 
+  MDR_PRO_STAMP(1);
   Calendar cal = calendar_time(t);
   if (p.solar || (p.state_flags & MDR_STATE_DAY)) calendar_date(cal);
+  MDR_PRO_STAMP(2);
   if (draw_od || draw_perlin) {  // warp-uniform
     // utils.Perlin.calculate_noise (utils.py:1247-1253) with hashed lattice gradients: item d < nb is octave d
     // (both lattice corners, see perlin_octave); the last item is the outdoor-temperature normal
@@ -332,6 +342,7 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
     if (draw_perlin) sig_noise = terms;
     if (draw_od) od_noise = p.temp_std * normal;
   }
+  MDR_PRO_STAMP(3);
   double od_new = od_prev;
   if (!reset) {
     // ClusterHouses.compute_OD_temp, :1070-1081 (amplitude, bias and 2*pi/24 folded on the host)
@@ -353,8 +364,10 @@ __device__ __forceinline__ int env_prologue(const KernelParams& p, EnvScratch& e
     due = tsi >= p.interp_update_period;
     if (due) tsi = 0;
   }
+  MDR_PRO_STAMP(4);
   double sig = s_old;
   if (!observe_only && !due) sig = grid_signal(p, base, time_sec, sig_noise, ratio, max_power);
+  MDR_PRO_STAMP(5);
   if (kPipe) {
     // pipelined kernel: the prologue warp owns the per-env outputs that neither depend on the houses
     // nor are read by them (each env belongs to exactly one tile per launch, so running ahead is safe)

@@ -39,6 +39,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
       g_trace[((w) * MDR_TRACE_TILES + (t)) * MDR_TRACE_POINTS + (k)] = global_ns();                  \
   } while (0)
 #define MDR_STAMP(k) MDR_STAMP_AT(warp, it, k)
+__device__ void trace_stamp_fn(int w, int t, int k) { MDR_STAMP_AT(w, t, k); }
 // per-CTA span of the launch: [0] kernel entry, [1] past griddepcontrol.wait, [2] tile loop done, [3] kernel exit
 __device__ unsigned long long g_cta_span[2048 * 8];
 #define MDR_CTA_STAMP(k)                                                                              \
@@ -245,6 +246,10 @@ __device__ __forceinline__ PipeEnv* dyn_recs(const KernelParams& p) {
 // Per-env prologue of a whole step by ALL warps of the step kernel (pro_batch tiles per warp and pass): records into
 // the global array, per-env outputs in place (as the strided lists' prologue warp does), a `due` word per tile and the
 // launch's due-tile count.  `warp_g` / `n_warps`: this warp's index among / the number of warps of the grid.
+// (Out of line.  Its timeline in a trace build, row 22: 1.2 us until the per-env loads are back, 1.7 us of draws --
+//  including a second round trip for the perlin seed; loading it with the others just moved the time -- 0.6 us sinpi,
+//  0.3 us signal, 1.7 us until the record / in-place stores and the due word are out.  Inlining it into the kernel
+//  changed nothing of that and spilled 150 bytes in the kernel.)
 __device__ __noinline__ void pro_all_tiles(const KernelParams& p, int warp_g, int n_warps) {
   const int lane = threadIdx.x & 31;
   // B tiles per warp and pass (pro_batch, a power of two with B * G <= 32), L lanes per env
@@ -258,6 +263,7 @@ __device__ __noinline__ void pro_all_tiles(const KernelParams& p, int warp_g, in
   const int my_k = lane / lanes_per_tile;
   const unsigned group_mask = (lanes_per_tile == 32 ? 0xffffffffu : ((1u << lanes_per_tile) - 1u)) << (my_k * lanes_per_tile);
   PipeEnv* const recs = dyn_recs(p);
+  MDR_STAMP_AT(threadIdx.x >> 5, 22, 0);
   for (int tile0 = warp_g * B; tile0 < p.n_tiles; tile0 += n_warps * B) {
   const int tile = tile0 + my_k;
   const bool tile_valid = tile < p.n_tiles;
@@ -281,6 +287,7 @@ __device__ __noinline__ void pro_all_tiles(const KernelParams& p, int warp_g, in
     if (due) __stcg(dyn_list(p) + atomicAdd(&dyn_hdr(p)->n_due, 1u), (unsigned)tile);  // the launch's due list
   }
   }
+  MDR_STAMP_AT(threadIdx.x >> 5, 22, 6);
 }
 
 // Deferred interpolation refresh (every interp_update_period seconds; PowerGrid.step :1250-1255,
