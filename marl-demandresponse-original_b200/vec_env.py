@@ -52,7 +52,9 @@ class VecDemandResponseEnv:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.seed, self.action_source, self.with_obs = int(seed), action_source, bool(with_obs)
         # L2 residency of the per-house state (None = MDR_L2_PERSIST env var; default OFF: measured 2x slower on c4)
-        self.l2_persist = (os.environ.get("MDR_L2_PERSIST", "0") == "1") if l2_persist is None else bool(l2_persist)
+        # ("table": the window covers the interpolation table instead -- 17 MB that the refreshes gather from)
+        env_l2 = os.environ.get("MDR_L2_PERSIST", "0")
+        self.l2_persist = ("table" if env_l2 == "table" else env_l2 == "1") if l2_persist is None else l2_persist
         self._l2_window = (0, 0, 1.0)
         self._flags, self._max_ctas = 0, 0
         self.n_envs = int(len(np.atleast_1d(population["t_epoch"])))
@@ -214,7 +216,13 @@ class VecDemandResponseEnv:
     def _setup_l2_window(self):
         """Persisting-L2 carve-out + access policy window over the state arena (B200: 126 MB L2)."""
         granted, max_window = C.c_size_t(), C.c_size_t()
-        nbytes = self._arena.numel()
+        target = self._arena
+        if self.l2_persist == "table":
+            if getattr(self, "_table", None) is None:
+                self._l2_window = (0, 0, 1.0)
+                return
+            target = self._table.view(torch.uint8)
+        nbytes = target.numel()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.mdr_l2_persist_limit(self.device.index, nbytes, C.byref(granted), C.byref(max_window)),
                        "mdr_l2_persist_limit")
@@ -222,7 +230,7 @@ class VecDemandResponseEnv:
         if granted.value == 0 or window == 0:
             self._l2_window = (0, 0, 1.0)
             return
-        self._l2_window = (self._arena.data_ptr(), window, min(1.0, granted.value / window))
+        self._l2_window = (target.data_ptr(), window, min(1.0, granted.value / window))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

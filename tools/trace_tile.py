@@ -48,6 +48,17 @@ for wi in (0, 3, 6):
     if np.isfinite(rel[wi, :, 9]).any():
         print("  ... within 'issued next+record': [tile start, ring slot of the next tile ready, next tile's copies issued]")
         print(rel[wi, :12][:, [0, 8, 9]])
+if np.isfinite(rel[0, 22, 6]):
+    print("per-env prologue of all warps (in-order claiming), warp 0, us since its start: "
+          "[start, loads back, calendar, draws + shuffles, outdoor temperature (sinpi), due logic, signal | all stores out]")
+    pr = t[0, 22, :7].astype(np.float64)
+    print(np.round((pr - pr[0]) / 1e3, 2))
+if np.isfinite(rel[0, 23, 5]):
+    print("own-tile refresh, warps 0 / 3 / 6, us since the refresh started: [start, table walk done, after barrier 1, "
+          "signal written (after barrier 2), rows landed, after barrier 3]")
+    for wi in (0, 3, 6):
+        rr = t[wi, 23, :6].astype(np.float64)
+        print(np.round((rr - t[0, 23, 0]) / 1e3, 2))
 print("prologue warp: per pass starting at tile it0: [wait for slot, start, end]")
 print(rel[7][:, [8, 0, 7]])
 
