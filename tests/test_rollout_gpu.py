@@ -23,12 +23,16 @@ def _env(seed=3, n_envs=64, n=50):
     return mdr_b200.VecDemandResponseEnv(cfg, pop, precision="fp32", seed=seed)
 
 
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_collector_matches_manual_stepping(use_graph):
+@pytest.mark.parametrize("use_graph,claimed", [(True, False), (False, False), (True, True)])
+def test_collector_matches_manual_stepping(use_graph, claimed):
+    """`claimed`: the collector's env runs the pipelined kernel with tiles claimed in order (one persistent CTA walks all
+    16 tiles: grid barrier, claim ring and workspace reuse inside a replayed CUDA graph); the twin keeps the strided lists."""
     import torch
     import mdr_b200
     torch.manual_seed(1)
     env, twin = _env(), _env()
+    if claimed:
+        env.set_launch_options(max_ctas=1)
     f = env.n_features
     actor = mdr_b200.ActorMLP(f, 2, [100, 100]).cuda()   # agents/network.py:14-33
     col = mdr_b200.DeviceRolloutCollector(env, n_steps=12, seed=7, use_graph=use_graph)
