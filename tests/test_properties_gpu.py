@@ -95,6 +95,25 @@ def test_determinism_and_shard_independence():
                 assert torch.equal(a[e:e + 1], b), (t, e)
 
 
+@pytest.mark.parametrize("window", ["table", True])
+def test_l2_residency_window_changes_nothing(window):
+    """The optional persisting-L2 access-policy window (over the interpolation table, or over the state arena) is a
+    cache hint: identical bits with and without it."""
+    import torch
+    _, _, _, a = _make(600, 100, True, seed=11)
+    _, _, _, b = _make(600, 100, True, seed=11, l2_persist=window)
+    for x in (a, b):
+        x.reset_tensor()
+        x.stagger_interp_clock(seed=4)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for t in range(80):
+        act = (torch.rand(600, 100, device="cuda", generator=g) < 0.5).to(torch.uint8)
+        oa, ob = a.step_tensor(act), b.step_tensor(act)
+        for x, y in zip(oa, ob):
+            assert torch.equal(x, y), t
+    assert torch.equal(a.temps, b.temps) and torch.equal(a.env["base_power"], b.env["base_power"])
+
+
 def test_on_device_bangbang_million_houses():
     """c3 shape: 1000 envs x 1000 houses, on-device bang-bang, no observation written."""
     import torch
